@@ -1,0 +1,366 @@
+// g2048_device.cuh -- device-side core of the 2048 environment for sm_100a.
+//
+// Board packing: one uint64 per board, cell (r,c) = nibble 4*(4r+c) holding the
+// tile exponent (0 = empty).  Kept as two 32-bit halves in registers: `lo` =
+// rows 0,1 and `hi` = rows 2,3, because every operation below is 32-bit SASS
+// (LOP3 / SHF / PRMT / VABSDIFF4) anyway.
+//
+// Reference semantics (file:line in the reference checkout):
+//   row slide+merge          game.py:224-257      -> row table (see lut_entry_for_row)
+//   simulate_move            game.py:121-160      -> move_canonical()
+//   legality / terminal      game.py:103-119,259-330 -> legal_mask()
+//   potentials               game.py:339-399,671-800 -> potentials()
+//   spawn                    game.py:923-940      -> spawn_tile()
+//   step                     game.py:952-1030     -> env_step()
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace g2048 {
+
+// ------------------------------------------------------------------ row table
+// One u32 per 16-bit row (cell 0 in the low nibble), describing a LEFT move of
+// that row and its per-line potentials:
+//   [15:0]  result row (a merge that would create exponent 16 saturates at 15)
+//   [19:16] c1 = (exponent created by the first merge) - 1, 0 = no merge
+//   [23:20] c2 = same for the second merge
+//   [25:24] ge = #adjacent pairs, both non-zero, left >= right   (game.py:714-719)
+//   [27:26] le = #adjacent pairs, both non-zero, left <= right
+//   [31:28] max exponent in the row
+// 65536 entries = 256 KiB in global memory (L2 resident).  Kernels that are
+// throughput-bound on it stage the first LUT_SMEM_ROWS entries (224 KiB, every
+// row whose cell 3 is below exponent 14) in shared memory and read the rare
+// remaining rows through L2.
+constexpr int LUT_ROWS = 65536;
+constexpr int LUT_SMEM_ROWS = 0xE000;
+constexpr int LUT_BYTES = LUT_ROWS * 4;
+constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
+
+__host__ __device__ inline uint32_t lut_entry_for_row(uint32_t row) {
+    int c[4] = {int(row & 15), int((row >> 4) & 15), int((row >> 8) & 15), int((row >> 12) & 15)};
+    int nz[4], n = 0;
+    for (int i = 0; i < 4; ++i)
+        if (c[i]) nz[n++] = c[i];
+    int out[4] = {0, 0, 0, 0}, m = 0, code[2] = {0, 0}, nm = 0;
+    for (int i = 0; i < n;) {
+        if (i + 1 < n && nz[i] == nz[i + 1]) {
+            int ne = nz[i] + 1;
+            out[m++] = ne > 15 ? 15 : ne;
+            code[nm++] = ne - 1;
+            i += 2;
+        } else {
+            out[m++] = nz[i];
+            i += 1;
+        }
+    }
+    int ge = 0, le = 0, mx = 0;
+    for (int i = 0; i < 3; ++i)
+        if (c[i] && c[i + 1]) {
+            ge += c[i] >= c[i + 1];
+            le += c[i] <= c[i + 1];
+        }
+    for (int i = 0; i < 4; ++i) mx = c[i] > mx ? c[i] : mx;
+    return uint32_t(out[0]) | uint32_t(out[1]) << 4 | uint32_t(out[2]) << 8 | uint32_t(out[3]) << 12 |
+           uint32_t(code[0]) << 16 | uint32_t(code[1]) << 20 | uint32_t(ge) << 24 | uint32_t(le) << 26 |
+           uint32_t(mx) << 28;
+}
+
+// Row-table readers.  LutShared: staged copy + L2 for the tail; LutGlobal: L2 only
+// (used where shared memory belongs to something else, e.g. the rollout kernel).
+struct LutShared {
+    const uint32_t* s;
+    const uint32_t* g;
+    __device__ __forceinline__ uint32_t operator()(uint32_t row) const {
+        return row < uint32_t(LUT_SMEM_ROWS) ? s[row] : __ldg(g + row);
+    }
+};
+struct LutGlobal {
+    const uint32_t* g;
+    __device__ __forceinline__ uint32_t operator()(uint32_t row) const { return __ldg(g + row); }
+};
+
+// ------------------------------------------------------------------ board ops
+struct Board {
+    uint32_t lo, hi;
+};
+
+__device__ __forceinline__ Board make_board(uint64_t b) { return {uint32_t(b), uint32_t(b >> 32)}; }
+__device__ __forceinline__ uint64_t pack_board(Board b) { return uint64_t(b.lo) | uint64_t(b.hi) << 32; }
+__device__ __forceinline__ bool same(Board a, Board b) { return ((a.lo ^ b.lo) | (a.hi ^ b.hi)) == 0; }
+
+// 4x4 nibble transpose: 2x2 nibble blocks inside each half, then 2x2 blocks of bytes.
+__device__ __forceinline__ Board transpose(Board b) {
+    uint32_t a0 = (b.lo & 0xF0F00F0Fu) | ((b.lo & 0x0000F0F0u) << 12) | ((b.lo & 0x0F0F0000u) >> 12);
+    uint32_t a1 = (b.hi & 0xF0F00F0Fu) | ((b.hi & 0x0000F0F0u) << 12) | ((b.hi & 0x0F0F0000u) >> 12);
+    return {__byte_perm(a0, a1, 0x6240), __byte_perm(a0, a1, 0x7351)};
+}
+
+// reverse the four nibbles of every 16-bit row
+__device__ __forceinline__ uint32_t rev_rows32(uint32_t x) {
+    uint32_t y = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+    return __byte_perm(y, 0, 0x2301);
+}
+__device__ __forceinline__ Board rev_rows(Board b) { return {rev_rows32(b.lo), rev_rows32(b.hi)}; }
+
+// bit 4i set <=> nibble i is non-zero
+__device__ __forceinline__ uint32_t nz_flags32(uint32_t x) {
+    uint32_t y = x | (x >> 1);
+    return (y | (y >> 2)) & 0x11111111u;
+}
+// bit 4i set <=> nibble i is zero
+__device__ __forceinline__ uint32_t z_flags32(uint32_t x) { return nz_flags32(x) ^ 0x11111111u; }
+
+__device__ __forceinline__ uint32_t row_of(Board b, int r) {
+    uint32_t w = r < 2 ? b.lo : b.hi;
+    return (r & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
+// The four line entries of a board (its rows, in order).
+struct Lines {
+    uint32_t e0, e1, e2, e3;
+};
+template <class Lut>
+__device__ __forceinline__ Lines lookup_rows(Board b, const Lut& lut) {
+    return {lut(b.lo & 0xFFFFu), lut(b.lo >> 16), lut(b.hi & 0xFFFFu), lut(b.hi >> 16)};
+}
+__device__ __forceinline__ Board result_of(Lines l) {
+    return {__byte_perm(l.e0, l.e1, 0x5410), __byte_perm(l.e2, l.e3, 0x5410)};
+}
+// byte k of the result = byte `which` of line k
+__device__ __forceinline__ uint32_t gather_byte2(Lines l) {
+    return __byte_perm(__byte_perm(l.e0, l.e1, 0x0062), __byte_perm(l.e2, l.e3, 0x0062), 0x5410);
+}
+__device__ __forceinline__ uint32_t gather_byte3(Lines l) {
+    return __byte_perm(__byte_perm(l.e0, l.e1, 0x0073), __byte_perm(l.e2, l.e3, 0x0073), 0x5410);
+}
+
+// merge points / largest exponent created / overflow of one move, from the 4 moved lines
+__device__ __forceinline__ void merge_stats(Lines l, int& points, int& max_tile, bool& overflow) {
+    uint32_t w = gather_byte2(l);  // per line: [c2 | c1]
+    uint32_t lo4 = w & 0x0F0F0F0Fu, hi4 = (w >> 4) & 0x0F0F0F0Fu;
+    uint32_t sum = 0, any = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t a = 1u << ((lo4 >> (8 * k)) & 0xFFu);
+        uint32_t b = 1u << ((hi4 >> (8 * k)) & 0xFFu);
+        sum += (a & ~1u) + (b & ~1u);
+        any |= a | b;
+    }
+    points = int(sum << 1);                       // sum of 2^(c+1) over merges (game.py:237)
+    max_tile = any > 1u ? 32 - __clz(any) : 0;    // max (c+1) (game.py:238)
+    overflow = (any >> 15) & 1u;                  // a merge created exponent 16
+}
+
+// ------------------------------------------------------------------ legality
+// bit d set <=> direction d (0=UP 1=DOWN 2=LEFT 3=RIGHT) changes the board, i.e.
+// can-slide or can-merge (game.py:116-119).  Slide toward a side <=> some empty cell
+// has a tile as its immediate neighbour on the far side; merge <=> equal adjacent tiles.
+__device__ __forceinline__ uint32_t legal_mask(Board b) {
+    uint32_t nzl = nz_flags32(b.lo), nzh = nz_flags32(b.hi);
+    uint32_t el = nzl ^ 0x11111111u, eh = nzh ^ 0x11111111u;
+    // horizontal neighbours (c, c+1), c = 0..2
+    uint32_t dl = b.lo ^ (b.lo >> 4), dh = b.hi ^ (b.hi >> 4);
+    uint32_t mh = ((z_flags32(dl) & nzl) | (z_flags32(dh) & nzh)) & 0x01110111u;
+    // vertical neighbours (r, r+1), r = 0..2
+    uint32_t lo16 = __funnelshift_r(b.lo, b.hi, 16);
+    uint32_t vl = b.lo ^ lo16, vh = b.hi ^ (b.hi >> 16);
+    uint32_t mv = (z_flags32(vl) & nzl) | (z_flags32(vh) & nzh & 0x00001111u);
+    uint32_t left = ((el & (nzl >> 4)) | (eh & (nzh >> 4))) & 0x01110111u;
+    uint32_t right = ((el & (nzl << 4)) | (eh & (nzh << 4))) & 0x11101110u;
+    uint32_t nz16 = __funnelshift_r(nzl, nzh, 16);
+    uint32_t up = (el & nz16) | (eh & (nzh >> 16));
+    uint32_t down = (eh & nz16) | (el & (nzl << 16));
+    uint32_t m = 0;
+    if (up | mv) m |= 1u;
+    if (down | mv) m |= 2u;
+    if (left | mh) m |= 4u;
+    if (right | mh) m |= 8u;
+    return m;
+}
+
+// ------------------------------------------------------------------ potentials
+struct Potentials {
+    int mono;       // game.py:683-800
+    int empt;       // game.py:671-680
+    int smooth_abs; // -smoothness_score (game.py:339-357), 0..360
+    int max_exp;    // game.py:989
+    int in_corner;  // 1 if ANY max tile sits in a corner (game.py:386-399)
+};
+
+// sum over the 4 lines of the 2-bit ge / le fields (entry bits 24-25 / 26-27)
+__device__ __forceinline__ void ge_le_sums(Lines l, uint32_t& ge, uint32_t& le) {
+    uint32_t w = gather_byte3(l);
+    ge = __vsadu4(w & 0x03030303u, 0u);
+    le = __vsadu4((w >> 2) & 0x03030303u, 0u);
+}
+
+// -smoothness: sum of |a-b| over the 24 neighbour pairs with both cells non-zero.
+// Cells are spread into byte lanes (E = even columns, O = odd columns) so that the
+// native 4-way byte abs-diff applies; `nz*` are the nibble non-zero flags of the board.
+__device__ __forceinline__ int smoothness_abs(Board b, uint32_t nzl, uint32_t nzh) {
+    const uint32_t M = 0x0F0F0F0Fu;
+    uint32_t El = b.lo & M, Ol = (b.lo >> 4) & M, Eh = b.hi & M, Oh = (b.hi >> 4) & M;
+    // 0x0F in every byte lane whose cell is non-zero
+    uint32_t mEl = (nzl & 0x01010101u) * 15u, mOl = ((nzl >> 4) & 0x01010101u) * 15u;
+    uint32_t mEh = (nzh & 0x01010101u) * 15u, mOh = ((nzh >> 4) & 0x01010101u) * 15u;
+    // horizontal (c0,c1) and (c2,c3)
+    uint32_t acc = (__vabsdiffu4(El, Ol) & mEl & mOl) + (__vabsdiffu4(Eh, Oh) & mEh & mOh);
+    // horizontal (c1,c2): O byte k against E byte k+1, valid in byte lanes 0 and 2
+    acc += (__vabsdiffu4(Ol, El >> 8) & mOl & (mEl >> 8) & 0x000F000Fu) +
+           (__vabsdiffu4(Oh, Eh >> 8) & mOh & (mEh >> 8) & 0x000F000Fu);
+    // vertical: rows (0,1),(1,2) live in lo vs funnel(lo,hi); rows (2,3) in hi vs hi>>16
+    uint32_t Em = __funnelshift_r(El, Eh, 16), Om = __funnelshift_r(Ol, Oh, 16);
+    uint32_t mEm = __funnelshift_r(mEl, mEh, 16), mOm = __funnelshift_r(mOl, mOh, 16);
+    acc += (__vabsdiffu4(El, Em) & mEl & mEm) + (__vabsdiffu4(Ol, Om) & mOl & mOm);
+    acc += (__vabsdiffu4(Eh, Eh >> 16) & mEh & (mEh >> 16)) + (__vabsdiffu4(Oh, Oh >> 16) & mOh & (mOh >> 16));
+    return int(__vsadu4(acc, 0u));   // <= 8 terms of <= 15 per byte lane: no carry between lanes
+}
+
+// `rows`/`cols`: line entries of the board's rows and columns in ANY of the 8 board
+// symmetries (pair counts, max and smoothness are symmetry invariant); `b` itself must be
+// in the real frame because the first-max-in-row-major-order corner rule is not.
+__device__ __forceinline__ Potentials potentials(Board b, Lines rows, Lines cols) {
+    Potentials p;
+    uint32_t hge, hle, vge, vle;
+    ge_le_sums(rows, hge, hle);
+    ge_le_sums(cols, vge, vle);
+    int pairs = int(max(hge, hle) + max(vge, vle));   // == best of the four rotations
+    uint32_t mx = max(max(rows.e0, rows.e1), max(rows.e2, rows.e3)) >> 28;
+    uint32_t nzl = nz_flags32(b.lo), nzh = nz_flags32(b.hi);
+    p.empt = 16 - __popc(nzl) - __popc(nzh);
+    p.max_exp = int(mx);
+    uint32_t rep = mx * 0x11111111u;
+    uint32_t ql = z_flags32(b.lo ^ rep), qh = z_flags32(b.hi ^ rep);  // cells equal to the max
+    // first max in row-major order = lowest set flag; corners are cells 0,3 (lo) and 12,15 (hi)
+    bool first_corner = ql ? ((ql & (0u - ql)) & 0x00001001u) != 0u : ((qh & (0u - qh)) & 0x10010000u) != 0u;
+    p.mono = first_corner ? pairs * 2 : pairs / 2;    // game.py:755-758
+    p.in_corner = ((ql & 0x00001001u) | (qh & 0x10010000u)) != 0u;
+    p.smooth_abs = smoothness_abs(b, nzl, nzh);
+    return p;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10
+struct U4 {
+    uint32_t x, y, z, w;
+};
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c1 = l1;
+        c2 = h0 ^ c3 ^ k1;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return {c0, c1, c2, c3};
+}
+// counter = (env_id, ctr), key = seed: one call per env step
+__device__ __forceinline__ U4 env_draws(uint64_t seed, uint64_t env_id, uint64_t ctr) {
+    return philox4x32_10(uint32_t(env_id), uint32_t(env_id >> 32), uint32_t(ctr), uint32_t(ctr >> 32),
+                         uint32_t(seed), uint32_t(seed >> 32));
+}
+
+// ------------------------------------------------------------------ spawn
+// game.py:923-940.  k = mulhi(u0, #empty) picks the k-th empty cell in row-major order,
+// exponent 2 iff u1 >= 3865470567 (<=> not u1/2^32 < 0.9).  The board must have an empty
+// cell and at most 15 of them... (reset handles the empty board itself).
+__device__ __forceinline__ Board spawn_tile(Board b, uint32_t u0, uint32_t u1) {
+    uint32_t zl = z_flags32(b.lo), zh = z_flags32(b.hi);
+    uint32_t pl = zl * 0x11111111u;            // nibble i = #empty cells among nibbles 0..i (<= 8)
+    uint32_t nl = pl >> 28, n = nl + __popc(zh);
+    uint32_t k = __umulhi(u0, n);
+    bool in_lo = k < nl;
+    uint32_t z = in_lo ? zl : zh;
+    uint32_t p = in_lo ? pl : zh * 0x11111111u;
+    uint32_t t = in_lo ? k + 1u : k + 1u - nl;
+    uint32_t hit = z_flags32(p ^ (t * 0x11111111u)) & z;   // the empty nibble whose prefix count is t
+    uint32_t tile = (u1 >= 3865470567u ? 2u : 1u) << (__ffs(int(hit)) - 1);
+    if (n != 0u) {
+        if (in_lo) b.lo |= tile;
+        else b.hi |= tile;
+    }
+    return b;
+}
+
+// game.py:942-950 reset: two spawns on the empty board, draws (x,y) then (z,w)
+__device__ __forceinline__ Board reset_board(U4 d) {
+    uint32_t k1 = __umulhi(d.x, 16u);
+    uint32_t v1 = d.y >= 3865470567u ? 2u : 1u;
+    uint32_t k2 = __umulhi(d.z, 15u);
+    uint32_t v2 = d.w >= 3865470567u ? 2u : 1u;
+    k2 += k2 >= k1;
+    uint64_t b = uint64_t(v1) << (4 * k1) | uint64_t(v2) << (4 * k2);
+    return make_board(b);
+}
+
+// ------------------------------------------------------------------ move
+// Canonical frame: every move becomes a LEFT move of `canon`:
+//   LEFT: board, RIGHT: rows reversed, UP: transposed, DOWN: transposed then rows reversed.
+__device__ __forceinline__ Board to_canonical(Board b, Board bt, uint32_t action) {
+    Board c = (action & 2u) ? b : bt;             // 2,3 horizontal; 0,1 vertical
+    return (action & 1u) ? rev_rows(c) : c;       // DOWN / RIGHT reverse
+}
+__device__ __forceinline__ Board from_canonical(Board c, uint32_t action) {
+    if (action & 1u) c = rev_rows(c);
+    return (action & 2u) ? c : transpose(c);
+}
+
+// ------------------------------------------------------------------ step
+// Packed shaping record (one u64 per transition, all zero for an invalid move):
+//  lo: [5:0] mono_before [11:6] mono_after [16:12] empt_before [21:17] empt_after
+//      [26:22] max_tile_created [30:27] max_exp_before [31] max-in-corner before
+//  hi: [3:0] max_exp_after [4] max-in-corner after [13:5] -smooth_before [22:14] -smooth_after
+// "after" = after the move, before the spawn (game.py:994-1002).
+struct StepOut {
+    Board board;       // post-spawn (unchanged if invalid)
+    int points;
+    uint32_t flags;    // bits 0-3 legal mask of `board`, 4 done, 5 invalid, 6 overflow
+    uint32_t shape_lo, shape_hi;
+};
+
+constexpr uint32_t FLAG_DONE = 16u, FLAG_INVALID = 32u, FLAG_OVERFLOW = 64u;
+
+template <bool SHAPING, class Lut>
+__device__ __forceinline__ StepOut env_step(Board b, uint32_t action, uint32_t u0, uint32_t u1, const Lut& lut) {
+    StepOut o;
+    Board bt = transpose(b);
+    Board canon = to_canonical(b, bt, action);
+    Lines mv = lookup_rows(canon, lut);
+    Board moved_c = result_of(mv);
+    bool valid = !same(moved_c, canon);            // game.py:959 (legal <=> the move changes the board)
+    int points, max_tile;
+    bool ovf;
+    merge_stats(mv, points, max_tile, ovf);
+    Board moved = from_canonical(moved_c, action);
+    o.shape_lo = 0u;
+    o.shape_hi = 0u;
+    if (SHAPING) {
+        // before: lines along the move axis come from the move lookups themselves
+        Board cross = (action & 2u) ? bt : b;
+        Potentials pb = potentials(b, mv, lookup_rows(cross, lut));
+        Potentials pa = potentials(moved, lookup_rows(moved_c, lut), lookup_rows(transpose(moved_c), lut));
+        uint32_t lo = uint32_t(pb.mono) | uint32_t(pa.mono) << 6 | uint32_t(pb.empt) << 12 |
+                      uint32_t(pa.empt) << 17 | uint32_t(max_tile) << 22 | uint32_t(pb.max_exp) << 27 |
+                      uint32_t(pb.in_corner) << 31;
+        uint32_t hi = uint32_t(pa.max_exp) | uint32_t(pa.in_corner) << 4 | uint32_t(pb.smooth_abs) << 5 |
+                      uint32_t(pa.smooth_abs) << 14;
+        o.shape_lo = valid ? lo : 0u;
+        o.shape_hi = valid ? hi : 0u;
+    }
+    Board spawned = spawn_tile(moved, u0, u1);     // game.py:1005
+    o.board = valid ? spawned : b;
+    o.points = valid ? points : 0;
+    uint32_t lm = legal_mask(o.board);             // game.py:1006 / 963
+    o.flags = lm | (lm == 0u ? FLAG_DONE : 0u) | (valid ? 0u : FLAG_INVALID) | ((valid && ovf) ? FLAG_OVERFLOW : 0u);
+    return o;
+}
+
+// ------------------------------------------------------------------ model input
+// game.py:92-101: 16 x [exponent, row/3, col/3]
+__device__ __forceinline__ float pos_feature(int i) { return float(i) / 3.0f; }
+
+}  // namespace g2048

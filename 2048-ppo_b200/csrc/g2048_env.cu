@@ -1,0 +1,298 @@
+// g2048_env.cu -- environment kernels (row table, reset, step, expand4, potentials, encode)
+// and their C-ABI entry points.  sm_100a only.
+//
+// Throughput kernels (step / expand4) are persistent: one CTA per SM, the row table staged
+// once per CTA into shared memory with bulk async copies (cp.async.bulk + mbarrier), then a
+// grid-stride loop with fully coalesced 8-byte board loads/stores.  They are HBM-/issue-bound
+// integer kernels; tensor cores are irrelevant here.
+#include "g2048_device.cuh"
+#include "g2048_host.h"
+
+namespace g2048 {
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Stage the first LUT_SMEM_ROWS table entries into shared memory (224 KiB, 7 bulk copies).
+__device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, uint64_t* bar) {
+    constexpr uint32_t CHUNK = 32768;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, LUT_SMEM_BYTES);
+#pragma unroll
+        for (uint32_t off = 0; off < uint32_t(LUT_SMEM_BYTES); off += CHUNK)
+            bulk_copy_g2s(reinterpret_cast<uint8_t*>(slut) + off, reinterpret_cast<const uint8_t*>(glut) + off, CHUNK, bar);
+    }
+    __syncthreads();          // barrier init visible to all waiters
+    mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void build_lut_kernel(uint32_t* lut) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < uint32_t(LUT_ROWS)) lut[row] = lut_entry_for_row(row);
+}
+
+__global__ void reset_kernel(uint64_t* boards, int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0,
+                             uint64_t ctr) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    U4 d;
+    if (replay) {
+        uint4 r = reinterpret_cast<const uint4*>(replay)[i];
+        d = {r.x, r.y, r.z, r.w};
+    } else {
+        d = env_draws(seed, env0 + uint64_t(i), ctr);
+    }
+    boards[i] = pack_board(reset_board(d));
+}
+
+constexpr int STEP_THREADS = 1024;
+
+template <bool SHAPING, class Lut>
+__device__ __forceinline__ void step_loop(const Lut& lut, const uint64_t* __restrict__ in,
+                                          const uint8_t* __restrict__ actions, uint64_t* __restrict__ out,
+                                          int32_t* __restrict__ points, uint8_t* __restrict__ flags,
+                                          uint64_t* __restrict__ shaping, int64_t n,
+                                          const uint32_t* __restrict__ replay, uint64_t seed, uint64_t env0,
+                                          uint64_t ctr) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Board b = make_board(__ldg(in + i));
+        uint32_t a = __ldg(actions + i) & 3u;
+        uint32_t u0, u1;
+        if (replay) {
+            uint2 r = __ldg(reinterpret_cast<const uint2*>(replay) + i);
+            u0 = r.x;
+            u1 = r.y;
+        } else {
+            U4 d = env_draws(seed, env0 + uint64_t(i), ctr);
+            u0 = d.x;
+            u1 = d.y;
+        }
+        StepOut o = env_step<SHAPING>(b, a, u0, u1, lut);
+        out[i] = pack_board(o.board);
+        points[i] = o.points;
+        flags[i] = uint8_t(o.flags);
+        if (SHAPING) shaping[i] = uint64_t(o.shape_lo) | uint64_t(o.shape_hi) << 32;
+    }
+}
+
+template <bool SHAPING>
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+step_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
+                   int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
+                   uint64_t seed, uint64_t env0, uint64_t ctr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
+    stage_lut(slut, glut, &bar);
+    step_loop<SHAPING>(LutShared{slut, glut}, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
+}
+
+template <bool SHAPING>
+__global__ void __launch_bounds__(256)
+step_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
+                   int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
+                   uint64_t seed, uint64_t env0, uint64_t ctr) {
+    step_loop<SHAPING>(LutGlobal{glut}, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
+}
+
+template <class Lut>
+__device__ __forceinline__ void expand4_loop(const Lut& lut, const uint64_t* __restrict__ boards,
+                                             uint64_t* __restrict__ succ, int32_t* __restrict__ points,
+                                             uint8_t* __restrict__ legal, uint8_t* __restrict__ max_tile, int64_t n) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Board b = make_board(__ldg(boards + i));
+        Board bt = transpose(b);
+        Lines lu = lookup_rows(bt, lut);              // UP    = left move of the columns
+        Lines ld = lookup_rows(rev_rows(bt), lut);    // DOWN  = right move of the columns
+        Lines ll = lookup_rows(b, lut);               // LEFT
+        Lines lr = lookup_rows(rev_rows(b), lut);     // RIGHT
+        Board s[4] = {transpose(result_of(lu)), transpose(rev_rows(result_of(ld))), result_of(ll),
+                      rev_rows(result_of(lr))};
+        int p[4], mt[4];
+        bool ovf;
+        merge_stats(lu, p[0], mt[0], ovf);
+        merge_stats(ld, p[1], mt[1], ovf);
+        merge_stats(ll, p[2], mt[2], ovf);
+        merge_stats(lr, p[3], mt[3], ovf);
+        uint32_t lm = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) lm |= same(s[d], b) ? 0u : (1u << d);
+        // 4 successors = 32 contiguous bytes per board, 16 bytes of points
+        uint4* so = reinterpret_cast<uint4*>(succ + 4 * i);
+        so[0] = make_uint4(s[0].lo, s[0].hi, s[1].lo, s[1].hi);
+        so[1] = make_uint4(s[2].lo, s[2].hi, s[3].lo, s[3].hi);
+        *reinterpret_cast<int4*>(points + 4 * i) = make_int4(p[0], p[1], p[2], p[3]);
+        legal[i] = uint8_t(lm);
+        if (max_tile)
+            *reinterpret_cast<uint32_t*>(max_tile + 4 * i) =
+                uint32_t(mt[0]) | uint32_t(mt[1]) << 8 | uint32_t(mt[2]) << 16 | uint32_t(mt[3]) << 24;
+    }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+expand4_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* boards, uint64_t* succ, int32_t* points,
+                      uint8_t* legal, uint8_t* max_tile, int64_t n) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
+    stage_lut(slut, glut, &bar);
+    expand4_loop(LutShared{slut, glut}, boards, succ, points, legal, max_tile, n);
+}
+
+__global__ void __launch_bounds__(256)
+expand4_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* boards, uint64_t* succ, int32_t* points,
+                      uint8_t* legal, uint8_t* max_tile, int64_t n) {
+    expand4_loop(LutGlobal{glut}, boards, succ, points, legal, max_tile, n);
+}
+
+__global__ void __launch_bounds__(256)
+potentials_kernel(const uint32_t* __restrict__ glut, const uint64_t* __restrict__ boards, int32_t* __restrict__ out,
+                  int64_t n) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    LutGlobal lut{glut};
+    Board b = make_board(boards[i]);
+    Potentials p = potentials(b, lookup_rows(b, lut), lookup_rows(transpose(b), lut));
+    int32_t* o = out + 6 * i;
+    o[0] = p.mono;
+    o[1] = p.empt;
+    o[2] = -p.smooth_abs;
+    o[3] = p.in_corner ? p.max_exp : -p.max_exp;
+    o[4] = p.max_exp;
+    o[5] = int32_t(legal_mask(b));
+}
+
+// one thread per (board, cell): coalesced 12-byte-per-thread stores of [exp, row/3, col/3]
+__global__ void __launch_bounds__(256) encode_kernel(const uint64_t* __restrict__ boards, float* __restrict__ out, int64_t n) {
+    int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * 16) return;
+    int64_t i = t >> 4;
+    int cell = int(t & 15);
+    uint64_t b = __ldg(boards + i);
+    float* o = out + 3 * t;
+    o[0] = float((b >> (4 * cell)) & 15u);
+    o[1] = pos_feature(cell >> 2);
+    o[2] = pos_feature(cell & 3);
+}
+
+// below this many units the 224 KiB table staging (per CTA) costs more than it saves
+constexpr int64_t STAGED_MIN_UNITS = 1 << 17;
+
+}  // namespace g2048
+
+using namespace g2048;
+
+extern "C" {
+
+int64_t g2048_lut_bytes(void) { return LUT_BYTES; }
+
+int g2048_build_lut(void* d_lut, void* stream) {
+    G2048_REQUIRE(d_lut != nullptr, "g2048_build_lut: d_lut is NULL");
+    build_lut_kernel<<<LUT_ROWS / 256, 256, 0, cudaStream_t(stream)>>>(static_cast<uint32_t*>(d_lut));
+    G2048_CHECK_LAUNCH("build_lut_kernel");
+    return G2048_OK;
+}
+
+int g2048_reset(uint64_t* boards, int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0, uint64_t ctr,
+                void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_reset: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(boards != nullptr, "g2048_reset: boards is NULL");
+    reset_kernel<<<unsigned((n + 255) / 256), 256, 0, cudaStream_t(stream)>>>(boards, n, replay, seed, env0, ctr);
+    G2048_CHECK_LAUNCH("reset_kernel");
+    return G2048_OK;
+}
+
+int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* actions, uint64_t* boards_out,
+               int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay, uint64_t seed,
+               uint64_t env0, uint64_t ctr, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_step: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_lut && boards_in && actions && boards_out && points && flags, "g2048_step: NULL pointer argument");
+    const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
+    cudaStream_t st = cudaStream_t(stream);
+    if (n >= STAGED_MIN_UNITS) {
+        auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;
+        G2048_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        kern<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,
+                                                              shaping, n, replay, seed, env0, ctr);
+        G2048_CHECK_LAUNCH("step_kernel_staged");
+    } else {
+        auto kern = shaping ? step_kernel_direct<true> : step_kernel_direct<false>;
+        kern<<<unsigned((n + 255) / 256), 256, 0, st>>>(lut, boards_in, actions, boards_out, points, flags, shaping, n,
+                                                        replay, seed, env0, ctr);
+        G2048_CHECK_LAUNCH("step_kernel_direct");
+    }
+    return G2048_OK;
+}
+
+int g2048_expand4(const void* d_lut, const uint64_t* boards, uint64_t* succ, int32_t* points, uint8_t* legal,
+                  uint8_t* max_tile, int64_t n, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_expand4: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_lut && boards && succ && points && legal, "g2048_expand4: NULL pointer argument");
+    const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
+    cudaStream_t st = cudaStream_t(stream);
+    if (n >= STAGED_MIN_UNITS) {
+        G2048_CHECK_CUDA(cudaFuncSetAttribute(expand4_kernel_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              LUT_SMEM_BYTES));
+        expand4_kernel_staged<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards, succ, points, legal,
+                                                                               max_tile, n);
+        G2048_CHECK_LAUNCH("expand4_kernel_staged");
+    } else {
+        expand4_kernel_direct<<<unsigned((n + 255) / 256), 256, 0, st>>>(lut, boards, succ, points, legal, max_tile, n);
+        G2048_CHECK_LAUNCH("expand4_kernel_direct");
+    }
+    return G2048_OK;
+}
+
+int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, int64_t n, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_potentials: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_lut && boards && out, "g2048_potentials: NULL pointer argument");
+    potentials_kernel<<<unsigned((n + 255) / 256), 256, 0, cudaStream_t(stream)>>>(static_cast<const uint32_t*>(d_lut),
+                                                                                  boards, out, n);
+    G2048_CHECK_LAUNCH("potentials_kernel");
+    return G2048_OK;
+}
+
+int g2048_encode(const uint64_t* boards, float* out, int64_t n, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_encode: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(boards && out, "g2048_encode: NULL pointer argument");
+    int64_t threads = n * 16;
+    encode_kernel<<<unsigned((threads + 255) / 256), 256, 0, cudaStream_t(stream)>>>(boards, out, n);
+    G2048_CHECK_LAUNCH("encode_kernel");
+    return G2048_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+"""Batched 2048 environment on the GPU + a drop-in facade for the reference's game.py API.
+
+Reference interfaces mirrored here (file:line in RobotSail/2048-PPO):
+  Direction                         game.py:14-18
+  Game2048.reset/step/...           game.py:45-1030 (see the method docstrings)
+Boards are int64 CUDA tensors holding the uint64 bit pattern described in include/g2048.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from enum import Enum
+
+import numpy as np
+import torch
+
+from . import _lib
+
+UP, DOWN, LEFT, RIGHT = 0, 1, 2, 3
+
+FLAG_LEGAL_MASK, FLAG_DONE, FLAG_INVALID, FLAG_OVERFLOW = 0x0F, 0x10, 0x20, 0x40
+
+
+class Direction(Enum):  # game.py:14-18
+    UP = "up"
+    DOWN = "down"
+    LEFT = "left"
+    RIGHT = "right"
+
+
+DIRECTIONS = [Direction.UP, Direction.DOWN, Direction.LEFT, Direction.RIGHT]  # train.py:266 order
+_DIR_INDEX = {d: i for i, d in enumerate(DIRECTIONS)}
+
+
+def direction_index(d) -> int:
+    if isinstance(d, int):
+        return d
+    if isinstance(d, Direction):
+        return _DIR_INDEX[d]
+    return _DIR_INDEX[Direction(getattr(d, "value", d))]  # the reference's own enum members
+
+
+# ----------------------------------------------------------------------------- plumbing
+
+def _ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+_LUTS: dict[int, torch.Tensor] = {}
+_INITED: set[int] = set()
+
+
+def init(device: torch.device | int | None = None) -> torch.device:
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("g2048 runs on CUDA devices only")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _INITED:
+        _lib.call("g2048_init", idx)
+        _INITED.add(idx)
+    return torch.device("cuda", idx)
+
+
+def lut(device=None) -> torch.Tensor:
+    """The 256 KiB row table of `device`, built on first use by g2048_build_lut."""
+    dev = init(device)
+    if dev.index not in _LUTS:
+        with torch.cuda.device(dev):
+            t = torch.empty(int(_lib.lib().g2048_lut_bytes()), dtype=torch.uint8, device=dev)
+            _lib.call("g2048_build_lut", _ptr(t), _stream())
+        _LUTS[dev.index] = t
+    return _LUTS[dev.index]
+
+
+# ----------------------------------------------------------------------------- batched API
+
+def reset(n: int, *, device=None, seed: int = 0, env0: int = 0, ctr: int = 0,
+          replay: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """game.py:942-950 for n boards.  replay: uint32-as-int32 [n,4] draws or None (Philox)."""
+    dev = init(device if out is None else out.device)
+    with torch.cuda.device(dev):
+        boards = torch.empty(n, dtype=torch.int64, device=dev) if out is None else _req(out, torch.int64, "out")
+        if replay is not None:
+            replay = _req(replay, torch.int32, "replay")
+            assert replay.numel() == 4 * n
+        _lib.call("g2048_reset", _ptr(boards), n, _ptr(replay), seed, env0, ctr, _stream())
+    return boards
+
+
+def step(boards: torch.Tensor, actions: torch.Tensor, *, seed: int = 0, env0: int = 0, ctr: int = 0,
+         replay: torch.Tensor | None = None, shaping: bool = True, out: dict | None = None) -> dict:
+    """game.py:952-1030 for every (board, action) pair.
+
+    Returns dict(boards int64[n], points int32[n], flags uint8[n], shaping int64[n] | None).
+    """
+    boards = _req(boards, torch.int64, "boards")
+    actions = _req(actions, torch.uint8, "actions")
+    n = boards.numel()
+    assert actions.numel() == n
+    dev = init(boards.device)
+    with torch.cuda.device(dev):
+        table = lut(dev)
+        if out is None:
+            out = dict(boards=torch.empty_like(boards), points=torch.empty(n, dtype=torch.int32, device=dev),
+                       flags=torch.empty(n, dtype=torch.uint8, device=dev),
+                       shaping=torch.empty(n, dtype=torch.int64, device=dev) if shaping else None)
+        if replay is not None:
+            replay = _req(replay, torch.int32, "replay")
+            assert replay.numel() == 2 * n
+        _lib.call("g2048_step", _ptr(table), _ptr(boards), _ptr(actions), _ptr(out["boards"]), _ptr(out["points"]),
+                  _ptr(out["flags"]), _ptr(out.get("shaping")), n, _ptr(replay), seed, env0, ctr, _stream())
+    return out
+
+
+def expand4(boards: torch.Tensor, *, want_max_tile: bool = False, out: dict | None = None) -> dict:
+    """All four pre-spawn successors (game.py:121-184, 295-299)."""
+    boards = _req(boards, torch.int64, "boards")
+    n = boards.numel()
+    dev = init(boards.device)
+    with torch.cuda.device(dev):
+        table = lut(dev)
+        if out is None:
+            out = dict(succ=torch.empty((n, 4), dtype=torch.int64, device=dev),
+                       points=torch.empty((n, 4), dtype=torch.int32, device=dev),
+                       legal=torch.empty(n, dtype=torch.uint8, device=dev),
+                       max_tile=torch.empty((n, 4), dtype=torch.uint8, device=dev) if want_max_tile else None)
+        _lib.call("g2048_expand4", _ptr(table), _ptr(boards), _ptr(out["succ"]), _ptr(out["points"]),
+                  _ptr(out["legal"]), _ptr(out.get("max_tile")), n, _stream())
+    return out
+
+
+def potentials(boards: torch.Tensor) -> torch.Tensor:
+    """int32 [n,6]: monotonicity, emptiness, smoothness, corner bonus, max exponent, legal mask."""
+    boards = _req(boards, torch.int64, "boards")
+    dev = init(boards.device)
+    with torch.cuda.device(dev):
+        out = torch.empty((boards.numel(), 6), dtype=torch.int32, device=dev)
+        _lib.call("g2048_potentials", _ptr(lut(dev)), _ptr(boards), _ptr(out), boards.numel(), _stream())
+    return out
+
+
+def encode(boards: torch.Tensor) -> torch.Tensor:
+    """game.py:92-101 to_model_format for a batch: float32 [n,48]."""
+    boards = _req(boards, torch.int64, "boards")
+    dev = init(boards.device)
+    with torch.cuda.device(dev):
+        out = torch.empty((boards.numel(), 48), dtype=torch.float32, device=dev)
+        _lib.call("g2048_encode", _ptr(boards), _ptr(out), boards.numel(), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- host helpers
+
+def pack_grid(grid) -> int:
+    """list[list[int]] exponents -> signed int64 bit pattern of the packed board."""
+    b = 0
+    for r in range(4):
+        for c in range(4):
+            e = int(grid[r][c])
+            if not 0 <= e <= 15:
+                raise ValueError(f"exponent {e} at ({r},{c}) does not fit the 4-bit board packing (valid: 0..15)")
+            b |= e << (4 * (4 * r + c))
+    return b - (1 << 64) if b >= (1 << 63) else b
+
+
+def unpack_board(b: int) -> list[list[int]]:
+    b = int(b) & ((1 << 64) - 1)
+    return [[(b >> (4 * (4 * r + c))) & 0xF for c in range(4)] for r in range(4)]
+
+
+def decode_shaping(w) -> dict:
+    """Unpack the u64 shaping records (include/g2048.h G2048_SH_*) into int arrays."""
+    w = np.asarray(w).astype(np.int64).view(np.uint64)
+    f = lambda sh, m: ((w >> np.uint64(sh)) & np.uint64(m)).astype(np.int32)
+    mb, ma = f(27, 15), f(32, 15)
+    cb = np.where(f(31, 1) == 1, mb, -mb)
+    ca = np.where(f(36, 1) == 1, ma, -ma)
+    return dict(mono_before=f(0, 63), mono_after=f(6, 63), empt_before=f(12, 31), empt_after=f(17, 31),
+                max_tile_created=f(22, 31), max_exp_before=mb, max_exp_after=ma, corner_before=cb,
+                corner_after=ca, smooth_before=-f(37, 511), smooth_after=-f(46, 511))
+
+
+# ----------------------------------------------------------------------------- facade
+
+class Game2048:
+    """Drop-in for the reference's Game2048 (game.py:45-1030), one board, state on the GPU.
+
+    Every query is a kernel call through the C ABI; this class only converts between the
+    reference's Grid (list[list[int]]) and the packed board.  Spawns come from the
+    counter-based Philox stream (seed, env_id, move counter) instead of Python's `random`.
+    """
+
+    def __init__(self, state=None, *, device=None, seed: int = 0, env_id: int = 0):
+        self.device = init(device)
+        self.seed, self.env_id, self._ctr = seed, env_id, 0
+        if state:
+            if not all(int(s) in range(0, 16) for row in state for s in row):   # game.py:58-60 (nibble: <= 15)
+                raise AssertionError("exponents must be in 0..15")
+            self._b = torch.tensor([pack_grid(state)], dtype=torch.int64, device=self.device)
+        else:
+            self._b = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    # -- state
+    @property
+    def grid(self):
+        return unpack_board(self._b.item())
+
+    @grid.setter
+    def grid(self, g):
+        self._b = torch.tensor([pack_grid(g)], dtype=torch.int64, device=self.device)
+
+    def score(self) -> int:  # game.py:63-64
+        return sum(2 ** k for row in self.grid for k in row if k > 0)
+
+    get_score = score
+
+    def _pot(self):
+        return potentials(self._b)[0].tolist()
+
+    # -- legality (game.py:103-119, 295-299)
+    def _legal(self) -> int:
+        return self._pot()[5]
+
+    def has_next_step(self) -> bool:
+        return self._legal() != 0
+
+    def direction_has_step(self, direction) -> bool:
+        return bool((self._legal() >> direction_index(direction)) & 1)
+
+    def current_valid_directions(self):
+        m = self._legal()
+        return [d for i, d in enumerate(DIRECTIONS) if (m >> i) & 1]
+
+    # -- moves
+    @staticmethod
+    def simulate_move(grid, direction, *, device=None):  # game.py:121-160
+        dev = init(device)
+        b = torch.tensor([pack_grid(grid)], dtype=torch.int64, device=dev)
+        r = expand4(b, want_max_tile=True)
+        d = direction_index(direction)
+        return unpack_board(r["succ"][0, d].item()), int(r["points"][0, d]), int(r["max_tile"][0, d])
+
+    def preview_move_rewards(self):  # game.py:167-184
+        r = expand4(self._b)
+        pts = r["points"][0].tolist()
+        return {d: int(pts[i]) for i, d in enumerate(DIRECTIONS)}
+
+    def move(self, direction):  # game.py:186-216
+        if not self.direction_has_step(direction):
+            raise ValueError(f"Cannot move in direction {getattr(direction, 'value', direction)}")
+        r = expand4(self._b)
+        self._b = r["succ"][0, direction_index(direction)].reshape(1).clone()
+        return self.grid
+
+    def to_model_format(self) -> torch.Tensor:  # game.py:92-101
+        return encode(self._b)[0]
+
+    def reset(self):  # game.py:942-950
+        self._ctr = 0
+        self._b = reset(1, device=self.device, seed=self.seed, env0=self.env_id, ctr=0)
+        self._ctr = 1
+        return self.grid
+
+    def step(self, direction):  # game.py:952-1030
+        a = torch.tensor([direction_index(direction)], dtype=torch.uint8, device=self.device)
+        r = step(self._b, a, seed=self.seed, env0=self.env_id, ctr=self._ctr, shaping=True)
+        flags = int(r["flags"].item())
+        if flags & FLAG_OVERFLOW:
+            raise OverflowError("a merge produced exponent 16, which the 4-bit board packing cannot represent")
+        self._b = r["boards"]
+        done = bool(flags & FLAG_DONE)
+        if flags & FLAG_INVALID:  # game.py:959-978
+            info = {"invalid_move": True, "smoothness_delta": 0.0, "max_tile_created": 0, "corner_delta": 0.0,
+                    "adjacency_delta": 0.0, "chain_delta": 0.0, "monotonicity_before": 0.0,
+                    "monotonicity_after": 0.0, "topological_delta": 0.0, "emptiness_before": 0.0,
+                    "emptiness_after": 0.0}
+            return self.grid, 0, done, info
+        self._ctr += 1
+        s = {k: int(v[0]) for k, v in decode_shaping(r["shaping"].cpu().numpy()).items()}
+        info = {  # game.py:1012-1029 (adjacency / chain / topological are out of scope: SURVEY section 8f N3)
+            "invalid_move": False,
+            "smoothness_delta": float(s["smooth_after"] - s["smooth_before"]),
+            "max_tile_created": s["max_tile_created"],
+            "max_exponent_before": s["max_exp_before"],
+            "max_exponent_after": s["max_exp_after"],
+            "corner_delta": float(s["corner_after"] - s["corner_before"]),
+            "monotonicity_before": s["mono_before"],
+            "monotonicity_after": s["mono_after"],
+            "emptiness_before": s["empt_before"],
+            "emptiness_after": s["empt_after"],
+        }
+        return self.grid, int(r["points"].item()), done, info
+
+    # -- potentials (static in the reference: game.py:339-399, 671-800)
+    @staticmethod
+    def _pot_of(grid, idx, device=None):
+        dev = init(device)
+        return int(potentials(torch.tensor([pack_grid(grid)], dtype=torch.int64, device=dev))[0, idx])
+
+    @staticmethod
+    def monotonicity(grid, require_corner_max: bool = False) -> int:
+        return Game2048._pot_of(grid, 0)
+
+    @staticmethod
+    def emptiness(grid) -> int:
+        return Game2048._pot_of(grid, 1)
+
+    @staticmethod
+    def smoothness_score(grid) -> float:
+        return float(Game2048._pot_of(grid, 2))
+
+    @staticmethod
+    def corner_bonus(grid) -> float:
+        return float(Game2048._pot_of(grid, 3))
+
+    @staticmethod
+    def state_has_next_step(state) -> bool:
+        return Game2048._pot_of(state, 5) != 0

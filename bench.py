@@ -1,0 +1,303 @@
+"""bench.py -- headline benchmark of the B200-native 2048-PPO hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of g2048_step over config C2 of BASELINE.json: 2^20 random boards x 4
+moves = 4,194,304 full Game2048.step transitions (move, merge points, shaping record, Philox
+spawn, legal mask / done) per GPU.  Prints ONE JSON line (see DESIGN.md "Measurement").
+
+  value     env-steps/s, inputs resident in HBM, CUDA-event timed on the launching stream
+  e2e       same metric through the public host API (g2048.env.step) with HOST pinned buffers,
+            host<->device copies inside the timed region
+  roofline  algorithmic bytes (30 B / transition) / measured kernel time vs the measured HBM peak
+  cpu_baseline  the C port of the reference (oracle/) on the host cores, bounded sample
+
+`--impl reference` times the reference's CPU algorithm (the oracle port; the reference itself is
+pure Python and does not travel to the GPU box) with all host threads on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "2048-ppo_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+N_BOARDS = 1 << 20
+MOVES = 4
+N_TRANS = N_BOARDS * MOVES
+BYTES_PER_TRANSITION = 30      # 8 board in + 1 action + 8 board out + 4 points + 1 flags + 8 shaping
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def c2_boards(seed: int) -> np.ndarray:
+    """SURVEY 8(d) C2 input: exponents 1..11, each cell emptied with probability 0.30."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randint(1, 12, (N_BOARDS, 16), generator=g, dtype=torch.int64)
+    e[torch.rand((N_BOARDS, 16), generator=g) < 0.30] = 0
+    sh = torch.arange(16, dtype=torch.int64) * 4
+    return (e << sh).sum(dim=1).numpy()
+
+
+def c2_transitions(seed: int):
+    """(boards int64[4M], actions uint8[4M]): transition d*2^20+i = board i, move d."""
+    b = c2_boards(seed)
+    boards = np.tile(b, MOVES)
+    actions = np.repeat(np.arange(MOVES, dtype=np.uint8), N_BOARDS)
+    return boards, actions
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_baseline(min_seconds: float = 10.0):
+    """C port of Game2048.step (oracle/) on all host threads, bounded sample of the C2 workload."""
+    from oracle import oracle as O
+    boards, actions = c2_transitions(2048)
+    n = 1 << 21
+    b, a = boards[:n].view(np.uint64), actions[:n]
+    # interleave the four moves so that the sample is representative
+    idx = (np.arange(n) % MOVES) * N_BOARDS + (np.arange(n) // MOVES)
+    b, a = np.ascontiguousarray(boards.view(np.uint64)[idx]), np.ascontiguousarray(actions[idx])
+    O.step_batch(b[:4096], a[:4096], seed=1, env0=0, ctr=1)
+    t0 = time.perf_counter()
+    done = 0
+    reps = 0
+    while time.perf_counter() - t0 < min_seconds:
+        O.step_batch(b, a, seed=1, env0=0, ctr=1 + reps)
+        done += n
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": f"{reps} x {n} C2 transitions ({dt:.1f} s) through oracle/oracle2048.c orc_step_batch (OpenMP)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    boards, actions = c2_transitions(2048)
+    n = 1 << 20   # bounded sample of the 4M-transition step
+    idx = (np.arange(n) % MOVES) * N_BOARDS + (np.arange(n) // MOVES)
+    b, a = np.ascontiguousarray(boards.view(np.uint64)[idx]), np.ascontiguousarray(actions[idx])
+    for w in range(args.warmup):
+        O.step_batch(b, a, seed=1, env0=0, ctr=w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        O.step_batch(b, a, seed=1, env0=0, ctr=100 + k)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = f"each step = {n} of the {N_TRANS} C2 transitions, oracle/oracle2048.c orc_step_batch, {O.num_threads()} OpenMP threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "c2_env_step: 2^20 boards x 4 moves, full Game2048.step", "sample_per_step": n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from g2048 import env
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    env.init(dev)
+    env.lut(dev)
+
+    # ring of buffer sets larger than L2 (126 MB): 6 x 120 MiB touched round-robin
+    RING = 6
+    sets = []
+    for s in range(RING):
+        b, a = c2_transitions(2048 + 97 * s + 1009 * rank)
+        sets.append(dict(
+            boards=torch.from_numpy(b).to(dev), actions=torch.from_numpy(a).to(dev),
+            out=dict(boards=torch.empty(N_TRANS, dtype=torch.int64, device=dev),
+                     points=torch.empty(N_TRANS, dtype=torch.int32, device=dev),
+                     flags=torch.empty(N_TRANS, dtype=torch.uint8, device=dev),
+                     shaping=torch.empty(N_TRANS, dtype=torch.int64, device=dev))))
+    env0 = rank * N_TRANS
+
+    def one_step(k):
+        s = sets[k % RING]
+        env.step(s["boards"], s["actions"], seed=2048, env0=env0, ctr=1 + k, shaping=True, out=s["out"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(max(args.warmup, 3)):
+        one_step(w)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        one_step(k)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * N_TRANS * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host pinned buffers, copies inside the timed region, through env.step
+    hb, ha = c2_transitions(4242 + rank)
+    h_boards, h_actions = torch.from_numpy(hb).pin_memory(), torch.from_numpy(ha).pin_memory()
+    h_out = dict(boards=torch.empty(N_TRANS, dtype=torch.int64).pin_memory(),
+                 points=torch.empty(N_TRANS, dtype=torch.int32).pin_memory(),
+                 flags=torch.empty(N_TRANS, dtype=torch.uint8).pin_memory(),
+                 shaping=torch.empty(N_TRANS, dtype=torch.int64).pin_memory())
+    d_in = dict(boards=torch.empty(N_TRANS, dtype=torch.int64, device=dev),
+                actions=torch.empty(N_TRANS, dtype=torch.uint8, device=dev))
+    d_out = sets[0]["out"]
+
+    def e2e_step(k):
+        d_in["boards"].copy_(h_boards, non_blocking=True)
+        d_in["actions"].copy_(h_actions, non_blocking=True)
+        env.step(d_in["boards"], d_in["actions"], seed=2048, env0=env0, ctr=1000 + k, shaping=True, out=d_out)
+        for key in h_out:
+            h_out[key].copy_(d_out[key], non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for w in range(3):
+        e2e_step(w)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * N_TRANS * e2e_steps / (e2e_ms * 1e-3)
+    h2d = N_TRANS * (8 + 1)
+    d2h = N_TRANS * (8 + 4 + 1 + 8)
+
+    if rank == 0:
+        peak, which = peaks()
+        achieved = BYTES_PER_TRANSITION * N_TRANS / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step (move+merge points+shaping+Philox spawn+legal/done), one g2048_step launch",
+                       "boards": N_BOARDS, "moves": MOVES, "l2": f"ring of {RING} distinct 120 MiB buffer sets (> 126 MB L2) used round-robin",
+                       "spawn": "philox4x32-10"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "kernel": "step_kernel_staged<true>",
+                         "bytes_per_unit": BYTES_PER_TRANSITION, "units_per_launch": N_TRANS},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

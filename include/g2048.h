@@ -1,0 +1,101 @@
+/*
+ * g2048.h -- C ABI of libg2048.so, the B200 (sm_100a) engine for the 2048-PPO hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what a binding for the
+ * reference's env / rollout / loss path would call.  The reference (pure Python) has no
+ * FFI of its own; each entry cites the reference interface it replaces (file:line in
+ * RobotSail/2048-PPO).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (G2048_OK) or a negative G2048_E* code; it never throws,
+ *     never exits and never falls back to the CPU.  g2048_last_error() returns the
+ *     message of the last failure on the calling thread.
+ *   - all data pointers are DEVICE pointers owned by the caller (e.g. torch tensors'
+ *     data_ptr()); nothing is allocated, freed or retained by the library.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronise the host.
+ *   - boards: one uint64 per board, cell (r,c) = nibble 4*(4r+c), value = tile exponent
+ *     (0 empty, e -> tile 2^e, e <= 15).  The reference's Grid is list[list[int]] of
+ *     exponents (game.py:3,50-51).
+ *   - actions / direction ids: 0=UP 1=DOWN 2=LEFT 3=RIGHT (train.py:266, game.py:1092).
+ *   - spawn draws: either a replay tensor of u32 pairs (u0,u1) or, when it is NULL, words
+ *     0,1 of Philox4x32-10(counter=(env_id, ctr), key=seed), env_id = env0 + index.
+ *     cell = k-th empty cell in row-major order, k = mulhi32(u0, #empty); exponent 2 iff
+ *     u1 >= 3865470567 (<=> not (u1/2^32 < 0.9), game.py:937-939).
+ */
+#ifndef G2048_H
+#define G2048_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2048_OK 0
+#define G2048_EINVAL (-1)   /* bad argument (null pointer, negative size, bad enum) */
+#define G2048_ECUDA (-2)    /* a CUDA runtime call / launch failed */
+#define G2048_EARCH (-3)    /* device is not sm_100 */
+#define G2048_ESHAPE (-4)   /* unsupported model shape */
+
+/* flags byte written by g2048_step */
+#define G2048_FLAG_LEGAL_MASK 0x0F /* bit d: direction d is legal on the returned board */
+#define G2048_FLAG_DONE 0x10       /* returned board has no legal move (game.py:1006 / 963) */
+#define G2048_FLAG_INVALID 0x20    /* the requested move was illegal: board unchanged (game.py:959-978) */
+#define G2048_FLAG_OVERFLOW 0x40   /* a merge created exponent 16, which a nibble cannot hold */
+
+/* packed shaping record written by g2048_step (u64 per transition; 0 for an invalid move).
+ * "after" = after the move, BEFORE the spawn (game.py:994-1002). */
+#define G2048_SH_MONO_BEFORE(w) ((int)((w) & 63))                 /* game.py:985  */
+#define G2048_SH_MONO_AFTER(w) ((int)(((w) >> 6) & 63))           /* game.py:999  */
+#define G2048_SH_EMPT_BEFORE(w) ((int)(((w) >> 12) & 31))         /* game.py:988  */
+#define G2048_SH_EMPT_AFTER(w) ((int)(((w) >> 17) & 31))          /* game.py:1000 */
+#define G2048_SH_MAX_TILE_CREATED(w) ((int)(((w) >> 22) & 31))    /* game.py:158  */
+#define G2048_SH_MAX_EXP_BEFORE(w) ((int)(((w) >> 27) & 15))      /* game.py:989  */
+#define G2048_SH_CORNER_BEFORE(w) ((((w) >> 31) & 1) ? G2048_SH_MAX_EXP_BEFORE(w) : -G2048_SH_MAX_EXP_BEFORE(w)) /* game.py:982 */
+#define G2048_SH_MAX_EXP_AFTER(w) ((int)(((w) >> 32) & 15))       /* game.py:1002 */
+#define G2048_SH_CORNER_AFTER(w) ((((w) >> 36) & 1) ? G2048_SH_MAX_EXP_AFTER(w) : -G2048_SH_MAX_EXP_AFTER(w))    /* game.py:996 */
+#define G2048_SH_SMOOTH_BEFORE(w) (-(int)(((w) >> 37) & 511))     /* game.py:981  */
+#define G2048_SH_SMOOTH_AFTER(w) (-(int)(((w) >> 46) & 511))      /* game.py:995  */
+
+const char* g2048_last_error(void);
+const char* g2048_version(void);
+
+/* Checks that `device` is a compute-capability-10.x GPU and makes it current. */
+int g2048_init(int device);
+
+/* Row table: 65536 x u32 (g2048_lut_bytes() = 262144 bytes), built on the device.
+ * Replaces game.py:224-257 (_merge_and_shift_left/right_with_score) for every row. */
+int64_t g2048_lut_bytes(void);
+int g2048_build_lut(void* d_lut, void* stream);
+
+/* game.py:942-950 Game2048.reset for n boards.  replay: u32[n,4] = (u0,u1) first spawn,
+ * (u2,u3) second spawn; NULL -> Philox words 0..3 at (env0+i, ctr). */
+int g2048_reset(uint64_t* boards, int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0,
+                uint64_t ctr, void* stream);
+
+/* game.py:952-1030 Game2048.step for n (board, action) pairs.
+ * boards_out / points / flags are required; shaping may be NULL (then the potentials are
+ * not computed).  replay: u32[n,2] or NULL (Philox words 0,1 at (env0+i, ctr)). */
+int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* actions, uint64_t* boards_out,
+               int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
+               uint64_t seed, uint64_t env0, uint64_t ctr, void* stream);
+
+/* All four moves of every board without spawning: game.py:121-160 simulate_move,
+ * game.py:167-184 preview_move_rewards, game.py:295-299 current_valid_directions.
+ * succ[n,4] (== board where illegal), points[n,4] (0 where illegal), legal[n] (bit d),
+ * max_tile[n,4] optional (NULL to skip). */
+int g2048_expand4(const void* d_lut, const uint64_t* boards, uint64_t* succ, int32_t* points, uint8_t* legal,
+                  uint8_t* max_tile, int64_t n, void* stream);
+
+/* Board potentials, out int32[n,6] = monotonicity (game.py:683-800), emptiness (671-680),
+ * smoothness (339-357), corner bonus (360-399), max exponent, legal mask (295-299). */
+int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, int64_t n, void* stream);
+
+/* game.py:92-101 to_model_format: out f32[n,48] = 16 x [exponent, row/3, col/3]. */
+int g2048_encode(const uint64_t* boards, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2048_H */

@@ -1,0 +1,242 @@
+"""GPU parity of the environment kernels, called through the C ABI (ctypes), against the
+oracle, the reference-generated fixtures and size-independent properties.  Bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+
+SH_KEYS = ("mono_before", "mono_after", "empt_before", "empt_after", "max_tile_created", "max_exp_before",
+           "max_exp_after", "smooth_before", "smooth_after", "corner_before", "corner_after")
+
+
+@pytest.fixture(scope="module")
+def env():
+    from g2048 import env as e
+    e.init(0)
+    return e
+
+
+def dev_boards(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).cuda()
+
+
+def host_u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def random_boards(n, seed, hi=12, p_empty=0.3):
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randint(1, hi, (n, 16), generator=g, dtype=torch.int64)
+    e[torch.rand((n, 16), generator=g) < p_empty] = 0
+    sh = torch.arange(16, dtype=torch.int64) * 4
+    return (e << sh).sum(dim=1).numpy().view(np.uint64)
+
+
+def check_step(env, boards, actions, draws, n_expected=None):
+    r = env.step(dev_boards(boards), torch.from_numpy(actions).cuda(),
+                 replay=torch.from_numpy(draws.view(np.int32)).cuda())
+    want_b, want = O.step_batch(boards, actions, replay=draws)
+    np.testing.assert_array_equal(host_u64(r["boards"]), want_b)
+    np.testing.assert_array_equal(r["points"].cpu().numpy(), want["points"])
+    fl = r["flags"].cpu().numpy()
+    np.testing.assert_array_equal(fl & 0x0F, want["legal_after"])
+    np.testing.assert_array_equal((fl >> 4) & 1, want["done"])
+    np.testing.assert_array_equal((fl >> 5) & 1, want["invalid"])
+    np.testing.assert_array_equal((fl >> 6) & 1, want["overflow"])
+    sh = env.decode_shaping(r["shaping"].cpu().numpy())
+    for k in SH_KEYS:
+        np.testing.assert_array_equal(sh[k], want[k], err_msg=k)
+    return r, want
+
+
+def test_row_table_matches_oracle(env):
+    lut = env.lut(0).cpu().numpy().view(np.uint32)
+    out4, score, mt = O.row_table()
+    res = np.stack([(lut >> (4 * k)) & 15 for k in range(4)], axis=1)
+    np.testing.assert_array_equal(res, np.minimum(out4, 15))
+    c1, c2 = (lut >> 16) & 15, (lut >> 20) & 15
+    sc = np.where(c1 > 0, 2 << c1.astype(np.int64), 0) + np.where(c2 > 0, 2 << c2.astype(np.int64), 0)
+    np.testing.assert_array_equal(sc, score)
+    np.testing.assert_array_equal(np.maximum(np.where(c1 > 0, c1 + 1, 0), np.where(c2 > 0, c2 + 1, 0)), mt)
+    assert int(sc.sum()) == 100660224
+
+
+def test_step_matches_reference_fixture(env, golden):
+    g = golden("env_step")
+    r = env.step(dev_boards(g["board"]), torch.from_numpy(g["action"]).cuda(),
+                 replay=torch.from_numpy(g["draw"].view(np.int32)).cuda())
+    got = host_u64(r["boards"])
+    sh16 = np.arange(16, dtype=np.uint64) * np.uint64(4)
+    cells = ((got[:, None] >> sh16) & np.uint64(15)).astype(np.uint8)
+    np.testing.assert_array_equal(cells, np.minimum(g["out_cells"], 15))
+    np.testing.assert_array_equal(r["points"].cpu().numpy(), g["points"])
+    fl = r["flags"].cpu().numpy()
+    np.testing.assert_array_equal(fl & 0x0F, g["legal_after"])
+    np.testing.assert_array_equal((fl >> 4) & 1, g["done"])
+    np.testing.assert_array_equal((fl >> 5) & 1, g["invalid"])
+    np.testing.assert_array_equal(((fl >> 6) & 1).astype(bool), (g["out_cells"] > 15).any(axis=1))
+    sh = env.decode_shaping(r["shaping"].cpu().numpy())
+    for k in SH_KEYS:
+        np.testing.assert_array_equal(sh[k], g[k], err_msg=k)
+    np.testing.assert_array_equal(sh["smooth_after"] - sh["smooth_before"], g["smooth_delta"])
+    np.testing.assert_array_equal(sh["corner_after"] - sh["corner_before"], g["corner_delta"])
+
+
+def test_step_without_shaping_small_and_large(env):
+    for n in (1000, 1 << 18):
+        boards = random_boards(n, 5)
+        actions = (np.arange(n) % 4).astype(np.uint8)
+        r = env.step(dev_boards(boards), torch.from_numpy(actions).cuda(), seed=9, env0=17, ctr=3, shaping=False)
+        want_b, want = O.step_batch(boards, actions, seed=9, env0=17, ctr=3)
+        np.testing.assert_array_equal(host_u64(r["boards"]), want_b)
+        np.testing.assert_array_equal(r["points"].cpu().numpy(), want["points"])
+        assert r["shaping"] is None
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, (1 << 17) + 77])
+def test_step_random_boards_replay(env, n):
+    rng = np.random.default_rng(n)
+    boards = random_boards(n, n)
+    actions = rng.integers(0, 4, n).astype(np.uint8)
+    draws = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    check_step(env, boards, actions, draws)
+
+
+def test_step_high_exponents_and_overflow(env):
+    n = 1 << 17
+    rng = np.random.default_rng(3)
+    boards = random_boards(n, 3, hi=16, p_empty=0.2)
+    actions = rng.integers(0, 4, n).astype(np.uint8)
+    draws = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    r, want = check_step(env, boards, actions, draws)
+    assert want["overflow"].sum() > 0
+
+
+def test_step_all_rows_exhaustive(env):
+    """Every row with exponents <= 14 tiled into the 4 rows of a board, and its transpose."""
+    vals = np.arange(15, dtype=np.uint64)
+    rows = (vals[:, None, None, None] | vals[None, :, None, None] << np.uint64(4) |
+            vals[None, None, :, None] << np.uint64(8) | vals[None, None, None, :] << np.uint64(12)).reshape(-1)
+    assert rows.size == 50625
+    horiz = rows | rows << np.uint64(16) | rows << np.uint64(32) | rows << np.uint64(48)
+    c = [(rows >> np.uint64(4 * k)) & np.uint64(15) for k in range(4)]
+    col = lambda v: v | v << np.uint64(4) | v << np.uint64(8) | v << np.uint64(12)
+    vert = col(c[0]) | col(c[1]) << np.uint64(16) | col(c[2]) << np.uint64(32) | col(c[3]) << np.uint64(48)
+    boards = np.concatenate([horiz, vert])
+    rng = np.random.default_rng(1)
+    for a in range(4):
+        actions = np.full(boards.size, a, dtype=np.uint8)
+        draws = rng.integers(0, 2**32, (boards.size, 2), dtype=np.uint64).astype(np.uint32)
+        check_step(env, boards, actions, draws)
+
+
+def test_philox_path_matches_oracle(env):
+    n = 1 << 17
+    boards = random_boards(n, 11)
+    actions = (np.arange(n) % 4).astype(np.uint8)
+    r = env.step(dev_boards(boards), torch.from_numpy(actions).cuda(), seed=0xDEADBEEFCAFE, env0=(1 << 33) + 5, ctr=7)
+    want_b, _ = O.step_batch(boards, actions, seed=0xDEADBEEFCAFE, env0=(1 << 33) + 5, ctr=7)
+    np.testing.assert_array_equal(host_u64(r["boards"]), want_b)
+
+
+def test_reset_matches_oracle(env):
+    for n in (1, 1000, 100000):
+        got = host_u64(env.reset(n, device=0, seed=2048, env0=3, ctr=0))
+        np.testing.assert_array_equal(got, O.reset_batch(n, seed=2048, env0=3, ctr=0))
+    rng = np.random.default_rng(0)
+    draws = rng.integers(0, 2**32, (5000, 4), dtype=np.uint64).astype(np.uint32)
+    got = host_u64(env.reset(5000, device=0, replay=torch.from_numpy(draws.view(np.int32)).cuda()))
+    np.testing.assert_array_equal(got, O.reset_batch(5000, replay=draws))
+    cells = ((got[:, None] >> (np.arange(16, dtype=np.uint64) * np.uint64(4))) & np.uint64(15))
+    assert ((cells > 0).sum(axis=1) == 2).all()
+
+
+@pytest.mark.parametrize("n", [7, 4097, 1 << 18])
+def test_expand4_matches_oracle(env, n):
+    boards = random_boards(n, n + 1, hi=15, p_empty=0.25)
+    r = env.expand4(dev_boards(boards), want_max_tile=True)
+    succ, points, mt, legal = O.expand4_batch(boards)
+    np.testing.assert_array_equal(host_u64(r["succ"]), succ)
+    np.testing.assert_array_equal(r["points"].cpu().numpy(), points)
+    np.testing.assert_array_equal(r["max_tile"].cpu().numpy(), mt)
+    np.testing.assert_array_equal(r["legal"].cpu().numpy(), legal)
+
+
+def test_expand4_best_game_replay(env, golden):
+    g = golden("best_game")
+    r = env.expand4(dev_boards(g["before"]))
+    idx = np.arange(len(g["action"]))
+    moved = host_u64(r["succ"])[idx, g["action"]]
+    np.testing.assert_array_equal(r["points"].cpu().numpy()[idx, g["action"]], g["points"])
+    sh16 = np.arange(16, dtype=np.uint64) * np.uint64(4)
+    mc = ((moved[:, None] >> sh16) & np.uint64(15)).astype(int)
+    ac = ((g["after"][:, None] >> sh16) & np.uint64(15)).astype(int)
+    diff = mc != ac
+    assert (diff.sum(axis=1) == 1).all() and (mc[diff] == 0).all() and np.isin(ac[diff], (1, 2)).all()
+
+
+def test_potentials_match_reference_fixture(env, golden):
+    g = golden("potentials")
+    got = env.potentials(dev_boards(g["board"])).cpu().numpy()
+    np.testing.assert_array_equal(got, g["values"])
+
+
+def test_encode_matches_reference_fixture(env, golden):
+    g = golden("model_best")
+    np.testing.assert_array_equal(env.encode(dev_boards(g["board"])).cpu().numpy(), g["inputs"])
+
+
+def test_symmetry_properties_full_size(env):
+    """Size-independent properties at the C2 size (2^20 boards): a move commutes with the
+    board's transpose (UP<->LEFT, DOWN<->RIGHT) and legality <=> the board changes."""
+    n = 1 << 20
+    boards = random_boards(n, 2048)
+    r = env.expand4(dev_boards(boards))
+    succ, legal = host_u64(r["succ"]), r["legal"].cpu().numpy()
+    changed = succ != boards[:, None]
+    np.testing.assert_array_equal(changed, ((legal[:, None] >> np.arange(4)) & 1).astype(bool))
+
+    def transpose(b):
+        out = np.zeros_like(b)
+        for rr in range(4):
+            for cc in range(4):
+                out |= ((b >> np.uint64(4 * (4 * rr + cc))) & np.uint64(15)) << np.uint64(4 * (4 * cc + rr))
+        return out
+
+    rt = env.expand4(dev_boards(transpose(boards)))
+    st = host_u64(rt["succ"])
+    np.testing.assert_array_equal(transpose(st[:, 2]), succ[:, 0])   # LEFT of transpose == UP
+    np.testing.assert_array_equal(transpose(st[:, 3]), succ[:, 1])   # RIGHT of transpose == DOWN
+    np.testing.assert_array_equal(rt["points"].cpu().numpy()[:, [2, 3, 0, 1]], r["points"].cpu().numpy())
+    # tile-value sum is conserved by a move (merging 2^e + 2^e = 2^(e+1))
+    val = lambda b: sum((np.uint64(1) << ((b >> np.uint64(4 * k)) & np.uint64(15))) * (((b >> np.uint64(4 * k)) & np.uint64(15)) > 0) for k in range(16))
+    for d in range(4):
+        np.testing.assert_array_equal(val(succ[:, d]), val(boards))
+
+
+def test_facade_matches_reference_semantics(env):
+    from g2048.env import Direction, Game2048
+    g = Game2048([[1, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]])
+    assert set(g.current_valid_directions()) == {Direction.DOWN, Direction.RIGHT}
+    grid, pts, done, info = g.step(Direction.UP)
+    assert info["invalid_move"] and pts == 0 and not done and grid[0][0] == 1
+    with pytest.raises(ValueError):
+        g.move(Direction.UP)
+    chk = Game2048([[1, 2, 1, 2], [2, 1, 2, 1], [1, 2, 1, 2], [2, 1, 2, 1]])
+    assert not chk.has_next_step()
+    grid, pts, done, info = chk.step(Direction.UP)
+    assert done and info["invalid_move"]
+    B = [[1, 2, 3, 4], [8, 7, 6, 5], [9, 10, 11, 12], [0, 0, 0, 13]]
+    assert Game2048.monotonicity(B) == 30 and Game2048.smoothness_score(B) == -42.0
+    assert Game2048.corner_bonus(B) == 13.0 and Game2048.emptiness(B) == 3
+    assert Game2048.simulate_move([[1, 1, 1, 1]] + [[0] * 4] * 3, Direction.LEFT) == \
+        ([[2, 2, 0, 0]] + [[0] * 4] * 3, 8, 2)
+    g2 = Game2048(seed=2048, env_id=0)
+    grid = g2.reset()
+    assert sum(1 for r in grid for c in r if c) == 2
+    assert g2.to_model_format().shape == (48,)
+    new, pts, done, info = g2.step(g2.current_valid_directions()[0])
+    assert not info["invalid_move"] and "monotonicity_before" in info
