@@ -65,14 +65,13 @@ __host__ __device__ inline uint32_t lut_entry_for_row(uint32_t row) {
            uint32_t(mx) << 28;
 }
 
-// Row-table readers.  LutShared: staged copy + L2 for the tail; LutGlobal: L2 only
-// (used where shared memory belongs to something else, e.g. the rollout kernel).
+// Row-table readers.  LutShared: the staged copy, valid only for rows < LUT_SMEM_ROWS --
+// callers guarantee that by sending boards with a cell >= 12 (see has_big_tile) down the
+// LutGlobal path; LutGlobal: L2 only (also used where shared memory belongs to something
+// else, e.g. the rollout kernel).
 struct LutShared {
     const uint32_t* s;
-    const uint32_t* g;
-    __device__ __forceinline__ uint32_t operator()(uint32_t row) const {
-        return row < uint32_t(LUT_SMEM_ROWS) ? s[row] : __ldg(g + row);
-    }
+    __device__ __forceinline__ uint32_t operator()(uint32_t row) const { return s[row]; }
 };
 struct LutGlobal {
     const uint32_t* g;
@@ -101,6 +100,13 @@ __device__ __forceinline__ uint32_t rev_rows32(uint32_t x) {
     return __byte_perm(y, 0, 0x2301);
 }
 __device__ __forceinline__ Board rev_rows(Board b) { return {rev_rows32(b.lo), rev_rows32(b.hi)}; }
+
+// some cell holds exponent >= 12 (tile 4096+).  Boards without one only produce rows below
+// 0xD000 before and after a move (a merge raises an exponent by one), which the staged part
+// of the row table covers.
+__device__ __forceinline__ bool has_big_tile(Board b) {
+    return (((b.lo & (b.lo >> 1)) | (b.hi & (b.hi >> 1))) & 0x44444444u) != 0u;
+}
 
 // bit 4i set <=> nibble i is non-zero
 __device__ __forceinline__ uint32_t nz_flags32(uint32_t x) {

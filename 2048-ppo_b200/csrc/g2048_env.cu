@@ -74,8 +74,9 @@ __global__ void reset_kernel(uint64_t* boards, int64_t n, const uint32_t* replay
 
 constexpr int STEP_THREADS = 1024;
 
-template <bool SHAPING, class Lut>
-__device__ __forceinline__ void step_loop(const Lut& lut, const uint64_t* __restrict__ in,
+template <bool SHAPING, bool STAGED>
+__device__ __forceinline__ void step_loop(const uint32_t* slut, const uint32_t* __restrict__ glut,
+                                          const uint64_t* __restrict__ in,
                                           const uint8_t* __restrict__ actions, uint64_t* __restrict__ out,
                                           int32_t* __restrict__ points, uint8_t* __restrict__ flags,
                                           uint64_t* __restrict__ shaping, int64_t n,
@@ -95,7 +96,9 @@ __device__ __forceinline__ void step_loop(const Lut& lut, const uint64_t* __rest
             u0 = d.x;
             u1 = d.y;
         }
-        StepOut o = env_step<SHAPING>(b, a, u0, u1, lut);
+        StepOut o;
+        if (STAGED && !has_big_tile(b)) o = env_step<SHAPING>(b, a, u0, u1, LutShared{slut});
+        else o = env_step<SHAPING>(b, a, u0, u1, LutGlobal{glut});   // rare: a 4096+ tile on the board
         out[i] = pack_board(o.board);
         points[i] = o.points;
         flags[i] = uint8_t(o.flags);
@@ -112,7 +115,7 @@ step_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* in, const 
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
     stage_lut(slut, glut, &bar);
-    step_loop<SHAPING>(LutShared{slut, glut}, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
+    step_loop<SHAPING, true>(slut, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
 }
 
 template <bool SHAPING>
@@ -120,21 +123,35 @@ __global__ void __launch_bounds__(256)
 step_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
                    int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
                    uint64_t seed, uint64_t env0, uint64_t ctr) {
-    step_loop<SHAPING>(LutGlobal{glut}, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
+    step_loop<SHAPING, false>(nullptr, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
 }
 
+struct FourLines {
+    Lines up, down, left, right;
+};
 template <class Lut>
-__device__ __forceinline__ void expand4_loop(const Lut& lut, const uint64_t* __restrict__ boards,
+__device__ __forceinline__ FourLines lookup_moves(Board b, const Lut& lut) {
+    Board bt = transpose(b);
+    FourLines f;
+    f.up = lookup_rows(bt, lut);               // UP    = left move of the columns
+    f.down = lookup_rows(rev_rows(bt), lut);   // DOWN  = right move of the columns
+    f.left = lookup_rows(b, lut);              // LEFT
+    f.right = lookup_rows(rev_rows(b), lut);   // RIGHT
+    return f;
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void expand4_loop(const uint32_t* slut, const uint32_t* __restrict__ glut,
+                                             const uint64_t* __restrict__ boards,
                                              uint64_t* __restrict__ succ, int32_t* __restrict__ points,
                                              uint8_t* __restrict__ legal, uint8_t* __restrict__ max_tile, int64_t n) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         Board b = make_board(__ldg(boards + i));
-        Board bt = transpose(b);
-        Lines lu = lookup_rows(bt, lut);              // UP    = left move of the columns
-        Lines ld = lookup_rows(rev_rows(bt), lut);    // DOWN  = right move of the columns
-        Lines ll = lookup_rows(b, lut);               // LEFT
-        Lines lr = lookup_rows(rev_rows(b), lut);     // RIGHT
+        FourLines f;
+        if (STAGED && !has_big_tile(b)) f = lookup_moves(b, LutShared{slut});
+        else f = lookup_moves(b, LutGlobal{glut});
+        const Lines &lu = f.up, &ld = f.down, &ll = f.left, &lr = f.right;
         Board s[4] = {transpose(result_of(lu)), transpose(rev_rows(result_of(ld))), result_of(ll),
                       rev_rows(result_of(lr))};
         int p[4], mt[4];
@@ -165,13 +182,13 @@ expand4_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* boards,
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
     stage_lut(slut, glut, &bar);
-    expand4_loop(LutShared{slut, glut}, boards, succ, points, legal, max_tile, n);
+    expand4_loop<true>(slut, glut, boards, succ, points, legal, max_tile, n);
 }
 
 __global__ void __launch_bounds__(256)
 expand4_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* boards, uint64_t* succ, int32_t* points,
                       uint8_t* legal, uint8_t* max_tile, int64_t n) {
-    expand4_loop(LutGlobal{glut}, boards, succ, points, legal, max_tile, n);
+    expand4_loop<false>(nullptr, glut, boards, succ, points, legal, max_tile, n);
 }
 
 __global__ void __launch_bounds__(256)

@@ -95,6 +95,41 @@ int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, in
 /* game.py:92-101 to_model_format: out f32[n,48] = 16 x [exponent, row/3, col/3]. */
 int g2048_encode(const uint64_t* boards, float* out, int64_t n, void* stream);
 
+/* ---- rollout buffers -------------------------------------------------------------------
+ * Time-major [T,B] arrays (index t*B + b).  flags = the g2048_step flags of the move plus
+ * G2048_FLAG_VALID when the slot holds a recorded move (a finished game without auto-reset
+ * leaves invalid slots behind).  A move with G2048_FLAG_DONE is the last of its episode. */
+#define G2048_FLAG_VALID 0x80
+
+/* Size of the scratch buffer the two reductions below need (device memory, caller-owned). */
+int64_t g2048_reduce_workspace_bytes(void);
+
+/* train.py:698-772 calculate_advantage (reward, discounted rewards-to-go per episode,
+ * normalisation with the bias-corrected EMA moments, advantage), float64 inside, one pass.
+ *   reward = w_points*points + w_mono*(gamma*mono_after - mono_before)
+ *                            + w_empt*(gamma*empt_after - empt_before)      (train.py:702-719)
+ *   with the terminal fix-up mono_after = empt_after = 0 on a DONE move       (train.py:318-322)
+ *   g_norm = (G - mu_corrected) / (stddev + 1e-8); adv = g_norm - value       (train.py:760,772)
+ * reward_out / g_raw_out may be NULL.  stats_out: f64[3] = {sum G, sum G^2, #valid} for the
+ * batch mean / variance of train.py:738-739 (and for the cross-GPU allreduce). */
+int g2048_rtg_advantage(const int32_t* points, const uint64_t* shaping, const uint8_t* flags, const float* value,
+                        int32_t T, int64_t B, double gamma, double w_points, double w_mono, double w_empt,
+                        double mu_corrected, double stddev, float* reward_out, float* g_raw_out, float* g_norm_out,
+                        float* adv_out, double* stats_out, void* workspace, void* stream);
+
+/* train.py:497-554: masked log-softmax, PPO-clip surrogate (eps = clip_eps), entropy of the
+ * clamped masked logits, smooth-L1 critic loss; loss = -(1/N) sum(ppo - c_v*vl + beta_ent*H).
+ * Forward and analytic backward in one pass: dlogits f32[n,4] and dvalue f32[n] hold
+ * d loss / d logits and d loss / d value (inv_n = 1/N already applied; N may be a global count).
+ * old_logp: f32[n,old_logp_stride], stride 4 = all four rollout log-probs (train.py:326),
+ * stride 1 = only the chosen action's.  legal: bit d = direction d legal (the reference's
+ * action_mask is the complement, train.py:138,268).  flags may be NULL (= all valid).
+ * stats_out: f64[4] = {sum ppo, sum smooth_l1, sum entropy, #valid}. */
+int g2048_ppo_loss(const float* logits, const float* value, const float* old_logp, int32_t old_logp_stride,
+                   const uint8_t* actions, const uint8_t* legal, const uint8_t* flags, const float* adv,
+                   const float* g_norm, int64_t n, float clip_eps, float c_v, float beta_ent, float inv_n,
+                   float* dlogits, float* dvalue, double* stats_out, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

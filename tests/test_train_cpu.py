@@ -1,0 +1,90 @@
+"""CPU: the policy mirror reproduces the reference network bit-for-bit on the shipped checkpoint,
+and the torch restatement of the loss (the checker of the fused CUDA loss) reproduces the stats and
+clipped gradients that the reference's own model_optimize_step produced (tests/golden/loss.npz)."""
+import numpy as np
+import torch
+
+from helpers import ref_ppo_loss_torch, rollout_as_tb
+
+
+def load_policy(golden, dropout=0.0):
+    from g2048 import policy
+    g = golden("model_best")
+    m = policy.GameMLP(policy.MLPConfig(hidden_dim=int(g["hidden_dim"]), num_layers=int(g["num_layers"]),
+                                        dropout=dropout))
+    m.load_state_dict(policy.load_state_dict_from_npz(g))
+    return m, g
+
+
+def policy_b(golden):
+    """The update-side policy of the loss fixture (oracle/make_golden.py gen_loss)."""
+    m, _ = load_policy(golden)
+    with torch.no_grad():
+        m.action_head.weight.mul_(1.3)
+        m.value_head.bias.add_(0.3)
+    return m
+
+
+def test_policy_mirror_matches_reference_forward(golden):
+    m, g = load_policy(golden)
+    m.eval()
+    with torch.no_grad():
+        logits, v = m(torch.from_numpy(g["inputs"]))
+    np.testing.assert_array_equal(logits.numpy(), g["logits"])
+    np.testing.assert_array_equal(v.numpy(), g["value"])
+    assert [d.value for d in m.directions] == ["up", "down", "left", "right"]
+    assert sum(p.numel() for p in m.parameters()) == 192 * 48 + 2 * 192 + 2 * (192 * 192 + 2 * 192) + 5 * 192 + 5
+
+
+def test_policy_state_dict_keys_h196():
+    from g2048 import policy
+    m = policy.GameMLP(policy.MLPConfig(hidden_dim=196))
+    keys = set(m.state_dict().keys())
+    assert {"stem.0.weight", "stem.1.weight", "stem.1.bias", "backbone.0.mlp.0.weight", "backbone.1.mlp.1.bias",
+            "action_head.weight", "action_head.bias", "value_head.weight", "value_head.bias"} <= keys
+    assert sum(p.numel() for p in m.parameters()) == 88401
+    groups = m.get_param_groups(1e-4, 1e-3)
+    assert [len(g["params"]) for g in groups] == [4, 7, 1, 1]
+
+
+def test_loss_restatement_matches_reference_optimize_step(golden):
+    from oracle import oracle as O
+    gr, ga, gl = golden("rollout"), golden("advantage"), golden("loss")
+    m = policy_b(golden)
+    m.train()
+    x = torch.from_numpy(O.encode_batch(gr["board"]))
+    adv = torch.from_numpy(ga["readme__adv"].astype(np.float32))
+    gn = torch.from_numpy(ga["readme__g_norm"].astype(np.float32))
+    for name in ("readme", "alt"):
+        ent, crit = gl[name + "__coef"].tolist()
+        m.zero_grad()
+        logits, v = m(x)
+        loss, parts = ref_ppo_loss_torch(logits, v, torch.from_numpy(gr["logp"]), torch.from_numpy(gr["action"]),
+                                         torch.from_numpy(gr["legal"]), adv, gn, 0.2, crit, ent)
+        loss.backward()
+        gnorm = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        want = gl[name + "__stats"]
+        np.testing.assert_allclose(float(loss), want[0], rtol=1e-5)
+        np.testing.assert_allclose(-float(parts["ppo"]), want[1], rtol=1e-5)
+        np.testing.assert_allclose(crit * float(parts["vl"]), want[2], rtol=1e-5)
+        np.testing.assert_allclose(float(parts["ent"]), want[3], rtol=1e-5)
+        np.testing.assert_allclose(float(gnorm), want[4], rtol=1e-4)
+        for k, p in m.named_parameters():
+            ref = gl[name + "__grad__" + k.replace(".", "__")]
+            np.testing.assert_allclose(p.grad.numpy(), ref, rtol=1e-3, atol=1e-6 * max(1.0, np.abs(ref).max()), err_msg=k)
+
+
+def test_rtg_moments_update_matches_reference(golden):
+    from g2048.ppo import RtgMoments
+    from oracle import oracle as O
+    g, adv = golden("rollout"), golden("advantage")
+    a, _ = rollout_as_tb(g)
+    for name in ("readme", "warm"):
+        gamma, wp, wm, we, beta, step, mu, m2 = adv[name + "__cfg"].tolist()
+        mom = RtgMoments(mu=mu, m2=m2, step=int(step))
+        mu_c, sd = mom.corrected(beta)
+        graw = adv[name + "__g_raw"]
+        mom.update(beta, float(graw.sum()), float((graw * graw).sum()), len(graw))
+        np.testing.assert_allclose([mom.mu, mom.m2], adv[name + "__moments_out"], rtol=1e-10)
+        gn = (graw - mu_c) / (sd + 1e-8)
+        np.testing.assert_allclose(gn, adv[name + "__g_norm"], rtol=1e-12, atol=1e-12)
