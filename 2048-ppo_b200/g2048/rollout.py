@@ -1,0 +1,233 @@
+"""Batched actor-critic rollout on the fused CUDA kernel + the `play_games_batched` drop-in.
+
+Reference interfaces (file:line in RobotSail/2048-PPO):
+  play_game_for_episode(model, max_steps, device) -> EpisodeData      train.py:213-345
+  batched_rollout.play_games_batched(model, num_games, max_steps, device) -> list[EpisodeData]
+      imported at train.py:30 and called at train.py:1677-1679, 2034 -- the module is missing
+      from the reference; this file (re-exported by /batched_rollout.py) fills that slot.
+  StepData / EpisodeData schemas                                        train.py:123-177
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, env
+from .env import DIRECTIONS, _ptr, _stream
+
+
+class _RolloutStruct(C.Structure):
+    _fields_ = [
+        ("B", C.c_int64), ("T", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32), ("auto_reset", C.c_int32),
+        ("seed", C.c_uint64), ("env0", C.c_uint64), ("ctr0", C.c_uint64),
+        ("packed_weights", C.c_void_p), ("lut", C.c_void_p), ("boards", C.c_void_p), ("alive", C.c_void_p),
+        ("forced_actions", C.c_void_p), ("rec_boards", C.c_void_p), ("rec_actions", C.c_void_p),
+        ("rec_legal", C.c_void_p), ("rec_logp", C.c_void_p), ("rec_value", C.c_void_p), ("rec_points", C.c_void_p),
+        ("rec_shaping", C.c_void_p), ("rec_flags", C.c_void_p), ("rec_entropy", C.c_void_p),
+    ]
+
+
+_lib.lib().g2048_mlp_packed_floats.restype = C.c_int64
+_lib.lib().g2048_mlp_packed_floats.argtypes = [C.c_int32, C.c_int32]
+_lib.register("g2048_mlp_pack", [C.c_int32, C.c_int32] + [C.c_void_p] * 12)
+_lib.register("g2048_rollout_mlp", [C.POINTER(_RolloutStruct), C.c_void_p])
+
+
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+@dataclass
+class PackedPolicy:
+    hidden: int
+    layers: int
+    weights: torch.Tensor   # float32, kernel layout
+
+
+def pack_policy(model, device=None) -> PackedPolicy:
+    """GameMLP (ours or the reference's: same state_dict keys, game.py:1064-1085) -> kernel layout."""
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    h = sd["stem.0.weight"].shape[0]
+    L = len({k.split(".")[1] for k in sd if k.startswith("backbone.")})
+    dev = env.init(device if device is not None else (sd["stem.0.weight"].device
+                                                       if sd["stem.0.weight"].is_cuda else None))
+    n = int(_lib.lib().g2048_mlp_packed_floats(h, L))
+    if n < 0:
+        raise ValueError(f"the fused rollout kernel supports hidden_dim <= 208 and <= 8 layers (got h={h}, L={L})")
+    f = lambda k: sd[k].to(device=dev, dtype=torch.float32).contiguous()
+    t = {k: f(k) for k in sd}
+    arr = lambda keys: (C.c_void_p * max(L, 1))(*[t[k].data_ptr() for k in keys])
+    bw = arr([f"backbone.{i}.mlp.0.weight" for i in range(L)])
+    bg = arr([f"backbone.{i}.mlp.1.weight" for i in range(L)])
+    bb = arr([f"backbone.{i}.mlp.1.bias" for i in range(L)])
+    with torch.cuda.device(dev):
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.call("g2048_mlp_pack", h, L, _dp(t["stem.0.weight"]), _dp(t["stem.1.weight"]), _dp(t["stem.1.bias"]),
+                  C.cast(bw, C.c_void_p), C.cast(bg, C.c_void_p), C.cast(bb, C.c_void_p),
+                  _dp(t["action_head.weight"]), _dp(t["action_head.bias"]), _dp(t["value_head.weight"]),
+                  _dp(t["value_head.bias"]), _dp(out), _stream())
+        torch.cuda.current_stream().synchronize()   # `t` (temporaries) must outlive the pack kernel
+    return PackedPolicy(h, L, out)
+
+
+@dataclass
+class RolloutBuffers:
+    """Time-major [T,B] records of one rollout call (include/g2048.h G2048Rollout)."""
+    boards: torch.Tensor     # int64  state_before
+    actions: torch.Tensor    # uint8
+    legal: torch.Tensor      # uint8  legal-direction bits of state_before
+    logp: torch.Tensor       # float32 [T,B,4]
+    value: torch.Tensor      # float32
+    points: torch.Tensor     # int32
+    shaping: torch.Tensor    # int64  packed G2048_SH_* words
+    flags: torch.Tensor      # uint8  step flags | 0x80 (valid)
+    entropy: torch.Tensor    # float32
+
+    @staticmethod
+    def allocate(T: int, B: int, device) -> "RolloutBuffers":
+        e = lambda dt, *s: torch.empty((T, B, *s), dtype=dt, device=device)
+        return RolloutBuffers(e(torch.int64), e(torch.uint8), e(torch.uint8), e(torch.float32, 4), e(torch.float32),
+                              e(torch.int32), e(torch.int64), e(torch.uint8), e(torch.float32))
+
+    @property
+    def shape(self):
+        return tuple(self.flags.shape)
+
+
+def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, env0: int = 0, ctr0: int = 1,
+            auto_reset: bool = True, alive: torch.Tensor | None = None, forced_actions: torch.Tensor | None = None,
+            out: RolloutBuffers | None = None) -> RolloutBuffers:
+    """Play T steps of every board in `boards` (updated in place) with one fused kernel launch."""
+    boards = env._req(boards, torch.int64, "boards")
+    B = boards.numel()
+    dev = env.init(boards.device)
+    with torch.cuda.device(dev):
+        buf = out if out is not None else RolloutBuffers.allocate(T, B, dev)
+        assert buf.shape == (T, B)
+        if forced_actions is not None:
+            forced_actions = env._req(forced_actions, torch.uint8, "forced_actions")
+            assert forced_actions.shape == (T, B)
+        if alive is not None:
+            alive = env._req(alive, torch.uint8, "alive")
+        s = _RolloutStruct(B, T, policy.hidden, policy.layers, int(auto_reset), seed, env0, ctr0,
+                           _dp(policy.weights), _dp(env.lut(dev)), _dp(boards), _dp(alive), _dp(forced_actions),
+                           _dp(buf.boards), _dp(buf.actions), _dp(buf.legal), _dp(buf.logp), _dp(buf.value),
+                           _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy))
+        _lib.call("g2048_rollout_mlp", C.byref(s), _stream())
+    return buf
+
+
+# ----------------------------------------------------------------------------- drop-in
+
+_GAMES_PLAYED = itertools.count()
+_CHUNK = 256
+
+
+def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, device) -> list[dict]:
+    """Device records -> list[EpisodeData] exactly as train.py:299-345 builds them (host-side slow path)."""
+    cat = lambda name: torch.cat([getattr(b, name) for b in bufs], dim=0)
+    boards, flags = cat("boards"), cat("flags")
+    T, B = flags.shape
+    game_state = env.encode(boards.reshape(-1)).reshape(T, B, 48)
+    ex = env.expand4(boards.reshape(-1))
+    pts_possible = ex["points"].reshape(T, B, 4).cpu().numpy()
+    h = {k: cat(k).cpu().numpy() for k in ("actions", "legal", "logp", "value", "points", "shaping", "entropy")}
+    boards_h, flags_h, final_h = boards.cpu().numpy(), flags.cpu().numpy(), final_boards.cpu().numpy()
+    sh = {k: v.reshape(T, B) for k, v in env.decode_shaping(h["shaping"].reshape(-1)).items()}
+    episodes = []
+    for b in range(B):
+        n = int((flags_h[:, b] & 0x80 != 0).sum())
+        moves = []
+        total_points = 0
+        for t in range(n):
+            done = bool(flags_h[t, b] & env.FLAG_DONE)
+            lm = int(h["legal"][t, b])
+            result = boards_h[t + 1, b] if t + 1 < n else final_h[b]
+            pp = {d: int(pts_possible[t, b, i]) for i, d in enumerate(DIRECTIONS)}
+            moves.append({
+                "predicted_future_value": float(h["value"][t, b]),
+                "selected_direction": int(h["actions"][t, b]),
+                "game_state": game_state[t, b],
+                "state_before": env.unpack_board(boards_h[t, b]),
+                "result_state": env.unpack_board(result),
+                "max_points_possible": max(pp.values()),
+                "points_earned": int(h["points"][t, b]),
+                "points_possible": pp,
+                "action_mask": [not bool((lm >> i) & 1) for i in range(4)],
+                "smoothness_delta": float(sh["smooth_after"][t, b] - sh["smooth_before"][t, b]),
+                "max_tile_created": int(sh["max_tile_created"][t, b]),
+                "max_exponent_before": int(sh["max_exp_before"][t, b]),
+                "max_exponent_after": int(sh["max_exp_after"][t, b]),
+                "corner_delta": float(sh["corner_after"][t, b] - sh["corner_before"][t, b]),
+                "adjacency_delta": 0.0, "chain_delta": 0.0, "topological_delta": 0.0,   # not computed
+                "monotonicity_after": int(sh["mono_after"][t, b]) if not done else 0.0,   # train.py:318-319
+                "monotonicity_before": int(sh["mono_before"][t, b]),
+                "emptiness_before": int(sh["empt_before"][t, b]),
+                "emptiness_after": int(sh["empt_after"][t, b]) if not done else 0.0,      # train.py:322
+                "entropy": float(h["entropy"][t, b]),
+                "policy_logprobs": [float(x) for x in h["logp"][t, b]],
+            })
+            total_points += int(h["points"][t, b])
+        ended = n > 0 and bool(flags_h[n - 1, b] & env.FLAG_DONE)
+        episodes.append({"moves": moves, "total_points": total_points,
+                         "total_steps": n - 1 if ended else n,                          # train.py:334-343
+                         "final_state": env.unpack_board(final_h[b])})
+    return episodes
+
+
+@torch.no_grad()
+def play_games_batched(model, num_games: int, max_steps: int | None = None, device=None, *, seed: int | None = None):
+    """Play `num_games` games to the end (or `max_steps` moves each) -> list[EpisodeData]."""
+    if device is None or torch.device(device).type != "cuda":
+        raise RuntimeError("play_games_batched runs on a CUDA device only (no CPU fallback); pass --gpu / device='cuda'")
+    dev = env.init(device)
+    policy = pack_policy(model, dev)
+    seed = int(os.environ.get("G2048_SEED", "2048")) if seed is None else seed
+    env0 = next(_GAMES_PLAYED) * (1 << 32)
+    boards = env.reset(num_games, device=dev, seed=seed, env0=env0, ctr=0)
+    alive = torch.ones(num_games, dtype=torch.uint8, device=dev)
+    bufs, played = [], 0
+    limit = max_steps if max_steps and max_steps > 0 else None
+    while True:
+        T = _CHUNK if limit is None else min(_CHUNK, limit - played)
+        if T <= 0:
+            break
+        bufs.append(rollout(policy, boards, T, seed=seed, env0=env0, ctr0=1 + played, auto_reset=False, alive=alive))
+        played += T
+        if not bool(alive.any()):
+            break
+    return _episode_dicts(bufs, boards, dev)
+
+
+def smoke(dev) -> None:
+    """Tiny fused rollout on `dev`, checked against the oracle env and the torch policy."""
+    from oracle import oracle as O
+    from .policy import GameMLP, MLPConfig
+    torch.manual_seed(0)
+    model = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.0)).to(dev).eval()
+    B, T, seed = 300, 24, 7
+    boards = env.reset(B, device=dev, seed=seed, env0=0, ctr=0)
+    start = boards.clone()
+    buf = rollout(pack_policy(model), boards, T, seed=seed, env0=0, ctr0=1, auto_reset=False,
+                  alive=torch.ones(B, dtype=torch.uint8, device=dev))
+    b = start.cpu().numpy().view(np.uint64)
+    for t in range(T):
+        valid = (buf.flags[t].cpu().numpy() & 0x80) != 0
+        np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64)[valid], b[valid])
+        nb, info = O.step_batch(b, buf.actions[t].cpu().numpy(), seed=seed, env0=0, ctr=1 + t)
+        np.testing.assert_array_equal(buf.points[t].cpu().numpy()[valid], info["points"][valid])
+        with torch.no_grad():
+            logits, v = model(env.encode(buf.boards[t]))
+        lm = buf.legal[t].long()
+        illegal = ((lm[:, None] >> torch.arange(4, device=dev)) & 1) == 0
+        ref = torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1)
+        vt = torch.from_numpy(valid).to(dev)
+        fin = torch.isfinite(ref) & vt[:, None]
+        assert torch.allclose(buf.logp[t][fin], ref[fin], rtol=1e-4, atol=1e-4)
+        assert torch.allclose(buf.value[t][vt], v.squeeze(1)[vt], rtol=1e-4, atol=1e-4)
+        b = np.where(valid, nb, b)

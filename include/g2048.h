@@ -130,6 +130,50 @@ int g2048_ppo_loss(const float* logits, const float* value, const float* old_log
                    const float* g_norm, int64_t n, float clip_eps, float c_v, float beta_ent, float inv_n,
                    float* dlogits, float* dvalue, double* stats_out, void* workspace, void* stream);
 
+/* ---- fused actor-critic rollout ------------------------------------------------------------
+ * Replaces the loop of train.py:213-345 (play_game_for_episode) for B environments at once and
+ * is what batched_rollout.play_games_batched (the module train.py:30 imports) is built on.
+ *
+ * Policy = the reference's GameMLP (game.py:1049-1220) in eval mode.  g2048_mlp_pack converts
+ * its state_dict tensors (device pointers, row-major as torch stores them) into the kernel's
+ * layout: stem.0.weight [h,48], stem.1.{weight,bias} [h], per block mlp.0.weight [h,h] and
+ * mlp.1.{weight,bias} [h] (host arrays of `layers` device pointers), action_head.{weight [4,h],
+ * bias [4]}, value_head.{weight [1,h], bias [1]}.  hidden <= 208, layers <= 8.
+ * g2048_mlp_packed_floats returns the number of floats `packed` must hold (or -1). */
+int64_t g2048_mlp_packed_floats(int32_t hidden, int32_t layers);
+int g2048_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
+                   const float* const* block_w, const float* const* block_ln_w, const float* const* block_ln_b,
+                   const float* action_w, const float* action_b, const float* value_w, const float* value_b,
+                   float* packed, void* stream);
+
+typedef struct G2048Rollout {
+    int64_t B;                 /* environments */
+    int32_t T;                 /* steps played by this call */
+    int32_t hidden, layers;    /* GameMLP shape (MLPConfig.hidden_dim / num_layers) */
+    int32_t auto_reset;        /* 1: a finished game restarts at once (fixed [T,B] rollouts);
+                                  0: it goes idle and its remaining slots are invalid (play to the end) */
+    uint64_t seed, env0, ctr0; /* Philox key, id of env 0, counter of step 0 (step t uses ctr0+t):
+                                  words 0,1 = spawn, word 2 = action sample; resets use the key
+                                  seed ^ 0x9E3779B97F4A7C15 at the same counter, words 0..3 */
+    const float* packed_weights;
+    const void* lut;
+    uint64_t* boards;              /* [B] in: start boards, out: boards after the last step */
+    uint8_t* alive;                /* [B] in/out, may be NULL (= all alive); only used without auto_reset */
+    const uint8_t* forced_actions; /* [T,B] or NULL: replay these actions instead of sampling */
+    /* records, time-major [T,B] (train.py:299-326 StepData) */
+    uint64_t* rec_boards;   /* state_before */
+    uint8_t* rec_actions;   /* selected_direction */
+    uint8_t* rec_legal;     /* bit d: direction d legal in state_before (complement of action_mask) */
+    float* rec_logp;        /* [T,B,4] policy_logprobs: log_softmax of the masked logits, -inf where illegal */
+    float* rec_value;       /* predicted_future_value */
+    int32_t* rec_points;    /* points_earned */
+    uint64_t* rec_shaping;  /* packed G2048_SH_* record of the move */
+    uint8_t* rec_flags;     /* g2048_step flags of the move | G2048_FLAG_VALID */
+    float* rec_entropy;     /* entropy of the masked action distribution; may be NULL */
+} G2048Rollout;
+
+int g2048_rollout_mlp(const G2048Rollout* params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

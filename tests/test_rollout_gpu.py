@@ -1,0 +1,191 @@
+"""GPU parity of the fused rollout kernel (through the C ABI): replay of the reference's own
+play_game_for_episode trajectories, oracle env simulation, torch fp32 policy, determinism,
+shard invariance, sampling statistics and the play_games_batched drop-in schema."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rollout_as_tb  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+RESET_TWEAK = 0x9E3779B97F4A7C15
+SH_KEYS = ("mono_before", "mono_after", "empt_before", "empt_after", "max_tile_created", "smooth_before",
+           "smooth_after", "corner_before", "corner_after", "max_exp_before", "max_exp_after")
+
+
+def best_model(golden):
+    from g2048 import policy
+    g = golden("model_best")
+    m = policy.GameMLP(policy.MLPConfig(hidden_dim=int(g["hidden_dim"]), num_layers=int(g["num_layers"]), dropout=0.0))
+    m.load_state_dict(policy.load_state_dict_from_npz(g))
+    return m.cuda().eval()
+
+
+def random_model(h=196, L=2, seed=0):
+    from g2048 import policy
+    torch.manual_seed(seed)
+    return policy.GameMLP(policy.MLPConfig(hidden_dim=h, num_layers=L, dropout=0.0)).cuda().eval()
+
+
+def torch_policy_outputs(model, boards, legal):
+    from g2048 import env
+    with torch.no_grad():
+        logits, v = model(env.encode(boards.reshape(-1)))
+    illegal = ((legal.reshape(-1).long()[:, None] >> torch.arange(4, device=boards.device)) & 1) == 0
+    lp = torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1)
+    p = lp.exp()
+    ent = -(torch.where(p > 0, p * lp, torch.zeros_like(p))).sum(-1)
+    return lp, v.squeeze(1), ent
+
+
+def test_replays_reference_play_game_for_episode(golden):
+    """Same weights, same Philox spawn draws, the reference's sampled actions forced: every StepData
+    field the reference recorded must come back (ints bit-exact, floats to 1e-5)."""
+    from g2048 import env, rollout
+    g = golden("rollout")
+    a, (t, e) = rollout_as_tb(g)
+    T, B = a["flags"].shape
+    seed = int(g["seed"])
+    model = best_model(golden)
+    boards = env.reset(B, device=0, seed=seed, env0=0, ctr=0)
+    forced = torch.from_numpy(a["action"]).cuda()
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=0, ctr0=1, auto_reset=False,
+                          alive=torch.ones(B, dtype=torch.uint8, device="cuda"), forced_actions=forced)
+    h = lambda x: x.cpu().numpy()
+    np.testing.assert_array_equal(h(buf.boards)[t, e].view(np.uint64), g["board"])
+    np.testing.assert_array_equal(h(buf.legal)[t, e], g["legal"])
+    np.testing.assert_array_equal(h(buf.points)[t, e], g["points"])
+    fl = h(buf.flags)[t, e]
+    assert (fl & 0x80).all()
+    np.testing.assert_array_equal((fl >> 4) & 1, g["done"])
+    sh = env.decode_shaping(h(buf.shaping)[t, e])
+    done = g["done"].astype(bool)
+    np.testing.assert_array_equal(sh["mono_before"], g["mono_before"])
+    np.testing.assert_array_equal(np.where(done, 0, sh["mono_after"]), g["mono_after"])      # train.py:318
+    np.testing.assert_array_equal(sh["empt_before"], g["empt_before"])
+    np.testing.assert_array_equal(np.where(done, 0, sh["empt_after"]), g["empt_after"])      # train.py:322
+    np.testing.assert_array_equal(sh["max_tile_created"], g["max_tile_created"])
+    np.testing.assert_array_equal(sh["smooth_after"] - sh["smooth_before"], g["smooth_delta"])
+    np.testing.assert_array_equal(sh["corner_after"] - sh["corner_before"], g["corner_delta"])
+    lp, ref = h(buf.logp)[t, e], g["logp"]
+    np.testing.assert_array_equal(np.isinf(lp), np.isinf(ref))
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(lp[fin], ref[fin], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(h(buf.value)[t, e], g["value"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(h(buf.entropy)[t, e], g["entropy"], rtol=1e-4, atol=2e-5)
+    # games that ended by `done` go idle: their later slots are invalid; final boards match
+    full = h(buf.flags)
+    for env_i, n in enumerate(g["ep_len"]):
+        if g["done"][(g["env"] == env_i)][-1]:
+            assert (full[n:, env_i] == 0).all()
+            assert h(boards).view(np.uint64)[env_i] == g["ep_final"][env_i]
+
+
+@pytest.mark.parametrize("h,L,B,T", [(196, 2, 1000, 48), (64, 1, 130, 40), (128, 3, 257, 16), (192, 2, 128, 8)])
+def test_rollout_matches_oracle_env_and_torch_policy(h, L, B, T):
+    from g2048 import env, rollout
+    model = random_model(h, L, seed=h + L)
+    seed, env0 = 99, 12345
+    boards = env.reset(B, device=0, seed=seed, env0=env0, ctr=0)
+    start = boards.clone()
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=env0, ctr0=1, auto_reset=True)
+    b = start.cpu().numpy().view(np.uint64)
+    n_done = 0
+    for t in range(T):
+        np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64), b)
+        acts = buf.actions[t].cpu().numpy()
+        nb, info = O.step_batch(b, acts, seed=seed, env0=env0, ctr=1 + t)
+        assert (info["invalid"] == 0).all()                       # sampled actions are always legal
+        np.testing.assert_array_equal(buf.legal[t].cpu().numpy(), info["legal_before"])
+        np.testing.assert_array_equal(buf.points[t].cpu().numpy(), info["points"])
+        fl = buf.flags[t].cpu().numpy()
+        np.testing.assert_array_equal(fl, 0x80 | info["legal_after"] | (info["done"] << 4))
+        sh = env.decode_shaping(buf.shaping[t].cpu().numpy())
+        for k in SH_KEYS:
+            np.testing.assert_array_equal(sh[k], info[k], err_msg=k)
+        d = info["done"].astype(bool)
+        n_done += int(d.sum())
+        if d.any():   # auto-reset: fresh board from the reset key stream at the same counter
+            fresh = O.reset_batch(B, seed=seed ^ RESET_TWEAK, env0=env0, ctr=1 + t)
+            nb = np.where(d, fresh, nb)
+        b = nb
+    np.testing.assert_array_equal(boards.cpu().numpy().view(np.uint64), b)
+    lp, v, ent = torch_policy_outputs(model, buf.boards, buf.legal)
+    got = buf.logp.reshape(-1, 4)
+    fin = torch.isfinite(lp)
+    assert torch.equal(torch.isfinite(got), fin)
+    torch.testing.assert_close(got[fin], lp[fin], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(buf.value.reshape(-1), v, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(buf.entropy.reshape(-1), ent, rtol=1e-4, atol=2e-5)
+
+
+def test_rollout_is_deterministic_and_shard_invariant():
+    from g2048 import env, rollout
+    model = random_model(196, 2, seed=5)
+    pol = rollout.pack_policy(model)
+    B, T, seed = 640, 32, 4
+
+    def run(lo, hi):
+        boards = env.reset(hi - lo, device=0, seed=seed, env0=lo, ctr=0)
+        return rollout.rollout(pol, boards, T, seed=seed, env0=lo, ctr0=1, auto_reset=True), boards
+
+    whole, wb = run(0, B)
+    again, _ = run(0, B)
+    left, lb = run(0, 300)
+    right, rb = run(300, B)
+    for name in ("boards", "actions", "legal", "points", "shaping", "flags"):
+        assert torch.equal(getattr(whole, name), getattr(again, name)), name
+        assert torch.equal(getattr(whole, name), torch.cat([getattr(left, name), getattr(right, name)], dim=1)), name
+    assert torch.equal(wb, torch.cat([lb, rb]))
+    assert torch.equal(whole.logp, again.logp) and torch.equal(whole.value, again.value)
+
+
+def test_sampling_follows_the_policy_distribution():
+    from g2048 import env, rollout
+    model = random_model(196, 2, seed=11)
+    B, T = 8192, 16
+    boards = env.reset(B, device=0, seed=1, env0=0, ctr=0)
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=1, env0=0, ctr0=1, auto_reset=True)
+    p = buf.logp.reshape(-1, 4).exp().double()
+    a = buf.actions.reshape(-1).long()
+    assert bool((torch.gather(p, 1, a[:, None]) > 0).all())          # never an illegal action
+    expected = p.sum(0)
+    observed = torch.bincount(a, minlength=4).double()
+    var = (p * (1 - p)).sum(0)
+    z = (observed - expected) / var.sqrt()
+    assert float(z.abs().max()) < 5.0, (observed, expected, z)
+
+
+def test_play_games_batched_drop_in_schema(golden):
+    import batched_rollout
+    from g2048 import env
+    model = best_model(golden)
+    eps = batched_rollout.play_games_batched(model, num_games=5, max_steps=None, device=torch.device("cuda:0"), seed=3)
+    assert len(eps) == 5
+    for ep in eps:
+        moves = ep["moves"]
+        assert set(ep) == {"moves", "total_points", "total_steps", "final_state"}
+        assert ep["total_steps"] == len(moves) - 1                   # ended by `done` (train.py:334-343)
+        assert ep["total_points"] == sum(m["points_earned"] for m in moves)
+        assert not env.Game2048.state_has_next_step(ep["final_state"])
+        for i, m in enumerate(moves):
+            assert m["game_state"].shape == (48,) and m["game_state"].is_cuda
+            assert len(m["policy_logprobs"]) == 4 and len(m["action_mask"]) == 4
+            assert not m["action_mask"][m["selected_direction"]]
+            assert np.isfinite(m["policy_logprobs"][m["selected_direction"]])
+            if i + 1 < len(moves):
+                assert m["result_state"] == moves[i + 1]["state_before"]
+        assert moves[-1]["result_state"] == ep["final_state"]
+        assert moves[-1]["monotonicity_after"] == 0.0 and moves[-1]["emptiness_after"] == 0.0
+        # replay through the oracle with the recorded actions
+        b = np.array([O.pack_grid(moves[0]["state_before"])], dtype=np.uint64)
+        pre = O.expand4_batch(b)[0][0, moves[0]["selected_direction"]]
+        cells = lambda x: np.array(O.unpack_board(x)).reshape(-1)
+        diff = cells(pre) != np.array(moves[0]["result_state"]).reshape(-1)
+        assert diff.sum() == 1
+    capped = batched_rollout.play_games_batched(model, num_games=3, max_steps=10, device="cuda:0", seed=3)
+    assert all(len(ep["moves"]) == 10 and ep["total_steps"] == 10 for ep in capped)
+    with pytest.raises(RuntimeError):
+        batched_rollout.play_games_batched(model, num_games=1, device=None)
