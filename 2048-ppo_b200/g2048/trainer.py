@@ -1,0 +1,193 @@
+"""Rollout + update driver for the hot path (the caller of the kernels, kept thin).
+
+Mirrors what train.py's loop does per train step (train.py:1669-1737) with the batched engine:
+fused rollout -> rewards-to-go / advantage -> PPO-clip + critic + entropy update, with the
+reference's optimiser stack (Muon for 2-D weights + AdamW for 1-D, cosine schedule with warm-up,
+train.py:1587-1612).  Orchestration only: the reference's CLI, logging, evaluation and
+checkpointing are out of scope.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import dp, env, ppo, rollout
+from .policy import GameMLP, MLPConfig
+
+
+@dataclass
+class TrainConfig:
+    hidden_dim: int = 196
+    num_layers: int = 2
+    envs: int = 65536              # global env count (sharded over ranks)
+    horizon: int = 512             # steps per rollout
+    gamma: float = 0.99            # README flags (README.md:11-13)
+    rtg_beta: float = 0.99
+    points_weight: float = 0.10
+    mono_weight: float = 1.0
+    emptiness_weight: float = 0.0
+    entropy_strength: float = 0.02
+    critic_strength: float = 0.2
+    clip_eps: float = 0.2          # train.py:518
+    lr: float = 1e-3
+    critic_lr: float = 1e-4
+    weight_decay: float = 0.01
+    warmup_steps: int = 10
+    total_steps: int = 20000
+    epochs: int = 1
+    minibatches: int = 1           # optimizer steps per epoch (1 = full batch)
+    chunk: int = 1 << 20           # samples per forward/backward chunk (memory bound only)
+    seed: int = 2048
+    zero_heads: bool = True        # train.py:1559-1567
+    dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
+
+
+def cosine_with_warmup(warmup: int, total: int):
+    def f(step: int) -> float:
+        if step < warmup:
+            return step / max(1, warmup)
+        prog = (step - warmup) / max(1, total - warmup)
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
+    return f
+
+
+class MultiOptimizer:  # train.py:1232-1281
+    def __init__(self, *pairs):
+        self.optimizers = [p[0] for p in pairs]
+        self.schedulers = [p[1] for p in pairs]
+
+    def step(self):
+        for o in self.optimizers:
+            o.step()
+
+    def zero_grad(self):
+        for o in self.optimizers:
+            o.zero_grad(set_to_none=True)
+
+    def scheduler_step(self):
+        for s in self.schedulers:
+            if s is not None:
+                s.step()
+
+    def get_lr(self):
+        return [o.param_groups[0]["lr"] for o in self.optimizers]
+
+
+def make_optimizer(model: GameMLP, cfg: TrainConfig) -> MultiOptimizer:
+    o2, o1, v2, v1 = model.get_param_groups(cfg.critic_lr, cfg.lr)
+    adamw = torch.optim.AdamW([o1, v1], betas=(0.9, 0.999), weight_decay=cfg.weight_decay)
+    muon = torch.optim.Muon([o2, v2], adjust_lr_fn="match_rms_adamw", weight_decay=cfg.weight_decay)
+    sched = lambda opt: torch.optim.lr_scheduler.LambdaLR(opt, cosine_with_warmup(cfg.warmup_steps, cfg.total_steps))
+    return MultiOptimizer((muon, sched(muon)), (adamw, sched(adamw)))
+
+
+@dataclass
+class StepTimes:
+    rollout_ms: float = 0.0
+    advantage_ms: float = 0.0
+    update_ms: float = 0.0
+    allreduce_ms: float = 0.0
+    optimizer_ms: float = 0.0
+
+
+class Trainer:
+    def __init__(self, cfg: TrainConfig, device: torch.device, model: GameMLP | None = None):
+        self.cfg, self.device = cfg, env.init(device)
+        self.rank, self.world = dp.world()
+        self.lo, self.hi = dp.shard_range(cfg.envs, self.rank, self.world)
+        torch.manual_seed(cfg.seed)   # identical initial weights on every rank
+        self.model = model if model is not None else GameMLP(
+            MLPConfig(hidden_dim=cfg.hidden_dim, num_layers=cfg.num_layers, dropout=cfg.dropout))
+        self.model.to(self.device)
+        if cfg.zero_heads and model is None:
+            with torch.no_grad():
+                for t in (self.model.action_head.weight, self.model.action_head.bias,
+                          self.model.value_head.weight, self.model.value_head.bias):
+                    t.zero_()
+        self.opt = make_optimizer(self.model, cfg)
+        self.bucket = dp.FlatGradBucket(self.model.parameters())
+        self.moments = ppo.RtgMoments()
+        self.B = self.hi - self.lo
+        self.boards = env.reset(self.B, device=self.device, seed=cfg.seed, env0=self.lo, ctr=0)
+        self.ctr = 1
+        self.buf = rollout.RolloutBuffers.allocate(cfg.horizon, self.B, self.device)
+        self.times = StepTimes()
+        self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+
+    # -- phases ---------------------------------------------------------------------------
+    def collect(self) -> rollout.RolloutBuffers:
+        self.model.eval()
+        pol = rollout.pack_policy(self.model, self.device)
+        rollout.rollout(pol, self.boards, self.cfg.horizon, seed=self.cfg.seed, env0=self.lo, ctr0=self.ctr,
+                        auto_reset=True, out=self.buf)
+        self.ctr += self.cfg.horizon
+        return self.buf
+
+    def advantages(self, buf) -> dict:
+        c = self.cfg
+        mu_c, sd = self.moments.corrected(c.rtg_beta)
+        return ppo.rtg_advantage(buf.points, buf.shaping, buf.flags, buf.value, gamma=c.gamma,
+                                 w_points=c.points_weight, w_mono=c.mono_weight, w_empt=c.emptiness_weight,
+                                 mu_c=mu_c, stddev=sd)
+
+    def update(self, buf, adv) -> dict:
+        c = self.cfg
+        n_local = buf.flags.numel()
+        flat = lambda t, *s: t.reshape(n_local, *s)
+        boards, actions, legal, flags = flat(buf.boards), flat(buf.actions), flat(buf.legal), flat(buf.flags)
+        logp, a, g = flat(buf.logp, 4), flat(adv["adv"]), flat(adv["g_norm"])
+        counts = torch.tensor([float(n_local)], dtype=torch.float64, device=self.device)
+        n_global = int(dp.allreduce_stats(counts).item())
+        self.model.train()
+        last = None
+        for _ in range(c.epochs):
+            order = None if c.minibatches == 1 else torch.randperm(n_local, device=self.device)
+            mb = (n_local + c.minibatches - 1) // c.minibatches
+            for m0 in range(0, n_local, mb):
+                m1 = min(n_local, m0 + mb)
+                n_mb_global = n_global if c.minibatches == 1 else (m1 - m0) * self.world
+                self.opt.zero_grad()
+                tot = torch.zeros(4, dtype=torch.float64, device=self.device)
+                for c0 in range(m0, m1, c.chunk):
+                    sl = slice(c0, min(m1, c0 + c.chunk)) if order is None else order[c0:min(m1, c0 + c.chunk)]
+                    logits, v = self.model(env.encode(boards[sl]))
+                    loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],
+                                               clip_eps=c.clip_eps, critic_strength=c.critic_strength,
+                                               entropy_strength=c.entropy_strength, n_total=n_mb_global)
+                    loss.backward()
+                    tot += stats
+                self.bucket.allreduce()
+                gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)   # train.py:561
+                self.opt.step()
+                last = (tot, gn)
+        self.opt.scheduler_step()                                                   # train.py:625
+        tot = dp.allreduce_stats(last[0].clone())
+        out = ppo.loss_stats(tot, c.critic_strength, c.entropy_strength)
+        out["grad_norm"] = float(last[1])
+        return out
+
+    def finish_moments(self, adv) -> None:
+        s = dp.allreduce_stats(adv["stats"].clone())
+        s1, s2, n = s.tolist()
+        self.moments.update(self.cfg.rtg_beta, s1, s2, n)
+
+    # -- one train step -------------------------------------------------------------------
+    def train_step(self) -> dict:
+        e = self._ev
+        e[0].record()
+        buf = self.collect()
+        e[1].record()
+        adv = self.advantages(buf)
+        e[2].record()
+        stats = self.update(buf, adv)
+        e[3].record()
+        self.finish_moments(adv)
+        e[4].record()
+        torch.cuda.synchronize(self.device)
+        self.times = StepTimes(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3]),
+                               e[3].elapsed_time(e[4]), 0.0)
+        stats["env_steps"] = buf.flags.numel() * self.world
+        stats["mean_points_per_step"] = float(buf.points.float().mean())
+        return stats

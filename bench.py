@@ -164,6 +164,62 @@ def run_reference(args):
     }))
 
 
+def rollout_section(args, dev, world, rank, barrier):
+    """Config C3 (per GPU; C4 when world > 1): GameMLP h=196 L=2, 65536 envs x 512 steps, Kaiming init
+    with non-zero heads, README reward flags.  Times the fused rollout kernel alone and the full
+    rollout + advantage + update (+ gradient / moment all-reduce) train step."""
+    import torch
+    import torch.distributed as dist
+
+    from g2048 import trainer as tr
+
+    envs_per_gpu, horizon = args.rollout_envs, args.rollout_steps
+    cfg = tr.TrainConfig(hidden_dim=196, num_layers=2, envs=envs_per_gpu * world, horizon=horizon, zero_heads=False,
+                         seed=2048)
+    t = tr.Trainer(cfg, dev)
+    n_local = envs_per_gpu * horizon
+    # rollout only
+    t.collect()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    ev0.record()
+    for _ in range(reps):
+        t.collect()
+    ev1.record()
+    barrier()
+    ro_ms = ev0.elapsed_time(ev1) / reps
+    # rollout + update
+    t.train_step()
+    barrier()
+    ev0.record()
+    for _ in range(reps):
+        stats = t.train_step()
+    ev1.record()
+    barrier()
+    step_ms = ev0.elapsed_time(ev1) / reps
+    times = t.times
+    if world > 1:
+        v = torch.tensor([ro_ms, step_ms], device=dev)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ro_ms, step_ms = (float(x) for x in v.tolist())
+    flops = 2 * (48 * 196 + 2 * 196 * 196 + 5 * 196)
+    env_sps = world * n_local / (ro_ms * 1e-3)
+    return {
+        "workload": f"c3: GameMLP h=196 L=2 fused rollout, {envs_per_gpu} envs x {horizon} steps per GPU, auto-reset, Philox seed 2048",
+        "env_steps_per_sec": env_sps,
+        "rollout_ms": ro_ms,
+        "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
+        "train_step_ms": step_ms,
+        "phase_ms_rank0": {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
+                           "moments_allreduce": times.allreduce_ms},
+        "model_flops_per_env_step": flops,
+        "rollout_fp32_tflops": env_sps * flops / 1e12,
+        "grad_allreduce_bytes": 88401 * 4,
+        "loss": stats["loss"],
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -259,6 +315,11 @@ def run_ours(args):
     h2d = N_TRANS * (8 + 1)
     d2h = N_TRANS * (8 + 4 + 1 + 8)
 
+    # ---- C3 / C4: fused MLP rollout (65536 envs x 512 steps per GPU) and rollout+update
+    ro = None
+    if not args.no_rollout:
+        ro = rollout_section(args, dev, world, rank, barrier)
+
     if rank == 0:
         peak, which = peaks()
         achieved = BYTES_PER_TRANSITION * N_TRANS / (ms_per_step * 1e-3) / 1e9
@@ -277,6 +338,8 @@ def run_ours(args):
                          "traffic": None, "peak_source": which, "kernel": "step_kernel_staged<true>",
                          "bytes_per_unit": BYTES_PER_TRANSITION, "units_per_launch": N_TRANS},
         }
+        if ro is not None:
+            line["rollout"] = ro
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line))
@@ -292,6 +355,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-rollout", action="store_true", help="skip the C3 rollout / update section")
+    ap.add_argument("--rollout-envs", type=int, default=65536)
+    ap.add_argument("--rollout-steps", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
