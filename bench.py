@@ -278,7 +278,32 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * N_TRANS * args.steps / (ms * 1e-3)
 
-    # ---- e2e: host pinned buffers, copies inside the timed region, through env.step
+    e2e_value = e2e_ms = None
+    e2e_steps = 0
+    h2d = N_TRANS * (8 + 1)
+    d2h = N_TRANS * (8 + 4 + 1 + 8)
+    if not args.no_e2e:
+        e2e_value, e2e_ms, e2e_steps = e2e_section(args, dev, world, rank, barrier, sets, env0)
+
+    # ---- C3 / C4: fused MLP rollout (65536 envs x 512 steps per GPU) and rollout+update
+    ro = None
+    if not args.no_rollout:
+        ro = rollout_section(args, dev, world, rank, barrier)
+
+    if rank == 0:
+        finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_section(args, dev, world, rank, barrier, sets, env0):
+    """Same metric through the public host API with HOST pinned buffers: every step copies the
+    inputs host->device, runs g2048_step and copies every output device->host."""
+    import torch
+    import torch.distributed as dist
+
+    from g2048 import env
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     hb, ha = c2_transitions(4242 + rank)
     h_boards, h_actions = torch.from_numpy(hb).pin_memory(), torch.from_numpy(ha).pin_memory()
     h_out = dict(boards=torch.empty(N_TRANS, dtype=torch.int64).pin_memory(),
@@ -306,21 +331,17 @@ def run_ours(args):
         e2e_step(k)
     ev1.record()
     barrier()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    e2e_ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * N_TRANS * e2e_steps / (e2e_ms * 1e-3)
-    h2d = N_TRANS * (8 + 1)
-    d2h = N_TRANS * (8 + 4 + 1 + 8)
+    return e2e_value, e2e_ms, e2e_steps
 
-    # ---- C3 / C4: fused MLP rollout (65536 envs x 512 steps per GPU) and rollout+update
-    ro = None
-    if not args.no_rollout:
-        ro = rollout_section(args, dev, world, rank, barrier)
 
-    if rank == 0:
+def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING):
+    if True:
         peak, which = peaks()
         achieved = BYTES_PER_TRANSITION * N_TRANS / (ms_per_step * 1e-3) / 1e9
         line = {
@@ -332,7 +353,7 @@ def run_ours(args):
                        "spawn": "philox4x32-10"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": (e2e_ms / e2e_steps) if e2e_steps else None},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": which, "kernel": "step_kernel_staged<true>",
@@ -343,8 +364,6 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -356,6 +375,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-rollout", action="store_true", help="skip the C3 rollout / update section")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     ap.add_argument("--rollout-envs", type=int, default=65536)
     ap.add_argument("--rollout-steps", type=int, default=512)
     args = ap.parse_args()
