@@ -18,6 +18,44 @@
 
 namespace g2048 {
 
+// ------------------------------------------------------------------ pipe balancing
+// The env kernels are bound by the integer ALU pipe (LOP3/SHF/PRMT; ncu: 91 % busy) while the
+// FMA pipe idles.  A shift by a constant is also a multiply: x << s = x * 2^s (IMAD) and
+// x >> s = umulhi(x, 2^(32-s)) (IMAD.HI), both issued on the FMA pipe.  The powers of two come
+// from constant memory so that ptxas cannot turn them back into shifts.
+#ifndef G2048_SHIFT_ON_FMA
+#define G2048_SHIFT_ON_FMA 0   // measured on B200 (r01): 119.1 us vs 115.1 us per 4.19M transitions -> off
+#endif
+static __constant__ uint32_t kPow2[33] = {
+    1u << 0,  1u << 1,  1u << 2,  1u << 3,  1u << 4,  1u << 5,  1u << 6,  1u << 7,  1u << 8,  1u << 9,  1u << 10,
+    1u << 11, 1u << 12, 1u << 13, 1u << 14, 1u << 15, 1u << 16, 1u << 17, 1u << 18, 1u << 19, 1u << 20, 1u << 21,
+    1u << 22, 1u << 23, 1u << 24, 1u << 25, 1u << 26, 1u << 27, 1u << 28, 1u << 29, 1u << 30, 1u << 31, 0u};
+template <int S>
+__device__ __forceinline__ uint32_t shl(uint32_t x) {
+#if G2048_SHIFT_ON_FMA
+    return x * kPow2[S];
+#else
+    return x << S;
+#endif
+}
+template <int S>
+__device__ __forceinline__ uint32_t shr(uint32_t x) {
+#if G2048_SHIFT_ON_FMA
+    return __umulhi(x, kPow2[32 - S]);
+#else
+    return x >> S;
+#endif
+}
+// acc + (x << S) for fields that do not overlap acc (bit-field packing)
+template <int S>
+__device__ __forceinline__ uint32_t put(uint32_t acc, uint32_t x) {
+#if G2048_SHIFT_ON_FMA
+    return x * kPow2[S] + acc;
+#else
+    return acc | (x << S);
+#endif
+}
+
 // ------------------------------------------------------------------ row table
 // One u32 per 16-bit row (cell 0 in the low nibble), describing a LEFT move of
 // that row and its per-line potentials:
@@ -89,14 +127,14 @@ __device__ __forceinline__ bool same(Board a, Board b) { return ((a.lo ^ b.lo) |
 
 // 4x4 nibble transpose: 2x2 nibble blocks inside each half, then 2x2 blocks of bytes.
 __device__ __forceinline__ Board transpose(Board b) {
-    uint32_t a0 = (b.lo & 0xF0F00F0Fu) | ((b.lo & 0x0000F0F0u) << 12) | ((b.lo & 0x0F0F0000u) >> 12);
-    uint32_t a1 = (b.hi & 0xF0F00F0Fu) | ((b.hi & 0x0000F0F0u) << 12) | ((b.hi & 0x0F0F0000u) >> 12);
+    uint32_t a0 = (b.lo & 0xF0F00F0Fu) | shl<12>(b.lo & 0x0000F0F0u) | shr<12>(b.lo & 0x0F0F0000u);
+    uint32_t a1 = (b.hi & 0xF0F00F0Fu) | shl<12>(b.hi & 0x0000F0F0u) | shr<12>(b.hi & 0x0F0F0000u);
     return {__byte_perm(a0, a1, 0x6240), __byte_perm(a0, a1, 0x7351)};
 }
 
 // reverse the four nibbles of every 16-bit row
 __device__ __forceinline__ uint32_t rev_rows32(uint32_t x) {
-    uint32_t y = ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+    uint32_t y = shl<4>(x & 0x0F0F0F0Fu) | (shr<4>(x) & 0x0F0F0F0Fu);
     return __byte_perm(y, 0, 0x2301);
 }
 __device__ __forceinline__ Board rev_rows(Board b) { return {rev_rows32(b.lo), rev_rows32(b.hi)}; }
@@ -105,13 +143,13 @@ __device__ __forceinline__ Board rev_rows(Board b) { return {rev_rows32(b.lo), r
 // 0xD000 before and after a move (a merge raises an exponent by one), which the staged part
 // of the row table covers.
 __device__ __forceinline__ bool has_big_tile(Board b) {
-    return (((b.lo & (b.lo >> 1)) | (b.hi & (b.hi >> 1))) & 0x44444444u) != 0u;
+    return (((b.lo & shr<1>(b.lo)) | (b.hi & shr<1>(b.hi))) & 0x44444444u) != 0u;
 }
 
 // bit 4i set <=> nibble i is non-zero
 __device__ __forceinline__ uint32_t nz_flags32(uint32_t x) {
-    uint32_t y = x | (x >> 1);
-    return (y | (y >> 2)) & 0x11111111u;
+    uint32_t y = x | shr<1>(x);
+    return (y | shr<2>(y)) & 0x11111111u;
 }
 // bit 4i set <=> nibble i is zero
 __device__ __forceinline__ uint32_t z_flags32(uint32_t x) { return nz_flags32(x) ^ 0x11111111u; }
@@ -143,7 +181,7 @@ __device__ __forceinline__ uint32_t gather_byte3(Lines l) {
 // merge points / largest exponent created / overflow of one move, from the 4 moved lines
 __device__ __forceinline__ void merge_stats(Lines l, int& points, int& max_tile, bool& overflow) {
     uint32_t w = gather_byte2(l);  // per line: [c2 | c1]
-    uint32_t lo4 = w & 0x0F0F0F0Fu, hi4 = (w >> 4) & 0x0F0F0F0Fu;
+    uint32_t lo4 = w & 0x0F0F0F0Fu, hi4 = shr<4>(w) & 0x0F0F0F0Fu;
     uint32_t sum = 0, any = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -165,17 +203,17 @@ __device__ __forceinline__ uint32_t legal_mask(Board b) {
     uint32_t nzl = nz_flags32(b.lo), nzh = nz_flags32(b.hi);
     uint32_t el = nzl ^ 0x11111111u, eh = nzh ^ 0x11111111u;
     // horizontal neighbours (c, c+1), c = 0..2
-    uint32_t dl = b.lo ^ (b.lo >> 4), dh = b.hi ^ (b.hi >> 4);
+    uint32_t dl = b.lo ^ shr<4>(b.lo), dh = b.hi ^ shr<4>(b.hi);
     uint32_t mh = ((z_flags32(dl) & nzl) | (z_flags32(dh) & nzh)) & 0x01110111u;
     // vertical neighbours (r, r+1), r = 0..2
     uint32_t lo16 = __funnelshift_r(b.lo, b.hi, 16);
-    uint32_t vl = b.lo ^ lo16, vh = b.hi ^ (b.hi >> 16);
+    uint32_t vl = b.lo ^ lo16, vh = b.hi ^ shr<16>(b.hi);
     uint32_t mv = (z_flags32(vl) & nzl) | (z_flags32(vh) & nzh & 0x00001111u);
-    uint32_t left = ((el & (nzl >> 4)) | (eh & (nzh >> 4))) & 0x01110111u;
-    uint32_t right = ((el & (nzl << 4)) | (eh & (nzh << 4))) & 0x11101110u;
+    uint32_t left = ((el & shr<4>(nzl)) | (eh & shr<4>(nzh))) & 0x01110111u;
+    uint32_t right = ((el & shl<4>(nzl)) | (eh & shl<4>(nzh))) & 0x11101110u;
     uint32_t nz16 = __funnelshift_r(nzl, nzh, 16);
-    uint32_t up = (el & nz16) | (eh & (nzh >> 16));
-    uint32_t down = (eh & nz16) | (el & (nzl << 16));
+    uint32_t up = (el & nz16) | (eh & shr<16>(nzh));
+    uint32_t down = (eh & nz16) | (el & shl<16>(nzl));
     uint32_t m = 0;
     if (up | mv) m |= 1u;
     if (down | mv) m |= 2u;
@@ -197,7 +235,7 @@ struct Potentials {
 __device__ __forceinline__ void ge_le_sums(Lines l, uint32_t& ge, uint32_t& le) {
     uint32_t w = gather_byte3(l);
     ge = __vsadu4(w & 0x03030303u, 0u);
-    le = __vsadu4((w >> 2) & 0x03030303u, 0u);
+    le = __vsadu4(shr<2>(w) & 0x03030303u, 0u);
 }
 
 // -smoothness: sum of |a-b| over the 24 neighbour pairs with both cells non-zero.
@@ -205,20 +243,20 @@ __device__ __forceinline__ void ge_le_sums(Lines l, uint32_t& ge, uint32_t& le) 
 // native 4-way byte abs-diff applies; `nz*` are the nibble non-zero flags of the board.
 __device__ __forceinline__ int smoothness_abs(Board b, uint32_t nzl, uint32_t nzh) {
     const uint32_t M = 0x0F0F0F0Fu;
-    uint32_t El = b.lo & M, Ol = (b.lo >> 4) & M, Eh = b.hi & M, Oh = (b.hi >> 4) & M;
+    uint32_t El = b.lo & M, Ol = shr<4>(b.lo) & M, Eh = b.hi & M, Oh = shr<4>(b.hi) & M;
     // 0x0F in every byte lane whose cell is non-zero
-    uint32_t mEl = (nzl & 0x01010101u) * 15u, mOl = ((nzl >> 4) & 0x01010101u) * 15u;
-    uint32_t mEh = (nzh & 0x01010101u) * 15u, mOh = ((nzh >> 4) & 0x01010101u) * 15u;
+    uint32_t mEl = (nzl & 0x01010101u) * 15u, mOl = (shr<4>(nzl) & 0x01010101u) * 15u;
+    uint32_t mEh = (nzh & 0x01010101u) * 15u, mOh = (shr<4>(nzh) & 0x01010101u) * 15u;
     // horizontal (c0,c1) and (c2,c3)
     uint32_t acc = (__vabsdiffu4(El, Ol) & mEl & mOl) + (__vabsdiffu4(Eh, Oh) & mEh & mOh);
     // horizontal (c1,c2): O byte k against E byte k+1, valid in byte lanes 0 and 2
-    acc += (__vabsdiffu4(Ol, El >> 8) & mOl & (mEl >> 8) & 0x000F000Fu) +
-           (__vabsdiffu4(Oh, Eh >> 8) & mOh & (mEh >> 8) & 0x000F000Fu);
+    acc += (__vabsdiffu4(Ol, shr<8>(El)) & mOl & shr<8>(mEl) & 0x000F000Fu) +
+           (__vabsdiffu4(Oh, shr<8>(Eh)) & mOh & shr<8>(mEh) & 0x000F000Fu);
     // vertical: rows (0,1),(1,2) live in lo vs funnel(lo,hi); rows (2,3) in hi vs hi>>16
     uint32_t Em = __funnelshift_r(El, Eh, 16), Om = __funnelshift_r(Ol, Oh, 16);
     uint32_t mEm = __funnelshift_r(mEl, mEh, 16), mOm = __funnelshift_r(mOl, mOh, 16);
     acc += (__vabsdiffu4(El, Em) & mEl & mEm) + (__vabsdiffu4(Ol, Om) & mOl & mOm);
-    acc += (__vabsdiffu4(Eh, Eh >> 16) & mEh & (mEh >> 16)) + (__vabsdiffu4(Oh, Oh >> 16) & mOh & (mOh >> 16));
+    acc += (__vabsdiffu4(Eh, shr<16>(Eh)) & mEh & shr<16>(mEh)) + (__vabsdiffu4(Oh, shr<16>(Oh)) & mOh & shr<16>(mOh));
     return int(__vsadu4(acc, 0u));   // <= 8 terms of <= 15 per byte lane: no carry between lanes
 }
 
@@ -231,7 +269,7 @@ __device__ __forceinline__ Potentials potentials(Board b, Lines rows, Lines cols
     ge_le_sums(rows, hge, hle);
     ge_le_sums(cols, vge, vle);
     int pairs = int(max(hge, hle) + max(vge, vle));   // == best of the four rotations
-    uint32_t mx = max(max(rows.e0, rows.e1), max(rows.e2, rows.e3)) >> 28;
+    uint32_t mx = shr<28>(max(max(rows.e0, rows.e1), max(rows.e2, rows.e3)));
     uint32_t nzl = nz_flags32(b.lo), nzh = nz_flags32(b.hi);
     p.empt = 16 - __popc(nzl) - __popc(nzh);
     p.max_exp = int(mx);
@@ -277,7 +315,7 @@ __device__ __forceinline__ U4 env_draws(uint64_t seed, uint64_t env_id, uint64_t
 __device__ __forceinline__ Board spawn_tile(Board b, uint32_t u0, uint32_t u1) {
     uint32_t zl = z_flags32(b.lo), zh = z_flags32(b.hi);
     uint32_t pl = zl * 0x11111111u;            // nibble i = #empty cells among nibbles 0..i (<= 8)
-    uint32_t nl = pl >> 28, n = nl + __popc(zh);
+    uint32_t nl = shr<28>(pl), n = nl + __popc(zh);
     uint32_t k = __umulhi(u0, n);
     bool in_lo = k < nl;
     uint32_t z = in_lo ? zl : zh;
@@ -349,11 +387,17 @@ __device__ __forceinline__ StepOut env_step(Board b, uint32_t action, uint32_t u
         Board cross = (action & 2u) ? bt : b;
         Potentials pb = potentials(b, mv, lookup_rows(cross, lut));
         Potentials pa = potentials(moved, lookup_rows(moved_c, lut), lookup_rows(transpose(moved_c), lut));
-        uint32_t lo = uint32_t(pb.mono) | uint32_t(pa.mono) << 6 | uint32_t(pb.empt) << 12 |
-                      uint32_t(pa.empt) << 17 | uint32_t(max_tile) << 22 | uint32_t(pb.max_exp) << 27 |
-                      uint32_t(pb.in_corner) << 31;
-        uint32_t hi = uint32_t(pa.max_exp) | uint32_t(pa.in_corner) << 4 | uint32_t(pb.smooth_abs) << 5 |
-                      uint32_t(pa.smooth_abs) << 14;
+        uint32_t lo = uint32_t(pb.mono);
+        lo = put<6>(lo, uint32_t(pa.mono));
+        lo = put<12>(lo, uint32_t(pb.empt));
+        lo = put<17>(lo, uint32_t(pa.empt));
+        lo = put<22>(lo, uint32_t(max_tile));
+        lo = put<27>(lo, uint32_t(pb.max_exp));
+        lo = put<31>(lo, uint32_t(pb.in_corner));
+        uint32_t hi = uint32_t(pa.max_exp);
+        hi = put<4>(hi, uint32_t(pa.in_corner));
+        hi = put<5>(hi, uint32_t(pb.smooth_abs));
+        hi = put<14>(hi, uint32_t(pa.smooth_abs));
         o.shape_lo = valid ? lo : 0u;
         o.shape_hi = valid ? hi : 0u;
     }

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libg2048.so")
+LIB_PATH = os.environ.get("G2048_LIB", os.path.join(HERE, "libg2048.so"))   # override: A/B builds only
 
 
 class G2048Error(RuntimeError):

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
-LIB = os.path.join(HERE, "libg2048.so")
+LIB = os.environ.get("G2048_LIB", os.path.join(HERE, "libg2048.so"))
 SOURCES = ["g2048_host.cu", "g2048_env.cu", "g2048_train.cu", "g2048_rollout.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -44,7 +44,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp", *sources()]
+    extra = os.environ.get("G2048_NVCC_DEFS", "").split()      # e.g. -DG2048_SHIFT_ON_FMA=0 for A/B runs
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp", *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -278,6 +278,30 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * N_TRANS * args.steps / (ms * 1e-3)
 
+    # ---- C2 in its 4-move expansion form (g2048_expand4: all four pre-spawn successors per board)
+    ex_sets = [dict(succ=torch.empty((N_BOARDS, 4), dtype=torch.int64, device=dev),
+                    points=torch.empty((N_BOARDS, 4), dtype=torch.int32, device=dev),
+                    legal=torch.empty(N_BOARDS, dtype=torch.uint8, device=dev), max_tile=None) for _ in range(RING * 2)]
+    ex_in = [s["boards"][:N_BOARDS] for s in sets] + [s["out"]["boards"][:N_BOARDS] for s in sets]
+    for k in range(3):
+        env.expand4(ex_in[k], out=ex_sets[k])
+    barrier()
+    ex_steps = max(args.steps, 20)
+    ev0.record()
+    for k in range(ex_steps):
+        env.expand4(ex_in[k % len(ex_in)], out=ex_sets[k % len(ex_sets)])
+    ev1.record()
+    barrier()
+    ex_ms = ev0.elapsed_time(ev1) / ex_steps
+    if world > 1:
+        t = torch.tensor([ex_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ex_ms = float(t.item())
+    expand = {"ms_per_launch": ex_ms, "boards_per_launch": N_BOARDS,
+              "transitions_per_sec": world * N_BOARDS * 4 / (ex_ms * 1e-3),
+              "bytes_per_board": 57, "achieved_gbs": 57 * N_BOARDS / (ex_ms * 1e-3) / 1e9,
+              "l2": "12 distinct input / output sets (57 MiB each) used round-robin"}
+
     e2e_value = e2e_ms = None
     e2e_steps = 0
     h2d = N_TRANS * (8 + 1)
@@ -291,7 +315,7 @@ def run_ours(args):
         ro = rollout_section(args, dev, world, rank, barrier)
 
     if rank == 0:
-        finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING)
+        finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING, expand)
     if world > 1:
         dist.destroy_process_group()
 
@@ -340,9 +364,10 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
     return e2e_value, e2e_ms, e2e_steps
 
 
-def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING):
+def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING, expand):
     if True:
         peak, which = peaks()
+        expand["frac_of_hbm_peak"] = expand["achieved_gbs"] / peak
         achieved = BYTES_PER_TRANSITION * N_TRANS / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -359,6 +384,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
                          "traffic": None, "peak_source": which, "kernel": "step_kernel_staged<true>",
                          "bytes_per_unit": BYTES_PER_TRANSITION, "units_per_launch": N_TRANS},
         }
+        line["expand4"] = expand
         if ro is not None:
             line["rollout"] = ro
         if world == 1 and not args.no_cpu:
