@@ -1,0 +1,81 @@
+// g2048_tc.cu -- tcgen05 building block self-test: C[128][N] = A[128][K] * W[N][K]^T with bf16
+// operands staged in 128B-swizzled K-major shared memory and the fp32 accumulator in TMEM.
+// Exists to pin the descriptor / swizzle / TMEM conventions of g2048_tc.cuh on real hardware
+// (tests/test_tc_gpu.py) before the fused rollout kernel relies on them.
+#include "g2048_host.h"
+#include "g2048_tc.cuh"
+
+namespace g2048 {
+
+__global__ void __launch_bounds__(128, 1)
+tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C, int K, int N) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int kblocks = (K + tc::BLOCK_K - 1) / tc::BLOCK_K;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + size_t(kblocks) * 128 * 128;
+    const uint32_t bytes_a = uint32_t(kblocks) * 128u * 128u, bytes_b = uint32_t(kblocks) * uint32_t(N) * 128u;
+
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_fence_init();
+    }
+    for (uint32_t i = tid * 16; i < bytes_a + bytes_b; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16*>(sA + tc::sw128_offset(128, r, k)) = __float2bfloat16(A[i]);
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int r = i / K, k = i % K;
+        *reinterpret_cast<__nv_bfloat16*>(sB + tc::sw128_offset(N, r, k)) = __float2bfloat16(W[i]);
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+        tc::fence_after_sync();
+        const uint32_t idesc = tc::make_idesc_bf16(128, N);
+        const uint32_t a0 = tc::smem_addr(sA), b0 = tc::smem_addr(sB);
+        for (int ks = 0; ks < K / tc::UMMA_K; ++ks) {
+            const uint32_t blk = ks >> 2, j = ks & 3;
+            tc::mma_bf16_ss(tmem_base, tc::make_desc_sw128(a0 + blk * 128u * 128u + j * 32u),
+                            tc::make_desc_sw128(b0 + blk * uint32_t(N) * 128u + j * 32u), idesc, ks > 0);
+        }
+        tc::mma_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) C[size_t(tid) * N + c0 + j] = v[j];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace g2048
+
+extern "C" int g2048_tc_gemm_selftest(const float* A, const float* W, float* C, int32_t K, int32_t N, void* stream) {
+    using namespace g2048;
+    G2048_REQUIRE(A && W && C, "g2048_tc_gemm_selftest: NULL pointer argument");
+    G2048_REQUIRE(K >= 16 && K <= 256 && K % 16 == 0, "g2048_tc_gemm_selftest: K must be a multiple of 16 in [16,256]");
+    G2048_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "g2048_tc_gemm_selftest: N must be a multiple of 16 in [16,256]");
+    const int kblocks = (K + 63) / 64;
+    const int smem = kblocks * 128 * (128 + N);
+    G2048_REQUIRE(smem <= 220 * 1024, "g2048_tc_gemm_selftest: tile does not fit shared memory");
+    G2048_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_gemm_selftest_kernel<<<1, 128, smem, cudaStream_t(stream)>>>(A, W, C, K, N);
+    G2048_CHECK_LAUNCH("tc_gemm_selftest_kernel");
+    return G2048_OK;
+}

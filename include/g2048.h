@@ -174,6 +174,11 @@ typedef struct G2048Rollout {
 
 int g2048_rollout_mlp(const G2048Rollout* params, void* stream);
 
+/* tcgen05 building-block self-test (not part of the reference's interface): C[128,N] =
+ * A[128,K] * W[N,K]^T with bf16-rounded operands and fp32 accumulation in tensor memory.
+ * K, N multiples of 16, <= 256.  Pins the UMMA descriptor / swizzle conventions on hardware. */
+int g2048_tc_gemm_selftest(const float* A, const float* W, float* C, int32_t K, int32_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
