@@ -20,54 +20,10 @@
 // shared memory k-major (X[k][env]) so both operands are conflict-free 128-bit loads.
 // fp32 accumulation keeps the recorded log-probs / values within ~1e-6 of the torch model.
 #include <cmath>
-#include "g2048_device.cuh"
-#include "g2048_host.h"
+#include <cuda_bf16.h>
+#include "g2048_rollout.cuh"
 
 namespace g2048 {
-
-constexpr int RO_TILE = 128;          // envs per tile
-constexpr int RO_CONSUMERS = 256;     // GEMM threads
-constexpr int RO_THREADS = RO_CONSUMERS + 32;   // + producer warp
-constexpr int RO_KC = 16;             // k rows per weight chunk
-constexpr int RO_STAGES = 4;
-constexpr uint64_t RESET_KEY_TWEAK = 0x9E3779B97F4A7C15ull;   // key stream of the auto-reset draws
-
-struct RolloutParams {
-    int64_t B;
-    int32_t T, hidden, layers, auto_reset;
-    uint64_t seed, env0, ctr0;
-    const float* packed;
-    const uint32_t* lut;
-    uint64_t* boards;              // in/out [B]
-    uint8_t* alive;                // in/out [B] or NULL
-    const uint8_t* forced_actions; // [T,B] or NULL
-    uint64_t* rec_boards;
-    uint8_t* rec_actions;
-    uint8_t* rec_legal;
-    float* rec_logp;               // [T,B,4]
-    float* rec_value;
-    int32_t* rec_points;
-    uint64_t* rec_shaping;
-    uint8_t* rec_flags;
-    float* rec_entropy;            // or NULL
-};
-
-// packed weight layout (floats), HP = padded hidden
-__host__ __device__ inline int64_t pk_stem_w(int) { return 0; }
-__host__ __device__ inline int64_t pk_stem_b0(int HP) { return int64_t(16) * HP; }
-__host__ __device__ inline int64_t pk_stem_g(int HP) { return int64_t(17) * HP; }
-__host__ __device__ inline int64_t pk_stem_beta(int HP) { return int64_t(18) * HP; }
-__host__ __device__ inline int64_t pk_layer(int HP, int l) { return int64_t(19) * HP + int64_t(l) * HP * (HP + 2); }
-__host__ __device__ inline int64_t pk_heads(int HP, int L) { return pk_layer(HP, L); }
-__host__ __device__ inline int64_t pk_total(int HP, int L) { return pk_heads(HP, L) + 5 * HP + 8; }
-
-__host__ __device__ inline int padded_hidden(int h) {
-    if (h <= 64) return 64;
-    if (h <= 128) return 128;
-    if (h <= 192) return 192;
-    if (h <= 208) return 208;
-    return -1;
-}
 
 // ------------------------------------------------------------------ weight packing
 struct PackSrc {
@@ -126,6 +82,36 @@ __global__ void pack_mlp_kernel(PackSrc s, int h, int HP, int L, float* __restri
             }
         }
         out[i] = v;
+    }
+}
+
+// bf16 operand images for the tensor-core kernel (layout: g2048_tc.cuh sw128_offset)
+__global__ void pack_mlp_images_kernel(PackSrc s, int h, int HP, int L, uint8_t* __restrict__ img) {
+    const int KB = kblocks_of(HP);
+    const int64_t stem_elems = int64_t(HP) * 64, layer_elems = int64_t(KB) * HP * 64;
+    const int64_t total = stem_elems + int64_t(L) * layer_elems;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        float v = 0.f;
+        uint8_t* base;
+        int n, k;
+        if (i < stem_elems) {
+            n = int(i / 64);
+            k = int(i % 64);
+            if (n < h && k < 16) v = s.stem_w[n * 48 + 3 * k];
+            base = img;
+        } else {
+            const int64_t r = i - stem_elems;
+            const int l = int(r / layer_elems);
+            const int64_t e = r % layer_elems;
+            n = int(e / (int64_t(KB) * 64));
+            k = int(e % (int64_t(KB) * 64));
+            if (n < h && k < h) v = s.blk_w[l][n * h + k];
+            base = img + img_stem_bytes(HP) + int64_t(l) * img_layer_bytes(HP);
+        }
+        const uint32_t blk = uint32_t(k) >> 6, kk = uint32_t(k) & 63u;
+        const uint32_t off = blk * uint32_t(HP) * 128u + uint32_t(n >> 3) * 1024u + uint32_t(n & 7) * 128u +
+                             (((kk >> 3) ^ uint32_t(n & 7)) << 4) + (kk & 7u) * 2u;
+        *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(v);
     }
 }
 
@@ -343,17 +329,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_mlp_kernel(RolloutParam
             const uint64_t ctr = p.ctr0 + uint64_t(t);
             uint32_t lm = 0;
             if (tid < RO_TILE) {
-                if (owner && alive) {
-                    lm = legal_mask(board);
-                    if (lm == 0u) {                              // terminal board handed in / left over
-                        if (p.auto_reset) {
-                            board = reset_board(env_draws(p.seed ^ RESET_KEY_TWEAK, p.env0 + uint64_t(env), ctr));
-                            lm = legal_mask(board);
-                        } else {
-                            alive = false;
-                        }
-                    }
-                }
+                if (owner) lm = begin_step(p, env, ctr, board, alive);
                 // model input: the 16 exponents (row/col features are folded into the stem bias)
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -404,76 +380,7 @@ __global__ void __launch_bounds__(RO_THREADS, 1) rollout_mlp_kernel(RolloutParam
                     for (int j = 0; j < 5; ++j) o[j] += S.headp[m][j] + S.headw[5 * HP + j];
                 }
                 // ---- policy + env step (one thread per env)
-                if (owner) {
-                    const int64_t ri = int64_t(t) * p.B + env;
-                    if (!alive) {
-                        p.rec_flags[ri] = 0;
-                        p.rec_boards[ri] = pack_board(board);
-                        p.rec_actions[ri] = 0;
-                        p.rec_legal[ri] = 0;
-                        p.rec_value[ri] = 0.f;
-                        p.rec_points[ri] = 0;
-                        p.rec_shaping[ri] = 0;
-                        reinterpret_cast<float4*>(p.rec_logp)[ri] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.rec_entropy) p.rec_entropy[ri] = 0.f;
-                    } else {
-                        // masked log-softmax (train.py:271-274, 326)
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if ((lm >> j) & 1u) mx = fmaxf(mx, o[j]);
-                        float e[4], se = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            e[j] = ((lm >> j) & 1u) ? expf(o[j] - mx) : 0.f;
-                            se += e[j];
-                        }
-                        const float lse = mx + logf(se);
-                        float lp[4], ent = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            lp[j] = ((lm >> j) & 1u) ? o[j] - lse : -INFINITY;
-                            const float pj = e[j] / se;
-                            if (pj > 0.f) ent -= pj * logf(pj);          // train.py:290-291
-                        }
-                        const U4 d = env_draws(p.seed, p.env0 + uint64_t(env), ctr);
-                        uint32_t a;
-                        if (p.forced_actions) {
-                            a = p.forced_actions[ri] & 3u;
-                        } else {
-                            // inverse-CDF categorical sample over the legal actions, 24-bit uniform from word 2
-                            const float thr = float(d.z >> 8) * (1.0f / 16777216.0f) * se;
-                            float cum = 0.f;
-                            a = 31u - uint32_t(__clz(int(lm)));          // last legal action (round-off guard)
-                            bool found = false;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                cum += e[j];
-                                if (!found && ((lm >> j) & 1u) && thr < cum) {
-                                    a = uint32_t(j);
-                                    found = true;
-                                }
-                            }
-                        }
-                        const StepOut so = env_step<true>(board, a, d.x, d.y, lut);   // train.py:294
-                        p.rec_boards[ri] = pack_board(board);
-                        p.rec_actions[ri] = uint8_t(a);
-                        p.rec_legal[ri] = uint8_t(lm);
-                        reinterpret_cast<float4*>(p.rec_logp)[ri] = make_float4(lp[0], lp[1], lp[2], lp[3]);
-                        p.rec_value[ri] = o[4];
-                        p.rec_points[ri] = so.points;
-                        p.rec_shaping[ri] = uint64_t(so.shape_lo) | uint64_t(so.shape_hi) << 32;
-                        p.rec_flags[ri] = uint8_t(so.flags | 0x80u);
-                        if (p.rec_entropy) p.rec_entropy[ri] = ent;
-                        board = so.board;
-                        if (so.flags & FLAG_DONE) {
-                            if (p.auto_reset)
-                                board = reset_board(env_draws(p.seed ^ RESET_KEY_TWEAK, p.env0 + uint64_t(env), ctr));
-                            else
-                                alive = false;
-                        }
-                    }
-                }
+                if (owner) policy_env_step(p, lut, t, env, ctr, lm, o, board, alive);
             }
             // X is rewritten by the owners at the top of the next step; all head reads of X are
             // ordered before it by the consumer_sync() inside this step's head phase for half 0/1
@@ -508,7 +415,7 @@ extern "C" {
 int64_t g2048_mlp_packed_floats(int32_t hidden, int32_t layers) {
     const int HP = padded_hidden(hidden);
     if (HP < 0 || layers < 0 || layers > 8) return -1;
-    return pk_total(HP, layers);
+    return pk_total_with_images(HP, layers);
 }
 
 int g2048_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
@@ -537,6 +444,9 @@ int g2048_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const fl
     s.val_b = value_b;
     pack_mlp_kernel<<<256, 256, 0, cudaStream_t(stream)>>>(s, hidden, HP, layers, packed);
     G2048_CHECK_LAUNCH("pack_mlp_kernel");
+    pack_mlp_images_kernel<<<256, 256, 0, cudaStream_t(stream)>>>(
+        s, hidden, HP, layers, reinterpret_cast<uint8_t*>(packed + pk_img_base(HP, layers)));
+    G2048_CHECK_LAUNCH("pack_mlp_images_kernel");
     return G2048_OK;
 }
 
@@ -575,6 +485,11 @@ int g2048_rollout_mlp(const G2048Rollout* r, void* stream) {
     p.rec_flags = r->rec_flags;
     p.rec_entropy = r->rec_entropy;
     cudaStream_t st = cudaStream_t(stream);
+    if (r->tensor_cores) {
+        G2048_REQUIRE((reinterpret_cast<uintptr_t>(r->packed_weights) & 127u) == 0,
+                      "g2048_rollout_mlp: packed_weights must be 128-byte aligned for the tensor-core kernel");
+        return launch_rollout_tc(p, HP, st);
+    }
     switch (HP) {
         case 64: return launch_rollout<64>(p, st);
         case 128: return launch_rollout<128>(p, st);

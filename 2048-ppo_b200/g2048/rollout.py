@@ -29,6 +29,7 @@ class _RolloutStruct(C.Structure):
         ("forced_actions", C.c_void_p), ("rec_boards", C.c_void_p), ("rec_actions", C.c_void_p),
         ("rec_legal", C.c_void_p), ("rec_logp", C.c_void_p), ("rec_value", C.c_void_p), ("rec_points", C.c_void_p),
         ("rec_shaping", C.c_void_p), ("rec_flags", C.c_void_p), ("rec_entropy", C.c_void_p),
+        ("tensor_cores", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -36,6 +37,9 @@ _lib.lib().g2048_mlp_packed_floats.restype = C.c_int64
 _lib.lib().g2048_mlp_packed_floats.argtypes = [C.c_int32, C.c_int32]
 _lib.register("g2048_mlp_pack", [C.c_int32, C.c_int32] + [C.c_void_p] * 12)
 _lib.register("g2048_rollout_mlp", [C.POINTER(_RolloutStruct), C.c_void_p])
+
+
+TC_MIN_ENVS = 16384   # "auto": envs per GPU from which the rollout GEMMs run on the tensor cores
 
 
 def _dp(t):
@@ -101,8 +105,13 @@ class RolloutBuffers:
 
 def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, env0: int = 0, ctr0: int = 1,
             auto_reset: bool = True, alive: torch.Tensor | None = None, forced_actions: torch.Tensor | None = None,
-            out: RolloutBuffers | None = None) -> RolloutBuffers:
-    """Play T steps of every board in `boards` (updated in place) with one fused kernel launch."""
+            out: RolloutBuffers | None = None, precision: str = "auto") -> RolloutBuffers:
+    """Play T steps of every board in `boards` (updated in place) with one fused kernel launch.
+
+    precision: "fp32" = FFMA GEMMs (parity-grade log-probs), "bf16" = tcgen05 tensor-core GEMMs with
+    fp32 accumulation, "auto" = bf16 from TC_MIN_ENVS envs up (tensor cores only at large env batch)."""
+    if precision not in ("auto", "fp32", "bf16"):
+        raise ValueError(f"precision must be auto, fp32 or bf16, got {precision!r}")
     boards = env._req(boards, torch.int64, "boards")
     B = boards.numel()
     dev = env.init(boards.device)
@@ -117,7 +126,8 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
         s = _RolloutStruct(B, T, policy.hidden, policy.layers, int(auto_reset), seed, env0, ctr0,
                            _dp(policy.weights), _dp(env.lut(dev)), _dp(boards), _dp(alive), _dp(forced_actions),
                            _dp(buf.boards), _dp(buf.actions), _dp(buf.legal), _dp(buf.logp), _dp(buf.value),
-                           _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy))
+                           _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy),
+                           int(precision == "bf16" or (precision == "auto" and B >= TC_MIN_ENVS)), 0)
         _lib.call("g2048_rollout_mlp", C.byref(s), _stream())
     return buf
 

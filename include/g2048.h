@@ -170,6 +170,10 @@ typedef struct G2048Rollout {
     uint64_t* rec_shaping;  /* packed G2048_SH_* record of the move */
     uint8_t* rec_flags;     /* g2048_step flags of the move | G2048_FLAG_VALID */
     float* rec_entropy;     /* entropy of the masked action distribution; may be NULL */
+    int32_t tensor_cores;   /* 0: fp32 FFMA GEMMs (log-probs within ~1e-6 of the torch policy);
+                               1: bf16 tcgen05 GEMMs with fp32 accumulation in tensor memory (large env
+                                  batches; recorded log-probs within ~1e-2 of the fp32 policy) */
+    int32_t reserved_;
 } G2048Rollout;
 
 int g2048_rollout_mlp(const G2048Rollout* params, void* stream);

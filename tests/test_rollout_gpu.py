@@ -204,3 +204,67 @@ def test_trainer_step_runs_and_learns_signal():
     assert not torch.equal(w0, t.model.action_head.weight)        # the optimizer moved the policy head
     assert t.moments.step == 3 and t.moments.m2 != 1.0
     assert abs(s1["entropy"]) > 0.5                                # zero-initialised heads: near-uniform policy
+
+
+def bf16_emulated_policy(model, boards, legal):
+    """The tensor-core kernel's arithmetic in plain torch: bf16-rounded GEMM operands, fp32
+    accumulation, fp32 LayerNorm / residual stream / heads."""
+    from g2048 import env
+    import torch.nn.functional as F
+    r = lambda t: t.bfloat16().float()
+    sd = model.state_dict()
+    x48 = env.encode(boards.reshape(-1))
+    w = sd["stem.0.weight"]
+    pos = x48.clone()
+    pos[:, 0::3] = 0
+    z = x48[:, 0::3] @ r(w[:, 0::3]).T + pos @ w.T           # exponents through bf16 weights, positions in fp32
+    h = w.shape[0]
+    x = F.relu(F.layer_norm(z, (h,), sd["stem.1.weight"], sd["stem.1.bias"], 1e-5))
+    L = len(model.backbone)
+    for l in range(L):
+        z = r(x) @ r(sd[f"backbone.{l}.mlp.0.weight"]).T
+        x = x + F.relu(F.layer_norm(z, (h,), sd[f"backbone.{l}.mlp.1.weight"], sd[f"backbone.{l}.mlp.1.bias"], 1e-5))
+    logits = x @ sd["action_head.weight"].T + sd["action_head.bias"]
+    v = (x @ sd["value_head.weight"].T + sd["value_head.bias"]).squeeze(1)
+    illegal = ((legal.reshape(-1).long()[:, None] >> torch.arange(4, device=boards.device)) & 1) == 0
+    return torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1), v
+
+
+@pytest.mark.parametrize("h,L,B,T", [(196, 2, 1000, 24), (64, 1, 130, 16), (192, 3, 300, 8), (196, 0, 128, 4)])
+def test_tensor_core_rollout(h, L, B, T):
+    """bf16 tcgen05 variant: the integer env path stays bit-exact; log-probs / values match a torch
+    emulation of the same bf16-operand arithmetic tightly and the fp32 policy to ~1e-2."""
+    from g2048 import env, rollout
+    model = random_model(h, L, seed=h + L + 1)
+    seed, env0 = 77, 999
+    boards = env.reset(B, device=0, seed=seed, env0=env0, ctr=0)
+    start = boards.clone()
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=env0, ctr0=1, auto_reset=True,
+                          precision="bf16")
+    torch.cuda.synchronize()
+    b = start.cpu().numpy().view(np.uint64)
+    for t in range(T):
+        np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64), b)
+        nb, info = O.step_batch(b, buf.actions[t].cpu().numpy(), seed=seed, env0=env0, ctr=1 + t)
+        assert (info["invalid"] == 0).all()
+        np.testing.assert_array_equal(buf.legal[t].cpu().numpy(), info["legal_before"])
+        np.testing.assert_array_equal(buf.points[t].cpu().numpy(), info["points"])
+        np.testing.assert_array_equal(buf.flags[t].cpu().numpy(), 0x80 | info["legal_after"] | (info["done"] << 4))
+        sh = env.decode_shaping(buf.shaping[t].cpu().numpy())
+        for k in SH_KEYS:
+            np.testing.assert_array_equal(sh[k], info[k], err_msg=k)
+        d = info["done"].astype(bool)
+        if d.any():
+            nb = np.where(d, O.reset_batch(B, seed=seed ^ RESET_TWEAK, env0=env0, ctr=1 + t), nb)
+        b = nb
+    got = buf.logp.reshape(-1, 4)
+    lp, v = bf16_emulated_policy(model, buf.boards, buf.legal)
+    fin = torch.isfinite(lp)
+    assert torch.equal(torch.isfinite(got), fin)
+    torch.testing.assert_close(got[fin], lp[fin], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(buf.value.reshape(-1), v, rtol=2e-3, atol=2e-3)
+    lp32, v32, _ = torch_policy_outputs(model, buf.boards, buf.legal)
+    err_lp = float((got[fin] - lp32[fin]).abs().max())
+    err_v = float((buf.value.reshape(-1) - v32).abs().max())
+    print(f"bf16 tensor-core rollout vs fp32 policy: max |dlogp| = {err_lp:.4f}, max |dV| = {err_v:.4f}")
+    assert err_lp < 0.1 and err_v < 0.1
