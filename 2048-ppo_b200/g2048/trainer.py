@@ -42,6 +42,7 @@ class TrainConfig:
     seed: int = 2048
     zero_heads: bool = True        # train.py:1559-1567
     dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
+    rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
 
 
 def cosine_with_warmup(warmup: int, total: int):
@@ -121,7 +122,7 @@ class Trainer:
         self.model.eval()
         pol = rollout.pack_policy(self.model, self.device)
         rollout.rollout(pol, self.boards, self.cfg.horizon, seed=self.cfg.seed, env0=self.lo, ctr0=self.ctr,
-                        auto_reset=True, out=self.buf)
+                        auto_reset=True, out=self.buf, precision=self.cfg.rollout_precision)
         self.ctr += self.cfg.horizon
         return self.buf
 

@@ -57,6 +57,13 @@ def c2_transitions(seed: int):
     return boards, actions
 
 
+def bf16_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["bf16_tflops"])
+    return 1590.0
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -178,17 +185,29 @@ def rollout_section(args, dev, world, rank, barrier):
                          seed=2048)
     t = tr.Trainer(cfg, dev)
     n_local = envs_per_gpu * horizon
-    # rollout only
-    t.collect()
-    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 2
-    ev0.record()
-    for _ in range(reps):
+
+    def time_rollout(precision):
+        cfg.rollout_precision = precision
         t.collect()
-    ev1.record()
-    barrier()
-    ro_ms = ev0.elapsed_time(ev1) / reps
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            t.collect()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1) / reps
+        if world > 1:
+            v = torch.tensor([ms], device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            ms = float(v.item())
+        return ms
+
+    # rollout only: fp32 FFMA kernel (parity-grade) and bf16 tcgen05 kernel (what "auto" picks at this size)
+    ro_fp32_ms = time_rollout("fp32")
+    ro_ms = time_rollout("bf16")
+    cfg.rollout_precision = "auto"
     # rollout + update
     t.train_step()
     barrier()
@@ -209,12 +228,16 @@ def rollout_section(args, dev, world, rank, barrier):
         "workload": f"c3: GameMLP h=196 L=2 fused rollout, {envs_per_gpu} envs x {horizon} steps per GPU, auto-reset, Philox seed 2048",
         "env_steps_per_sec": env_sps,
         "rollout_ms": ro_ms,
+        "rollout_kernel": "rollout_mlp_tc_kernel<208> (bf16 tcgen05.mma, fp32 accumulate in TMEM)",
+        "fp32_ffma_rollout": {"ms": ro_fp32_ms, "env_steps_per_sec": world * n_local / (ro_fp32_ms * 1e-3),
+                              "kernel": "rollout_mlp_kernel<208>"},
         "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
         "train_step_ms": step_ms,
         "phase_ms_rank0": {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
                            "moments_allreduce": times.allreduce_ms},
         "model_flops_per_env_step": flops,
-        "rollout_fp32_tflops": env_sps * flops / 1e12,
+        "rollout_model_tflops": env_sps * flops / 1e12,
+        "rollout_frac_of_bf16_peak": (env_sps / world) * flops / 1e12 / bf16_peak(),
         "grad_allreduce_bytes": 88401 * 4,
         "loss": stats["loss"],
     }

@@ -261,8 +261,10 @@ def test_tensor_core_rollout(h, L, B, T):
     lp, v = bf16_emulated_policy(model, buf.boards, buf.legal)
     fin = torch.isfinite(lp)
     assert torch.equal(torch.isfinite(got), fin)
-    torch.testing.assert_close(got[fin], lp[fin], rtol=2e-3, atol=2e-3)
-    torch.testing.assert_close(buf.value.reshape(-1), v, rtol=2e-3, atol=2e-3)
+    # (a 1e-7 difference before a bf16 rounding can flip one operand ulp: 1e-2, not fp32 tolerances)
+    torch.testing.assert_close(got[fin], lp[fin], rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(buf.value.reshape(-1), v, rtol=1e-2, atol=1e-2)
+    assert float((got[fin] - lp[fin]).abs().mean()) < 5e-4
     lp32, v32, _ = torch_policy_outputs(model, buf.boards, buf.legal)
     err_lp = float((got[fin] - lp32[fin]).abs().max())
     err_v = float((buf.value.reshape(-1) - v32).abs().max())

@@ -18,6 +18,7 @@ ap.add_argument("--steps", type=int, default=32)
 ap.add_argument("--hidden", type=int, default=196)
 ap.add_argument("--layers", type=int, default=2)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--precision", default="fp32")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -28,8 +29,8 @@ buf = rollout.RolloutBuffers.allocate(a.steps, a.envs, dev)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for r in range(a.reps):
     ev0.record()
-    rollout.rollout(pol, boards, a.steps, seed=1, env0=0, ctr0=1 + r * a.steps, out=buf)
+    rollout.rollout(pol, boards, a.steps, seed=1, env0=0, ctr0=1 + r * a.steps, out=buf, precision=a.precision)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    print(f"rollout {a.envs} envs x {a.steps} steps: {ms:.3f} ms, {a.envs * a.steps / ms * 1e3:.4g} env-steps/s")
+    print(f"[{a.precision}] rollout {a.envs} envs x {a.steps} steps: {ms:.3f} ms, {a.envs * a.steps / ms * 1e3:.4g} env-steps/s")
