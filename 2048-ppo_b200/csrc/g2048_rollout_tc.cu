@@ -31,9 +31,12 @@ struct TcSmem {
     alignas(1024) uint8_t A[KB * 128 * 128];        // activations, bf16 swizzled
     alignas(1024) uint8_t Bw[KB * HP * 128];        // current block's weights
     alignas(1024) uint8_t Bstem[HP * 128];          // stem weights (k-step 0 of a 64-wide block)
-    float b0[HP], stem_g[HP], stem_b[HP];
-    float ln_g[8][HP], ln_b[8][HP];
-    float headw[5 * HP + 8];
+    alignas(16) float b0[HP];
+    alignas(16) float stem_g[HP];
+    alignas(16) float stem_b[HP];
+    alignas(16) float ln_g[8][HP];
+    alignas(16) float ln_b[8][HP];
+    alignas(16) float headw[5 * HP + 8];
     float red[2][2][128];                           // [sum | sq][column half][row]
     float headp[128][5];
     uint64_t a_ready, mma_done, b_full, stem_full;
@@ -52,22 +55,29 @@ template <int HP, bool STEM, bool HEADS>
 __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int row, int half, int h,
                                          const float* __restrict__ bias, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float (&o)[5]) {
+    // Columns >= h are padding: their weights, biases, gamma and beta are zero in the packed buffer,
+    // so they produce z = 0 and x = 0 without any masking here.
     constexpr int NH = HP / 2;
     const int c0 = half * NH;
     const uint32_t tD = tmem_lane + uint32_t(c0), tX = tmem_lane + TC_X_COL + uint32_t(c0);
     const float inv_h = 1.0f / float(h);
+    const float4* bias4 = reinterpret_cast<const float4*>(bias + (STEM ? c0 : 0));
+    const float4* gamma4 = reinterpret_cast<const float4*>(gamma + c0);
+    const float4* beta4 = reinterpret_cast<const float4*>(beta + c0);
     float sum = 0.f, sq = 0.f;
 #pragma unroll 1
     for (int g = 0; g < NH / 8; ++g) {
         float v[8];
         tc::tmem_ld8(tD + uint32_t(8 * g), v);
+        if (STEM) {
+            const float4 ba = bias4[2 * g], bb = bias4[2 * g + 1];
+            v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
+            v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int n = c0 + 8 * g + j;
-            float z = STEM ? v[j] + bias[n] : v[j];
-            z = n < h ? z : 0.f;
-            sum += z;
-            sq = fmaf(z, z, sq);
+            sum += v[j];
+            sq = fmaf(v[j], v[j], sq);
         }
     }
     S.red[0][half][row] = sum;
@@ -76,22 +86,33 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
     const float mean = (S.red[0][0][row] + S.red[0][1][row]) * inv_h;
     const float var = fmaxf((S.red[1][0][row] + S.red[1][1][row]) * inv_h - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float shift = -mean * rstd;
     uint8_t* arow = S.A + uint32_t(row >> 3) * 1024u + uint32_t(row & 7) * 128u;
 #pragma unroll 1
     for (int g = 0; g < NH / 8; ++g) {
         float v[8], x[8];
         tc::tmem_ld8(tD + uint32_t(8 * g), v);
         if (!STEM) tc::tmem_ld8(tX + uint32_t(8 * g), x);
+        if (STEM) {
+            const float4 ba = bias4[2 * g], bb = bias4[2 * g + 1];
+            v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
+            v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+        }
+        const float4 ga = gamma4[2 * g], gb = gamma4[2 * g + 1], ea = beta4[2 * g], eb = beta4[2 * g + 1];
+        const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float bt[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int n = c0 + 8 * g + j;
-            const float z = STEM ? v[j] + bias[n] : v[j];
-            float y = fmaxf(fmaf((z - mean) * rstd, gamma[n], beta[n]), 0.f);
-            y = STEM ? y : x[j] + y;
-            x[j] = n < h ? y : 0.f;
-            if (HEADS) {
+            const float y = fmaxf(fmaf(fmaf(v[j], rstd, shift), gm[j], bt[j]), 0.f);
+            x[j] = STEM ? y : x[j] + y;
+        }
+        if (HEADS) {
 #pragma unroll
-                for (int q = 0; q < 5; ++q) o[q] = fmaf(S.headw[q * HP + n], x[j], o[q]);
+            for (int q = 0; q < 5; ++q) {
+                const float4* hw = reinterpret_cast<const float4*>(S.headw + q * HP + c0 + 8 * g);
+                const float4 ha = hw[0], hb = hw[1];
+                o[q] = fmaf(ha.x, x[0], fmaf(ha.y, x[1], fmaf(ha.z, x[2], fmaf(ha.w, x[3], o[q]))));
+                o[q] = fmaf(hb.x, x[4], fmaf(hb.y, x[5], fmaf(hb.z, x[6], fmaf(hb.w, x[7], o[q]))));
             }
         }
         tc::tmem_st8(tX + uint32_t(8 * g), x);
