@@ -71,8 +71,16 @@ __device__ __forceinline__ uint32_t put(uint32_t acc, uint32_t x) {
 // remaining rows through L2.
 constexpr int LUT_ROWS = 65536;
 constexpr int LUT_SMEM_ROWS = 0xE000;
-constexpr int LUT_BYTES = LUT_ROWS * 4;
 constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
+// A second table of the same size follows the first one in the caller's buffer: the "move table"
+// used by the 4-move expansion, which needs the merge points directly instead of the potentials:
+//   [15:0] left-move result, [27:16] merge points / 4, [31:28] largest exponent created.
+// Its fields are exact for rows whose cells are all <= 11 (points <= 8192, created exponent <= 12):
+// boards with a bigger tile take the general-table path.  Rows below 0xC000 (192 KiB) are staged.
+constexpr int MOVE_LUT_OFFSET = LUT_ROWS;            // in entries
+constexpr int MOVE_SMEM_ROWS = 0xC000;
+constexpr int MOVE_SMEM_BYTES = MOVE_SMEM_ROWS * 4;
+constexpr int LUT_BYTES = 2 * LUT_ROWS * 4;
 
 __host__ __device__ inline uint32_t lut_entry_for_row(uint32_t row) {
     int c[4] = {int(row & 15), int((row >> 4) & 15), int((row >> 8) & 15), int((row >> 12) & 15)};
@@ -101,6 +109,18 @@ __host__ __device__ inline uint32_t lut_entry_for_row(uint32_t row) {
     return uint32_t(out[0]) | uint32_t(out[1]) << 4 | uint32_t(out[2]) << 8 | uint32_t(out[3]) << 12 |
            uint32_t(code[0]) << 16 | uint32_t(code[1]) << 20 | uint32_t(ge) << 24 | uint32_t(le) << 26 |
            uint32_t(mx) << 28;
+}
+
+__host__ __device__ inline uint32_t move_entry_for_row(uint32_t row) {
+    const uint32_t e = lut_entry_for_row(row);
+    const uint32_t c1 = (e >> 16) & 15u, c2 = (e >> 20) & 15u;
+    uint32_t pts = (c1 ? (2u << c1) : 0u) + (c2 ? (2u << c2) : 0u);
+    uint32_t mt = c1 > c2 ? c1 : c2;
+    mt = mt ? mt + 1u : 0u;
+    pts >>= 2;
+    if (pts > 0xFFFu) pts = 0xFFFu;        // only for rows outside the table's contract (a cell >= 12)
+    if (mt > 15u) mt = 15u;
+    return (e & 0xFFFFu) | pts << 16 | mt << 28;
 }
 
 // Row-table readers.  LutShared: the staged copy, valid only for rows < LUT_SMEM_ROWS --
@@ -193,6 +213,15 @@ __device__ __forceinline__ void merge_stats(Lines l, int& points, int& max_tile,
     points = int(sum << 1);                       // sum of 2^(c+1) over merges (game.py:237)
     max_tile = any > 1u ? 32 - __clz(any) : 0;    // max (c+1) (game.py:238)
     overflow = (any >> 15) & 1u;                  // a merge created exponent 16
+}
+
+// merge points / largest exponent created of one move from 4 move-table entries
+__device__ __forceinline__ void move_stats(Lines l, int& points, int& max_tile) {
+    const uint32_t t = __byte_perm(l.e0, l.e1, 0x7632) & 0x0FFF0FFFu;   // [points/4 of e0 | of e1] in 16-bit lanes
+    const uint32_t u = __byte_perm(l.e2, l.e3, 0x7632) & 0x0FFF0FFFu;
+    const uint32_t v = t + u;                                            // <= 4096 per lane: no carry across lanes
+    points = int(((v & 0xFFFFu) + (v >> 16)) << 2);
+    max_tile = int(max(max(l.e0, l.e1), max(l.e2, l.e3)) >> 28);        // the top nibble dominates the compare
 }
 
 // ------------------------------------------------------------------ legality

@@ -38,14 +38,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Stage the first LUT_SMEM_ROWS table entries into shared memory (224 KiB, 7 bulk copies).
+// Stage the first BYTES of a table into shared memory (224 / 192 KiB, 32 KiB bulk copies).
+template <uint32_t BYTES = uint32_t(LUT_SMEM_BYTES)>
 __device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, uint64_t* bar) {
     constexpr uint32_t CHUNK = 32768;
+    static_assert(BYTES % CHUNK == 0, "whole chunks");
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, LUT_SMEM_BYTES);
+        mbar_expect_tx(bar, BYTES);
 #pragma unroll
-        for (uint32_t off = 0; off < uint32_t(LUT_SMEM_BYTES); off += CHUNK)
+        for (uint32_t off = 0; off < BYTES; off += CHUNK)
             bulk_copy_g2s(reinterpret_cast<uint8_t*>(slut) + off, reinterpret_cast<const uint8_t*>(glut) + off, CHUNK, bar);
     }
     __syncthreads();          // barrier init visible to all waiters
@@ -55,7 +57,10 @@ __device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, 
 // ------------------------------------------------------------------ kernels
 __global__ void build_lut_kernel(uint32_t* lut) {
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row < uint32_t(LUT_ROWS)) lut[row] = lut_entry_for_row(row);
+    if (row < uint32_t(LUT_ROWS)) {
+        lut[row] = lut_entry_for_row(row);
+        lut[MOVE_LUT_OFFSET + row] = move_entry_for_row(row);
+    }
 }
 
 __global__ void reset_kernel(uint64_t* boards, int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0,
@@ -149,17 +154,25 @@ __device__ __forceinline__ void expand4_loop(const uint32_t* slut, const uint32_
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         Board b = make_board(__ldg(boards + i));
         FourLines f;
-        if (STAGED && !has_big_tile(b)) f = lookup_moves(b, LutShared{slut});
-        else f = lookup_moves(b, LutGlobal{glut});
+        int p[4], mt[4];
+        if (STAGED && !has_big_tile(b)) {
+            // every cell <= 11: the staged move table gives result, points and created tile directly
+            f = lookup_moves(b, LutShared{slut});
+            move_stats(f.up, p[0], mt[0]);
+            move_stats(f.down, p[1], mt[1]);
+            move_stats(f.left, p[2], mt[2]);
+            move_stats(f.right, p[3], mt[3]);
+        } else {
+            f = lookup_moves(b, LutGlobal{glut});
+            bool ovf;
+            merge_stats(f.up, p[0], mt[0], ovf);
+            merge_stats(f.down, p[1], mt[1], ovf);
+            merge_stats(f.left, p[2], mt[2], ovf);
+            merge_stats(f.right, p[3], mt[3], ovf);
+        }
         const Lines &lu = f.up, &ld = f.down, &ll = f.left, &lr = f.right;
         Board s[4] = {transpose(result_of(lu)), transpose(rev_rows(result_of(ld))), result_of(ll),
                       rev_rows(result_of(lr))};
-        int p[4], mt[4];
-        bool ovf;
-        merge_stats(lu, p[0], mt[0], ovf);
-        merge_stats(ld, p[1], mt[1], ovf);
-        merge_stats(ll, p[2], mt[2], ovf);
-        merge_stats(lr, p[3], mt[3], ovf);
         uint32_t lm = 0;
 #pragma unroll
         for (int d = 0; d < 4; ++d) lm |= same(s[d], b) ? 0u : (1u << d);
@@ -181,7 +194,7 @@ expand4_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* boards,
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
-    stage_lut(slut, glut, &bar);
+    stage_lut<uint32_t(MOVE_SMEM_BYTES)>(slut, glut + MOVE_LUT_OFFSET, &bar);
     expand4_loop<true>(slut, glut, boards, succ, points, legal, max_tile, n);
 }
 
@@ -259,7 +272,7 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
     cudaStream_t st = cudaStream_t(stream);
     if (n >= STAGED_MIN_UNITS) {
         auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;
-        G2048_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES));
+        G2048_CHECK_CUDA(ensure_smem(kern, LUT_SMEM_BYTES));
         kern<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,
                                                               shaping, n, replay, seed, env0, ctr);
         G2048_CHECK_LAUNCH("step_kernel_staged");
@@ -280,9 +293,8 @@ int g2048_expand4(const void* d_lut, const uint64_t* boards, uint64_t* succ, int
     const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
     cudaStream_t st = cudaStream_t(stream);
     if (n >= STAGED_MIN_UNITS) {
-        G2048_CHECK_CUDA(cudaFuncSetAttribute(expand4_kernel_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              LUT_SMEM_BYTES));
-        expand4_kernel_staged<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards, succ, points, legal,
+        G2048_CHECK_CUDA(ensure_smem(expand4_kernel_staged, MOVE_SMEM_BYTES));
+        expand4_kernel_staged<<<num_sms(), STEP_THREADS, MOVE_SMEM_BYTES, st>>>(lut, boards, succ, points, legal,
                                                                                max_tile, n);
         G2048_CHECK_LAUNCH("expand4_kernel_staged");
     } else {

@@ -29,6 +29,20 @@ int num_sms() {
     return cached;
 }
 
+cudaError_t ensure_smem_impl(const void* kernel, int bytes) {
+    struct Entry { const void* k; int dev; int bytes; };
+    static thread_local Entry cache[64];
+    static thread_local int used = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k == kernel && cache[i].dev == dev && cache[i].bytes >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && used < 64) cache[used++] = {kernel, dev, bytes};
+    return e;
+}
+
 }  // namespace g2048
 
 extern "C" {

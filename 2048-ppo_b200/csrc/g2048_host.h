@@ -11,6 +11,14 @@ char* last_error_buf();   // thread-local, 512 bytes
 int fail(int code, const char* fmt, ...);
 int num_sms();            // SM count of the current device (cached per device)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of per launch.
+// Keyed by the kernel's address (template instantiations share a function TYPE, not an address).
+cudaError_t ensure_smem_impl(const void* kernel, int bytes);
+template <class K>
+inline cudaError_t ensure_smem(K kernel, int bytes) {
+    return ensure_smem_impl(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 #define G2048_CHECK_CUDA(expr)                                                                   \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \

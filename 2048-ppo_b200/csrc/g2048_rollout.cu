@@ -398,7 +398,7 @@ template <int HP>
 int launch_rollout(const RolloutParams& p, cudaStream_t st) {
     const int smem = int(sizeof(RolloutSmem<HP>));
     auto kern = rollout_mlp_kernel<HP>;
-    G2048_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    G2048_CHECK_CUDA(ensure_smem(kern, smem));
     const int64_t ntiles = (p.B + RO_TILE - 1) / RO_TILE;
     const int grid = int(ntiles < num_sms() ? ntiles : num_sms());
     kern<<<grid, RO_THREADS, smem, st>>>(p);

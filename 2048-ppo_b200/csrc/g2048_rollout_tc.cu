@@ -301,7 +301,7 @@ template <int HP>
 static int launch_tc(const RolloutParams& p, cudaStream_t st) {
     const int smem = int(sizeof(TcSmem<HP>)) + 1024;
     auto kern = rollout_mlp_tc_kernel<HP>;
-    G2048_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    G2048_CHECK_CUDA(ensure_smem(kern, smem));
     const int64_t ntiles = (p.B + 127) / 128;
     const int grid = int(ntiles < num_sms() ? ntiles : num_sms());
     kern<<<grid, TC_THREADS, smem, st>>>(p);

@@ -64,8 +64,10 @@ const char* g2048_version(void);
 /* Checks that `device` is a compute-capability-10.x GPU and makes it current. */
 int g2048_init(int device);
 
-/* Row table: 65536 x u32 (g2048_lut_bytes() = 262144 bytes), built on the device.
- * Replaces game.py:224-257 (_merge_and_shift_left/right_with_score) for every row. */
+/* Row tables: 2 x 65536 x u32 (g2048_lut_bytes() = 524288 bytes), built on the device: the general
+ * table (move result, merge codes, per-line potentials) and the move table of the 4-move expansion
+ * (move result, merge points, created tile).  Replace game.py:224-257
+ * (_merge_and_shift_left/right_with_score) for every row. */
 int64_t g2048_lut_bytes(void);
 int g2048_build_lut(void* d_lut, void* stream);
 

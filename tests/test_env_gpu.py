@@ -56,8 +56,16 @@ def check_step(env, boards, actions, draws, n_expected=None):
 
 
 def test_row_table_matches_oracle(env):
-    lut = env.lut(0).cpu().numpy().view(np.uint32)
+    both = env.lut(0).cpu().numpy().view(np.uint32)
+    lut, mv = both[:65536], both[65536:]
     out4, score, mt = O.row_table()
+    # move table of the 4-move expansion: exact for rows whose cells are all <= 11
+    idx = np.arange(65536)
+    small = ((idx & 15) <= 11) & (((idx >> 4) & 15) <= 11) & (((idx >> 8) & 15) <= 11) & ((idx >> 12) <= 11)
+    assert small.sum() == 12 ** 4
+    np.testing.assert_array_equal(np.stack([(mv >> (4 * k)) & 15 for k in range(4)], axis=1)[small], out4[small])
+    np.testing.assert_array_equal((((mv >> 16) & 0xFFF) * 4)[small], score[small])
+    np.testing.assert_array_equal((mv >> 28)[small], mt[small])
     res = np.stack([(lut >> (4 * k)) & 15 for k in range(4)], axis=1)
     np.testing.assert_array_equal(res, np.minimum(out4, 15))
     c1, c2 = (lut >> 16) & 15, (lut >> 20) & 15
