@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import dp, env, ppo, rollout
+from . import dp, env, fused, ppo, rollout
 from .policy import GameMLP, MLPConfig
 
 
@@ -153,7 +153,7 @@ class Trainer:
                 tot = torch.zeros(4, dtype=torch.float64, device=self.device)
                 for c0 in range(m0, m1, c.chunk):
                     sl = slice(c0, min(m1, c0 + c.chunk)) if order is None else order[c0:min(m1, c0 + c.chunk)]
-                    logits, v = self.model(env.encode(boards[sl]))
+                    logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]))
                     loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],
                                                clip_eps=c.clip_eps, critic_strength=c.critic_strength,
                                                entropy_strength=c.entropy_strength, n_total=n_mb_global)

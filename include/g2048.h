@@ -180,6 +180,19 @@ typedef struct G2048Rollout {
 
 int g2048_rollout_mlp(const G2048Rollout* params, void* stream);
 
+/* ---- policy update: fused y = res + ReLU(LayerNorm(z)) and its backward ---------------------
+ * The elementwise chain of a GameMLP block (game.py:1038-1046; stem: game.py:1069-1073, res = NULL)
+ * in eval/p=0 dropout form.  Row-major [n,h] fp32, h a multiple of 4 up to 256, eps = 1e-5 in the
+ * reference.  forward also returns the per-row mean and rstd the backward needs.  backward
+ * returns dz, dgamma, dbeta (d res = gout, unchanged); `workspace` holds
+ * g2048_ln_workspace_floats(h) floats.  The GEMMs around it stay in torch/cuBLAS. */
+int64_t g2048_ln_workspace_floats(int32_t h);
+int g2048_ln_relu_res_fwd(const float* z, const float* gamma, const float* beta, const float* res, float* y,
+                          float* mean, float* rstd, int64_t n, int32_t h, float eps, void* stream);
+int g2048_ln_relu_res_bwd(const float* z, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                          const float* gout, float* dz, float* dgamma, float* dbeta, float* workspace, int64_t n,
+                          int32_t h, void* stream);
+
 /* tcgen05 building-block self-test (not part of the reference's interface): C[128,N] =
  * A[128,K] * W[N,K]^T with bf16-rounded operands and fp32 accumulation in tensor memory.
  * K, N multiples of 16, <= 256.  Pins the UMMA descriptor / swizzle conventions on hardware. */
