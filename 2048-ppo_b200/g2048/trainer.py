@@ -43,6 +43,7 @@ class TrainConfig:
     zero_heads: bool = True        # train.py:1559-1567
     dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
     rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
+    update_matmul: str = "fp32"       # cuBLAS mode of the update's Linear GEMMs: "fp32" (reference precision) or "tf32"
 
 
 def cosine_with_warmup(warmup: int, total: int):
@@ -143,6 +144,8 @@ class Trainer:
         n_global = int(dp.allreduce_stats(counts).item())
         self.model.train()
         last = None
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = c.update_matmul == "tf32"
         for _ in range(c.epochs):
             order = None if c.minibatches == 1 else torch.randperm(n_local, device=self.device)
             mb = (n_local + c.minibatches - 1) // c.minibatches
@@ -163,6 +166,7 @@ class Trainer:
                 gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)   # train.py:561
                 self.opt.step()
                 last = (tot, gn)
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
         self.opt.scheduler_step()                                                   # train.py:625
         tot = dp.allreduce_stats(last[0].clone())
         out = ppo.loss_stats(tot, c.critic_strength, c.entropy_strength)

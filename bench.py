@@ -208,20 +208,24 @@ def rollout_section(args, dev, world, rank, barrier):
     ro_fp32_ms = time_rollout("fp32")
     ro_ms = time_rollout("bf16")
     cfg.rollout_precision = "auto"
-    # rollout + update
-    t.train_step()
-    barrier()
-    ev0.record()
-    for _ in range(reps):
-        stats = t.train_step()
-    ev1.record()
-    barrier()
-    step_ms = ev0.elapsed_time(ev1) / reps
-    times = t.times
+    # rollout + update (fp32 cuBLAS GEMMs = the reference's precision; tf32 reported beside it)
+    def time_train(matmul):
+        cfg.update_matmul = matmul
+        t.train_step()
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            st = t.train_step()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1) / reps, st, t.times
+
+    tf32_ms, _, _ = time_train("tf32")
+    step_ms, stats, times = time_train("fp32")
     if world > 1:
-        v = torch.tensor([ro_ms, step_ms], device=dev)
+        v = torch.tensor([step_ms, tf32_ms], device=dev)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        ro_ms, step_ms = (float(x) for x in v.tolist())
+        step_ms, tf32_ms = (float(x) for x in v.tolist())
     flops = 2 * (48 * 196 + 2 * 196 * 196 + 5 * 196)
     env_sps = world * n_local / (ro_ms * 1e-3)
     return {
@@ -233,6 +237,8 @@ def rollout_section(args, dev, world, rank, barrier):
                               "kernel": "rollout_mlp_kernel<208>"},
         "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
         "train_step_ms": step_ms,
+        "update": "torch autograd + cuBLAS fp32 SGEMM for the Linear layers, fused g2048 LayerNorm/ReLU/residual and PPO-loss kernels, Muon+AdamW",
+        "tf32_update_variant": {"train_step_ms": tf32_ms, "rollout_update_steps_per_sec": world * n_local / (tf32_ms * 1e-3)},
         "phase_ms_rank0": {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
                            "moments_allreduce": times.allreduce_ms},
         "model_flops_per_env_step": flops,
