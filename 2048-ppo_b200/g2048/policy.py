@@ -100,3 +100,110 @@ def load_state_dict_from_npz(npz, prefix: str = "sd__") -> dict:
     """Rebuild a state_dict from tests/golden/model_best.npz (keys stored with '__' for '.')."""
     return {k[len(prefix):].replace("__", "."): torch.from_numpy(npz[k].copy())
             for k in npz.files if k.startswith(prefix)}
+
+
+# ----------------------------------------------------------------------------- GameURM (config #5)
+
+@dataclass
+class GameURMConfig:  # game.py:31-42
+    hidden_dim: int = 64
+    num_layers: int = 2
+    num_heads: int = 4
+    expansion: float = 2.67
+    dropout: float = 0.1
+    num_loops: int = 4
+    num_truncated_loops: int = 1
+    conv_kernel: int = 2
+    rms_norm_eps: float = 1e-5
+
+
+def rms_norm(x: torch.Tensor, eps: float) -> torch.Tensor:  # game.py:1223-1229
+    x32 = x.to(torch.float32)
+    return (x32 * torch.rsqrt(x32.square().mean(-1, keepdim=True) + eps)).to(x.dtype)
+
+
+class GameConvSwiGLU(nn.Module):  # game.py:1232-1276
+    def __init__(self, hidden_size: int, expansion: float, conv_kernel: int = 2):
+        super().__init__()
+        inter = ((round(expansion * hidden_size * 2 / 3) + 7) // 8) * 8
+        self.inter = inter
+        self.gate_up_proj = nn.Linear(hidden_size, inter * 2, bias=False)
+        self.dwconv = nn.Conv1d(inter, inter, kernel_size=conv_kernel, padding=conv_kernel // 2, groups=inter, bias=True)
+        self.down_proj = nn.Linear(inter, hidden_size, bias=False)
+
+    def forward(self, x):
+        gate, up = self.gate_up_proj(x).chunk(2, dim=-1)
+        h = torch.nn.functional.silu(gate) * up
+        c = self.dwconv(h.transpose(1, 2))[..., : h.size(1)]
+        return self.down_proj(torch.nn.functional.silu(c).transpose(1, 2).contiguous())
+
+
+class GameURMAttention(nn.Module):  # game.py:1279-1317
+    def __init__(self, hidden_size: int, num_heads: int, dropout: float = 0.0):
+        super().__init__()
+        self.hidden_size, self.num_heads, self.head_dim, self.dropout = hidden_size, num_heads, hidden_size // num_heads, dropout
+        self.qkv_proj = nn.Linear(hidden_size, hidden_size * 3, bias=False)
+        self.o_proj = nn.Linear(hidden_size, hidden_size, bias=False)
+
+    def forward(self, x):
+        b, s, _ = x.shape
+        qkv = self.qkv_proj(x).view(b, s, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+        o = torch.nn.functional.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2],
+                                                             dropout_p=self.dropout if self.training else 0.0, is_causal=False)
+        return self.o_proj(o.transpose(1, 2).contiguous().view(b, s, self.hidden_size))
+
+
+class GameURMBlock(nn.Module):  # game.py:1320-1352
+    def __init__(self, config: GameURMConfig):
+        super().__init__()
+        self.attn = GameURMAttention(config.hidden_dim, config.num_heads, config.dropout)
+        self.mlp = GameConvSwiGLU(config.hidden_dim, config.expansion, config.conv_kernel)
+        self.norm_eps = config.rms_norm_eps
+
+    def forward(self, h):
+        h = rms_norm(h + self.attn(h), self.norm_eps)
+        return rms_norm(h + self.mlp(h), self.norm_eps)
+
+
+class GameURM(nn.Module):  # game.py:1355-1458
+    N = 16
+    NUM_ACTIONS = 4
+
+    def __init__(self, config: GameURMConfig):
+        super().__init__()
+        self.config = config
+        self.stem = nn.Sequential(nn.Linear(3, config.hidden_dim, bias=False), nn.LayerNorm(config.hidden_dim), nn.SiLU())
+        self.layers = nn.ModuleList([GameURMBlock(config) for _ in range(config.num_layers)])
+        self.init_hidden = nn.Parameter(torch.zeros(1, self.N, config.hidden_dim))
+        nn.init.trunc_normal_(self.init_hidden, std=0.02)
+        self.action_head = nn.Linear(config.hidden_dim, self.NUM_ACTIONS, bias=True)
+        self.value_head = nn.Linear(config.hidden_dim, 1, bias=True)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_uniform_(m.weight, nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    @property
+    def directions(self):
+        return list(DIRECTIONS)
+
+    def forward(self, inputs: torch.Tensor):
+        if inputs.ndim == 1:
+            inputs = inputs.unsqueeze(0)
+        b = inputs.shape[0]
+        emb = self.stem(inputs.view(b, self.N, 3))
+        h = self.init_hidden.expand(b, -1, -1).clone()
+        trunc = self.config.num_truncated_loops
+        if trunc > 0:
+            with torch.no_grad():
+                for _ in range(trunc):
+                    h = h + emb
+                    for layer in self.layers:
+                        h = layer(h)
+        for _ in range(self.config.num_loops - trunc):
+            h = h + emb
+            for layer in self.layers:
+                h = layer(h)
+        pooled = h.mean(dim=1)
+        return self.action_head(pooled), self.value_head(pooled)

@@ -387,7 +387,30 @@ def main():
     episodes = gen_rollout(model)
     eps_adv = gen_advantage(episodes)
     gen_loss(eps_adv)
+    gen_urm(np.random.default_rng(13))
+
+
+
+def gen_urm(rng):
+    """Reference GameURM (game.py:1355-1458), default config, seeded init, eval mode."""
+    torch.manual_seed(64)
+    cfg = G.GameURMConfig()
+    model = G.GameURM(cfg).eval()
+    boards = random_boards(rng)[:256]
+    x = torch.stack([G.Game2048(b.reshape(4, 4).tolist() if b.any() else None).to_model_format() for b in boards])
+    with torch.no_grad():
+        logits, v = model(x)
+    sd = {k.replace(".", "__"): t.numpy() for k, t in model.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "model_urm.npz"),
+                        board=np.array([pack(b.reshape(4, 4)) for b in boards], dtype=np.uint64),
+                        inputs=x.numpy(), logits=logits.numpy(), value=v.numpy(),
+                        **{"sd__" + k: a for k, a in sd.items()})
+    print("model_urm:", {k: tuple(v.shape) for k, v in model.state_dict().items()})
 
 
 if __name__ == "__main__":
-    main()
+    if "--urm-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        gen_urm(np.random.default_rng(13))
+    else:
+        main()

@@ -88,3 +88,15 @@ def test_rtg_moments_update_matches_reference(golden):
         np.testing.assert_allclose([mom.mu, mom.m2], adv[name + "__moments_out"], rtol=1e-10)
         gn = (graw - mu_c) / (sd + 1e-8)
         np.testing.assert_allclose(gn, adv[name + "__g_norm"], rtol=1e-12, atol=1e-12)
+
+
+def test_urm_mirror_matches_reference_forward(golden):
+    from g2048 import policy
+    g = golden("model_urm")
+    m = policy.GameURM(policy.GameURMConfig()).eval()
+    m.load_state_dict(policy.load_state_dict_from_npz(g))
+    with torch.no_grad():
+        logits, v = m(torch.from_numpy(g["inputs"]))
+    np.testing.assert_array_equal(logits.numpy(), g["logits"])
+    np.testing.assert_array_equal(v.numpy(), g["value"])
+    assert m.layers[0].mlp.inter == 120
