@@ -37,6 +37,10 @@ _lib.lib().g2048_mlp_packed_floats.restype = C.c_int64
 _lib.lib().g2048_mlp_packed_floats.argtypes = [C.c_int32, C.c_int32]
 _lib.register("g2048_mlp_pack", [C.c_int32, C.c_int32] + [C.c_void_p] * 12)
 _lib.register("g2048_rollout_mlp", [C.POINTER(_RolloutStruct), C.c_void_p])
+_lib.lib().g2048_urm_packed_floats.restype = C.c_int64
+_lib.lib().g2048_urm_packed_floats.argtypes = [C.c_int32] * 4
+_lib.register("g2048_urm_pack", [C.c_int32] + [C.c_void_p] * 16)
+_lib.register("g2048_rollout_urm", [C.POINTER(_RolloutStruct), C.c_int32, C.c_void_p])
 
 
 TC_MIN_ENVS = 16384   # "auto": envs per GPU from which the rollout GEMMs run on the tensor cores
@@ -51,10 +55,39 @@ class PackedPolicy:
     hidden: int
     layers: int
     weights: torch.Tensor   # float32, kernel layout
+    kind: str = "mlp"       # "mlp" (GameMLP) or "urm" (GameURM)
+    loops: int = 0          # GameURMConfig.num_loops
+
+
+def _pack_urm(model, device) -> PackedPolicy:
+    """GameURM (ours or the reference's, game.py:1355-1458) -> kernel layout."""
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    cfg = model.config
+    h, L = sd["stem.0.weight"].shape[0], len({k.split(".")[1] for k in sd if k.startswith("layers.")})
+    inter = sd["layers.0.mlp.down_proj.weight"].shape[1]
+    dev = env.init(device if device is not None else (sd["stem.0.weight"].device if sd["stem.0.weight"].is_cuda else None))
+    n = int(_lib.lib().g2048_urm_packed_floats(h, L, cfg.num_heads, inter))
+    if n < 0 or cfg.conv_kernel != 2 or abs(cfg.rms_norm_eps - 1e-5) > 1e-12:
+        raise ValueError("the fused URM kernel is built for hidden_dim=64, num_heads=4, inter=120, conv_kernel=2, "
+                         f"rms_norm_eps=1e-5, 1..2 layers (got h={h}, heads={cfg.num_heads}, inter={inter}, L={L})")
+    t = {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in sd.items()}
+    arr = lambda fmt: C.cast((C.c_void_p * L)(*[t[fmt.format(i)].data_ptr() for i in range(L)]), C.c_void_p)
+    with torch.cuda.device(dev):
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.call("g2048_urm_pack", L, _dp(t["stem.0.weight"]), _dp(t["stem.1.weight"]), _dp(t["stem.1.bias"]),
+                  _dp(t["init_hidden"]), arr("layers.{}.attn.qkv_proj.weight"), arr("layers.{}.attn.o_proj.weight"),
+                  arr("layers.{}.mlp.gate_up_proj.weight"), arr("layers.{}.mlp.dwconv.weight"),
+                  arr("layers.{}.mlp.dwconv.bias"), arr("layers.{}.mlp.down_proj.weight"),
+                  _dp(t["action_head.weight"]), _dp(t["action_head.bias"]), _dp(t["value_head.weight"]),
+                  _dp(t["value_head.bias"]), _dp(out), _stream())
+        torch.cuda.current_stream().synchronize()
+    return PackedPolicy(h, L, out, kind="urm", loops=int(cfg.num_loops))
 
 
 def pack_policy(model, device=None) -> PackedPolicy:
     """GameMLP (ours or the reference's: same state_dict keys, game.py:1064-1085) -> kernel layout."""
+    if "init_hidden" in dict(model.named_parameters()):
+        return _pack_urm(model, device)
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     h = sd["stem.0.weight"].shape[0]
     L = len({k.split(".")[1] for k in sd if k.startswith("backbone.")})
@@ -128,7 +161,10 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
                            _dp(buf.boards), _dp(buf.actions), _dp(buf.legal), _dp(buf.logp), _dp(buf.value),
                            _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy),
                            int(precision == "bf16" or (precision == "auto" and B >= TC_MIN_ENVS)), 0)
-        _lib.call("g2048_rollout_mlp", C.byref(s), _stream())
+        if policy.kind == "urm":
+            _lib.call("g2048_rollout_urm", C.byref(s), policy.loops, _stream())
+        else:
+            _lib.call("g2048_rollout_mlp", C.byref(s), _stream())
     return buf
 
 

@@ -180,6 +180,21 @@ typedef struct G2048Rollout {
 
 int g2048_rollout_mlp(const G2048Rollout* params, void* stream);
 
+/* GameURM policy (game.py:1223-1458, default GameURMConfig game.py:31-42: hidden 64, 4 heads,
+ * inter 120, conv kernel 2; 1..2 layers) -- BASELINE config #5.  Same G2048Rollout records; the
+ * projections run on tcgen05 (bf16 operands, fp32 accumulate), attention / norms / conv on CUDA
+ * cores.  `loops` = GameURMConfig.num_loops.  Pointer arrays hold `layers` device pointers:
+ * layers.{l}.attn.qkv_proj.weight [192,64], attn.o_proj.weight [64,64], mlp.gate_up_proj.weight
+ * [240,64], mlp.dwconv.weight [120,1,2], mlp.dwconv.bias [120], mlp.down_proj.weight [64,120];
+ * stem.0.weight [64,3], stem.1.{weight,bias} [64], init_hidden [1,16,64], heads as for the MLP. */
+int64_t g2048_urm_packed_floats(int32_t hidden, int32_t layers, int32_t heads, int32_t inter);
+int g2048_urm_pack(int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
+                   const float* init_hidden, const float* const* qkv_w, const float* const* o_w,
+                   const float* const* gate_up_w, const float* const* dwconv_w, const float* const* dwconv_b,
+                   const float* const* down_w, const float* action_w, const float* action_b, const float* value_w,
+                   const float* value_b, float* packed, void* stream);
+int g2048_rollout_urm(const G2048Rollout* params, int32_t loops, void* stream);
+
 /* ---- policy update: fused y = res + ReLU(LayerNorm(z)) and its backward ---------------------
  * The elementwise chain of a GameMLP block (game.py:1038-1046; stem: game.py:1069-1073, res = NULL)
  * in eval/p=0 dropout form.  Row-major [n,h] fp32, h a multiple of 4 up to 256, eps = 1e-5 in the

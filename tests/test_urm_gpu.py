@@ -1,0 +1,115 @@
+"""GameURM fused rollout kernel (BASELINE config #5) through the C ABI: the integer env path
+bit-exact against the oracle; log-probs / values against (a) a torch emulation of the kernel's
+arithmetic (bf16 GEMM operands and K/V, fp32 elsewhere) tightly and (b) the fp32 reference model
+(the reference-generated fixture tests/golden/model_urm.npz) at bf16 tolerance."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+
+RESET_TWEAK = 0x9E3779B97F4A7C15
+
+
+def load_urm(golden):
+    from g2048 import policy
+    g = golden("model_urm")
+    m = policy.GameURM(policy.GameURMConfig(dropout=0.0)).eval()
+    m.load_state_dict(policy.load_state_dict_from_npz(g))
+    return m.cuda(), g
+
+
+def urm_bf16_emulation(model, x48):
+    from g2048.policy import rms_norm
+    r = lambda t: t.bfloat16().float()
+    b = x48.shape[0]
+    cfg = model.config
+    emb = model.stem(x48.view(b, 16, 3))
+    h = model.init_hidden.expand(b, -1, -1).clone()
+    for _ in range(cfg.num_loops):
+        h = h + emb
+        for layer in model.layers:
+            a = layer.attn
+            qkv = (r(h) @ r(a.qkv_proj.weight).T).view(b, 16, 3, a.num_heads, a.head_dim).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv[0], r(qkv[1]), r(qkv[2])
+            p = torch.softmax((q @ k.transpose(-1, -2)) * 0.25, dim=-1)
+            o = (p @ v).transpose(1, 2).reshape(b, 16, 64)
+            h = rms_norm(h + r(o) @ r(a.o_proj.weight).T, 1e-5)
+            m = layer.mlp
+            gate, up = (r(h) @ r(m.gate_up_proj.weight).T).chunk(2, dim=-1)
+            x = F.silu(gate) * up
+            c = m.dwconv(x.transpose(1, 2))[..., :16]
+            xc = F.silu(c).transpose(1, 2)
+            h = rms_norm(h + r(xc) @ r(m.down_proj.weight).T, 1e-5)
+    pooled = h.mean(1)
+    return model.action_head(pooled), model.value_head(pooled).squeeze(1)
+
+
+def masked_lp(logits, legal):
+    illegal = ((legal.reshape(-1).long()[:, None] >> torch.arange(4, device=logits.device)) & 1) == 0
+    return torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1)
+
+
+def test_urm_rollout_first_step_matches_reference_fixture(golden):
+    from g2048 import rollout
+    model, g = load_urm(golden)
+    boards_np = g["board"]
+    keep = np.array([O.potentials_batch(boards_np[i:i + 1])[0, 5] != 0 for i in range(len(boards_np))])
+    boards_np = boards_np[keep]
+    ref_logits, ref_v = torch.from_numpy(g["logits"][keep]).cuda(), torch.from_numpy(g["value"][keep]).cuda().squeeze(1)
+    boards = torch.from_numpy(boards_np.view(np.int64).copy()).cuda()
+    B = boards.numel()
+    buf = rollout.rollout(rollout.pack_policy(model), boards.clone(), 1, seed=5, env0=0, ctr0=1, auto_reset=False,
+                          alive=torch.ones(B, dtype=torch.uint8, device="cuda"))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(buf.boards[0].cpu().numpy().view(np.uint64), boards_np)
+    want = masked_lp(ref_logits, buf.legal[0])
+    got = buf.logp[0]
+    fin = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got), fin)
+    err_lp = float((got[fin] - want[fin]).abs().max())
+    err_v = float((buf.value[0] - ref_v).abs().max())
+    print(f"URM tensor-core rollout vs the reference's fp32 outputs: max |dlogp| = {err_lp:.4f}, max |dV| = {err_v:.4f}")
+    assert err_lp < 0.15 and err_v < 0.15
+    from g2048 import env
+    with torch.no_grad():
+        el, ev = urm_bf16_emulation(model, env.encode(boards))
+    emu = masked_lp(el, buf.legal[0])
+    torch.testing.assert_close(got[fin], emu[fin], rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(buf.value[0], ev, rtol=2e-2, atol=2e-2)
+    assert float((got[fin] - emu[fin]).abs().mean()) < 2e-3
+
+
+@pytest.mark.parametrize("B,T,layers", [(100, 6, 2), (8, 3, 1), (1000, 2, 2)])
+def test_urm_rollout_env_path_bit_exact(B, T, layers):
+    from g2048 import env, policy, rollout
+    torch.manual_seed(B)
+    model = policy.GameURM(policy.GameURMConfig(num_layers=layers, dropout=0.0)).cuda().eval()
+    seed, env0 = 31, 77
+    boards = env.reset(B, device=0, seed=seed, env0=env0, ctr=0)
+    start = boards.clone()
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=env0, ctr0=1, auto_reset=True)
+    torch.cuda.synchronize()
+    b = start.cpu().numpy().view(np.uint64)
+    for t in range(T):
+        np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64), b)
+        nb, info = O.step_batch(b, buf.actions[t].cpu().numpy(), seed=seed, env0=env0, ctr=1 + t)
+        assert (info["invalid"] == 0).all()
+        np.testing.assert_array_equal(buf.legal[t].cpu().numpy(), info["legal_before"])
+        np.testing.assert_array_equal(buf.points[t].cpu().numpy(), info["points"])
+        np.testing.assert_array_equal(buf.flags[t].cpu().numpy(), 0x80 | info["legal_after"] | (info["done"] << 4))
+        d = info["done"].astype(bool)
+        if d.any():
+            nb = np.where(d, O.reset_batch(B, seed=seed ^ RESET_TWEAK, env0=env0, ctr=1 + t), nb)
+        b = nb
+    with torch.no_grad():
+        el, ev = urm_bf16_emulation(model, env.encode(buf.boards.reshape(-1)))
+    emu = masked_lp(el, buf.legal)
+    got = buf.logp.reshape(-1, 4)
+    fin = torch.isfinite(emu)
+    assert torch.equal(torch.isfinite(got), fin)
+    torch.testing.assert_close(got[fin], emu[fin], rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(buf.value.reshape(-1), ev, rtol=2e-2, atol=2e-2)
