@@ -10,7 +10,7 @@ for p in (ROOT, os.path.join(ROOT, "2048-ppo_b200")):
 import torch  # noqa: E402
 
 from g2048 import env, rollout  # noqa: E402
-from g2048.policy import GameMLP, MLPConfig  # noqa: E402
+from g2048.policy import GameMLP, GameURM, GameURMConfig, MLPConfig  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=148 * 128)
@@ -19,10 +19,14 @@ ap.add_argument("--hidden", type=int, default=196)
 ap.add_argument("--layers", type=int, default=2)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--precision", default="fp32")
+ap.add_argument("--urm", action="store_true", help="GameURM (config #5) instead of GameMLP")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = GameMLP(MLPConfig(hidden_dim=a.hidden, num_layers=a.layers, dropout=0.0)).to(dev).eval()
+if a.urm:
+    model = GameURM(GameURMConfig(dropout=0.0)).to(dev).eval()
+else:
+    model = GameMLP(MLPConfig(hidden_dim=a.hidden, num_layers=a.layers, dropout=0.0)).to(dev).eval()
 pol = rollout.pack_policy(model)
 boards = env.reset(a.envs, device=dev, seed=1, env0=0, ctr=0)
 buf = rollout.RolloutBuffers.allocate(a.steps, a.envs, dev)
