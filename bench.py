@@ -226,6 +226,32 @@ def rollout_section(args, dev, world, rank, barrier):
         v = torch.tensor([step_ms, tf32_ms], device=dev)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         step_ms, tf32_ms = (float(x) for x in v.tolist())
+    # ---- C5: GameURM rollout (default config), a few steps at the configured env count
+    urm = None
+    if args.urm_envs > 0:
+        from g2048 import env as genv, rollout as gro
+        from g2048.policy import GameURM, GameURMConfig
+        torch.manual_seed(5)
+        um = GameURM(GameURMConfig(dropout=0.0)).to(dev).eval()
+        upol = gro.pack_policy(um)
+        ub = genv.reset(args.urm_envs, device=dev, seed=5, env0=rank * args.urm_envs, ctr=0)
+        ubuf = gro.RolloutBuffers.allocate(args.urm_steps, args.urm_envs, dev)
+        gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=1, out=ubuf)
+        barrier()
+        ev0.record()
+        gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=1 + args.urm_steps, out=ubuf)
+        ev1.record()
+        barrier()
+        ums = ev0.elapsed_time(ev1)
+        if world > 1:
+            v = torch.tensor([ums], device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            ums = float(v.item())
+        urm = {"workload": f"c5: GameURM (hidden 64, 2 layers, 4 heads, 4 loops) fused rollout, {args.urm_envs} envs x {args.urm_steps} steps per GPU",
+               "env_steps_per_sec": world * args.urm_envs * args.urm_steps / (ums * 1e-3), "ms": ums,
+               "kernel": "rollout_urm_kernel (bf16 tcgen05.mma projections, CUDA-core attention)"}
+        del ubuf, ub
+
     flops = 2 * (48 * 196 + 2 * 196 * 196 + 5 * 196)
     env_sps = world * n_local / (ro_ms * 1e-3)
     return {
@@ -245,6 +271,7 @@ def rollout_section(args, dev, world, rank, barrier):
         "rollout_model_tflops": env_sps * flops / 1e12,
         "rollout_frac_of_bf16_peak": (env_sps / world) * flops / 1e12 / bf16_peak(),
         "grad_allreduce_bytes": 88401 * 4,
+        "urm": urm,
         "loss": stats["loss"],
     }
 
@@ -449,6 +476,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     ap.add_argument("--rollout-envs", type=int, default=65536)
     ap.add_argument("--rollout-steps", type=int, default=512)
+    ap.add_argument("--urm-envs", type=int, default=262144, help="config #5 env count per GPU (0 = skip)")
+    ap.add_argument("--urm-steps", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
