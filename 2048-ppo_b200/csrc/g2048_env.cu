@@ -234,6 +234,52 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint64_t* __restrict_
     o[2] = pos_feature(cell & 3);
 }
 
+// Symmetry augmentation (train.py:774-881, game.py:508-590) of recorded steps: op 0 = mirror
+// horizontal, 1 = mirror vertical, 2/3/4 = rotate 90/180/270 clockwise.  Boards are transformed by
+// nibble permutations; the action, the legal mask and the four log-probs move with the direction
+// remap new[remap(old)] = old (train.py:784-824).
+__device__ __forceinline__ Board mirror_v(Board b) {
+    return {__funnelshift_l(b.hi, b.hi, 16), __funnelshift_l(b.lo, b.lo, 16)};
+}
+__device__ __forceinline__ Board apply_symmetry(Board b, uint32_t op) {
+    switch (op) {
+        case 0: return rev_rows(b);
+        case 1: return mirror_v(b);
+        case 2: return rev_rows(transpose(b));      // rotated[j][3-i] = g[i][j]
+        case 3: return rev_rows(mirror_v(b));
+        default: return mirror_v(transpose(b));     // rotated[3-j][i] = g[i][j]
+    }
+}
+__global__ void __launch_bounds__(256)
+augment_kernel(const uint64_t* __restrict__ before, const uint64_t* __restrict__ after, const uint8_t* __restrict__ action,
+               const uint8_t* __restrict__ legal, const float4* __restrict__ logp, const uint8_t* __restrict__ op,
+               uint64_t* __restrict__ before_out, uint64_t* __restrict__ after_out, uint8_t* __restrict__ action_out,
+               uint8_t* __restrict__ legal_out, float4* __restrict__ logp_out, int64_t n) {
+    // remap tables, one nibble per old direction (UP, DOWN, LEFT, RIGHT)
+    const uint32_t remap_tab[5] = {0x2310u, 0x3201u, 0x1023u, 0x2301u, 0x0132u};
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t o = min(uint32_t(op[i]), 4u), tab = remap_tab[o];
+    before_out[i] = pack_board(apply_symmetry(make_board(before[i]), o));
+    after_out[i] = pack_board(apply_symmetry(make_board(after[i]), o));
+    const uint32_t a = action[i] & 3u, lm = legal[i] & 15u;
+    action_out[i] = uint8_t((tab >> (4 * a)) & 3u);
+    const float4 l = logp[i];
+    const float lp[4] = {l.x, l.y, l.z, l.w};
+    float out[4];
+    uint32_t lm_out = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const uint32_t nd = (tab >> (4 * d)) & 3u;
+        lm_out |= ((lm >> d) & 1u) << nd;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (nd == uint32_t(k)) out[k] = lp[d];
+    }
+    legal_out[i] = uint8_t(lm_out);
+    logp_out[i] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
 // below this many units the 224 KiB table staging (per CTA) costs more than it saves
 constexpr int64_t STAGED_MIN_UNITS = 1 << 17;
 
@@ -311,6 +357,21 @@ int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, in
     potentials_kernel<<<unsigned((n + 255) / 256), 256, 0, cudaStream_t(stream)>>>(static_cast<const uint32_t*>(d_lut),
                                                                                   boards, out, n);
     G2048_CHECK_LAUNCH("potentials_kernel");
+    return G2048_OK;
+}
+
+int g2048_augment(const uint64_t* before, const uint64_t* after, const uint8_t* action, const uint8_t* legal,
+                  const float* logp, const uint8_t* op, uint64_t* before_out, uint64_t* after_out, uint8_t* action_out,
+                  uint8_t* legal_out, float* logp_out, int64_t n, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_augment: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(before && after && action && legal && logp && op && before_out && after_out && action_out && legal_out &&
+                      logp_out,
+                  "g2048_augment: NULL pointer argument");
+    augment_kernel<<<unsigned((n + 255) / 256), 256, 0, cudaStream_t(stream)>>>(
+        before, after, action, legal, reinterpret_cast<const float4*>(logp), op, before_out, after_out, action_out,
+        legal_out, reinterpret_cast<float4*>(logp_out), n);
+    G2048_CHECK_LAUNCH("augment_kernel");
     return G2048_OK;
 }
 

@@ -160,6 +160,25 @@ def encode(boards: torch.Tensor) -> torch.Tensor:
     return out
 
 
+MIRROR_H, MIRROR_V, ROT90, ROT180, ROT270 = 0, 1, 2, 3, 4
+
+
+def augment(before, after, action, legal, logp, op) -> dict:
+    """Mirror / rotate recorded steps (train.py:774-881).  op: uint8[n] of MIRROR_H .. ROT270."""
+    before, after = _req(before, torch.int64, "before"), _req(after, torch.int64, "after")
+    action, legal, op = _req(action, torch.uint8, "action"), _req(legal, torch.uint8, "legal"), _req(op, torch.uint8, "op")
+    logp = _req(logp, torch.float32, "logp")
+    n = before.numel()
+    dev = init(before.device)
+    with torch.cuda.device(dev):
+        out = dict(before=torch.empty_like(before), after=torch.empty_like(after), action=torch.empty_like(action),
+                   legal=torch.empty_like(legal), logp=torch.empty_like(logp))
+        _lib.call("g2048_augment", _ptr(before), _ptr(after), _ptr(action), _ptr(legal), _ptr(logp), _ptr(op),
+                  _ptr(out["before"]), _ptr(out["after"]), _ptr(out["action"]), _ptr(out["legal"]), _ptr(out["logp"]),
+                  n, _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------- host helpers
 
 def pack_grid(grid) -> int:

@@ -251,29 +251,32 @@ def play_games_batched(model, num_games: int, max_steps: int | None = None, devi
 
 
 def smoke(dev) -> None:
-    """Tiny fused rollout on `dev`, checked against the oracle env and the torch policy."""
+    """Tiny fused rollouts on `dev` (fp32 FFMA, bf16 tcgen05, GameURM), checked against the oracle env
+    and the torch policy."""
     from oracle import oracle as O
-    from .policy import GameMLP, MLPConfig
+    from .policy import GameMLP, GameURM, GameURMConfig, MLPConfig
     torch.manual_seed(0)
-    model = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.0)).to(dev).eval()
-    B, T, seed = 300, 24, 7
-    boards = env.reset(B, device=dev, seed=seed, env0=0, ctr=0)
-    start = boards.clone()
-    buf = rollout(pack_policy(model), boards, T, seed=seed, env0=0, ctr0=1, auto_reset=False,
-                  alive=torch.ones(B, dtype=torch.uint8, device=dev))
-    b = start.cpu().numpy().view(np.uint64)
-    for t in range(T):
-        valid = (buf.flags[t].cpu().numpy() & 0x80) != 0
-        np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64)[valid], b[valid])
-        nb, info = O.step_batch(b, buf.actions[t].cpu().numpy(), seed=seed, env0=0, ctr=1 + t)
-        np.testing.assert_array_equal(buf.points[t].cpu().numpy()[valid], info["points"][valid])
-        with torch.no_grad():
-            logits, v = model(env.encode(buf.boards[t]))
-        lm = buf.legal[t].long()
-        illegal = ((lm[:, None] >> torch.arange(4, device=dev)) & 1) == 0
-        ref = torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1)
-        vt = torch.from_numpy(valid).to(dev)
-        fin = torch.isfinite(ref) & vt[:, None]
-        assert torch.allclose(buf.logp[t][fin], ref[fin], rtol=1e-4, atol=1e-4)
-        assert torch.allclose(buf.value[t][vt], v.squeeze(1)[vt], rtol=1e-4, atol=1e-4)
-        b = np.where(valid, nb, b)
+    mlp = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.0)).to(dev).eval()
+    urm = GameURM(GameURMConfig(dropout=0.0)).to(dev).eval()
+    for model, precision, tol in ((mlp, "fp32", 1e-4), (mlp, "bf16", 0.1), (urm, "bf16", 0.3)):
+        B, T, seed = 300, 12, 7
+        boards = env.reset(B, device=dev, seed=seed, env0=0, ctr=0)
+        start = boards.clone()
+        buf = rollout(pack_policy(model), boards, T, seed=seed, env0=0, ctr0=1, auto_reset=False,
+                      alive=torch.ones(B, dtype=torch.uint8, device=dev), precision=precision)
+        b = start.cpu().numpy().view(np.uint64)
+        for t in range(T):
+            valid = (buf.flags[t].cpu().numpy() & 0x80) != 0
+            np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64)[valid], b[valid])
+            nb, info = O.step_batch(b, buf.actions[t].cpu().numpy(), seed=seed, env0=0, ctr=1 + t)
+            np.testing.assert_array_equal(buf.points[t].cpu().numpy()[valid], info["points"][valid])
+            with torch.no_grad():
+                logits, v = model(env.encode(buf.boards[t]))
+            lm = buf.legal[t].long()
+            illegal = ((lm[:, None] >> torch.arange(4, device=dev)) & 1) == 0
+            ref = torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1)
+            vt = torch.from_numpy(valid).to(dev)
+            fin = torch.isfinite(ref) & vt[:, None]
+            assert torch.allclose(buf.logp[t][fin], ref[fin], rtol=tol, atol=tol)
+            assert torch.allclose(buf.value[t][vt], v.squeeze(1)[vt], rtol=tol, atol=tol)
+            b = np.where(valid, nb, b)

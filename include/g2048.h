@@ -97,6 +97,14 @@ int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, in
 /* game.py:92-101 to_model_format: out f32[n,48] = 16 x [exponent, row/3, col/3]. */
 int g2048_encode(const uint64_t* boards, float* out, int64_t n, void* stream);
 
+/* Symmetry augmentation of recorded steps (train.py:774-881; game.py:508-590 mirror_grid /
+ * rotate_grid): op[i] = 0 mirror horizontal, 1 mirror vertical, 2 / 3 / 4 rotate 90 / 180 / 270
+ * clockwise.  state_before / result_state boards are transformed, the action, the legal-direction
+ * bits and the four log-probs (f32[n,4]) follow the direction remap of train.py:784-824. */
+int g2048_augment(const uint64_t* before, const uint64_t* after, const uint8_t* action, const uint8_t* legal,
+                  const float* logp, const uint8_t* op, uint64_t* before_out, uint64_t* after_out, uint8_t* action_out,
+                  uint8_t* legal_out, float* logp_out, int64_t n, void* stream);
+
 /* ---- rollout buffers -------------------------------------------------------------------
  * Time-major [T,B] arrays (index t*B + b).  flags = the g2048_step flags of the move plus
  * G2048_FLAG_VALID when the slot holds a recorded move (a finished game without auto-reset

@@ -408,8 +408,24 @@ def gen_urm(rng):
     print("model_urm:", {k: tuple(v.shape) for k, v in model.state_dict().items()})
 
 
+def gen_augment(rng):
+    """Reference mirror_grid / rotate_grid (game.py:508-590) on random boards: ops 0..4 =
+    mirror horizontal, mirror vertical, rotate 90 / 180 / 270 clockwise."""
+    boards = random_boards(rng)[:2000]
+    ops = [lambda g: G.Game2048.mirror_grid(g, "horizontal"), lambda g: G.Game2048.mirror_grid(g, "vertical"),
+           lambda g: G.Game2048.rotate_grid(g, 90), lambda g: G.Game2048.rotate_grid(g, 180),
+           lambda g: G.Game2048.rotate_grid(g, 270)]
+    out = np.array([[pack(op(b.reshape(4, 4).tolist())) for op in ops] for b in boards], dtype=np.uint64)
+    np.savez_compressed(os.path.join(OUT, "augment.npz"),
+                        board=np.array([pack(b.reshape(4, 4)) for b in boards], dtype=np.uint64), transformed=out)
+    print("augment:", out.shape)
+
+
 if __name__ == "__main__":
-    if "--urm-only" in sys.argv:
+    if "--augment-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        gen_augment(np.random.default_rng(17))
+    elif "--urm-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         gen_urm(np.random.default_rng(13))
     else:

@@ -255,3 +255,29 @@ def test_facade_matches_reference_semantics(env):
     assert g2.to_model_format().shape == (48,)
     new, pts, done, info = g2.step(g2.current_valid_directions()[0])
     assert not info["invalid_move"] and "monotonicity_before" in info
+
+
+def test_augment_matches_reference_and_commutes_with_the_env(env, golden):
+    """Boards against the reference's mirror_grid / rotate_grid (fixture); the direction remap against the
+    environment itself: moving the transformed board in the remapped direction gives the transformed successor."""
+    g = golden("augment")
+    boards = g["board"]
+    n = len(boards)
+    ex = env.expand4(dev_boards(boards))
+    succ, legal = host_u64(ex["succ"]), ex["legal"]
+    rng = np.random.default_rng(0)
+    action = rng.integers(0, 4, n).astype(np.uint8)
+    logp = torch.randn((n, 4), generator=torch.Generator().manual_seed(1)).cuda()
+    after = succ[np.arange(n), action]
+    for op in range(5):
+        r = env.augment(dev_boards(boards), dev_boards(after), torch.from_numpy(action).cuda(), legal, logp,
+                        torch.full((n,), op, dtype=torch.uint8, device="cuda"))
+        np.testing.assert_array_equal(host_u64(r["before"]), g["transformed"][:, op])
+        ex2 = env.expand4(r["before"])
+        np.testing.assert_array_equal(r["legal"].cpu().numpy(), ex2["legal"].cpu().numpy())
+        a2 = r["action"].cpu().numpy()
+        np.testing.assert_array_equal(host_u64(ex2["succ"])[np.arange(n), a2], host_u64(r["after"]))
+        got = torch.gather(r["logp"], 1, r["action"].long()[:, None]).squeeze(1)
+        want = torch.gather(logp, 1, torch.from_numpy(action).cuda().long()[:, None]).squeeze(1)
+        assert torch.equal(got, want)
+        assert torch.equal(r["logp"].sort(dim=1).values, logp.sort(dim=1).values)
