@@ -123,6 +123,58 @@ def step(boards: torch.Tensor, actions: torch.Tensor, *, seed: int = 0, env0: in
     return out
 
 
+class HostStepper:
+    """Game2048.step for HOST (pinned) arrays: the batch is cut into chunks that flow through
+    host->device copy, g2048_step and device->host copies on a ring of CUDA streams, so the two PCIe
+    directions and the kernel overlap.  Same results as step(); this is the host-buffer entry point
+    that bench.py's `e2e` figure measures."""
+
+    def __init__(self, n: int, *, device=None, chunk: int = 1 << 19, streams: int = 3, shaping: bool = True):
+        self.n, self.chunk, self.shaping = n, min(chunk, max(n, 1)), shaping
+        self.dev = init(device)
+        self.table = lut(self.dev)
+        with torch.cuda.device(self.dev):
+            self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(streams)]
+            c = self.chunk
+            self.slots = [dict(boards=torch.empty(c, dtype=torch.int64, device=self.dev),
+                               actions=torch.empty(c, dtype=torch.uint8, device=self.dev),
+                               out_boards=torch.empty(c, dtype=torch.int64, device=self.dev),
+                               points=torch.empty(c, dtype=torch.int32, device=self.dev),
+                               flags=torch.empty(c, dtype=torch.uint8, device=self.dev),
+                               shaping=torch.empty(c, dtype=torch.int64, device=self.dev) if shaping else None)
+                          for _ in range(streams)]
+
+    def step(self, h_boards, h_actions, h_out: dict, *, seed: int = 0, env0: int = 0, ctr: int = 0) -> dict:
+        """h_boards int64[n], h_actions uint8[n], h_out = dict(boards, points, flags[, shaping]) of pinned
+        host tensors.  Returns h_out after all copies completed."""
+        for t in (h_boards, h_actions, *[v for v in h_out.values() if v is not None]):
+            if t.is_cuda or not t.is_pinned():
+                raise ValueError("HostStepper works on pinned host tensors")
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            st.wait_stream(cur)
+        k = 0
+        for lo in range(0, self.n, self.chunk):
+            hi = min(self.n, lo + self.chunk)
+            m = hi - lo
+            st, sl = self.streams[k % len(self.streams)], self.slots[k % len(self.slots)]
+            k += 1
+            with torch.cuda.stream(st):
+                sl["boards"][:m].copy_(h_boards[lo:hi], non_blocking=True)
+                sl["actions"][:m].copy_(h_actions[lo:hi], non_blocking=True)
+                _lib.call("g2048_step", _ptr(self.table), _ptr(sl["boards"]), _ptr(sl["actions"]), _ptr(sl["out_boards"]),
+                          _ptr(sl["points"]), _ptr(sl["flags"]), _ptr(sl["shaping"]), m, None, seed, env0 + lo, ctr,
+                          C.c_void_p(st.cuda_stream))
+                h_out["boards"][lo:hi].copy_(sl["out_boards"][:m], non_blocking=True)
+                h_out["points"][lo:hi].copy_(sl["points"][:m], non_blocking=True)
+                h_out["flags"][lo:hi].copy_(sl["flags"][:m], non_blocking=True)
+                if self.shaping:
+                    h_out["shaping"][lo:hi].copy_(sl["shaping"][:m], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return h_out
+
+
 def expand4(boards: torch.Tensor, *, want_max_tile: bool = False, out: dict | None = None) -> dict:
     """All four pre-spawn successors (game.py:121-184, 295-299)."""
     boards = _req(boards, torch.int64, "boards")

@@ -393,8 +393,9 @@ def run_ours(args):
 
 
 def e2e_section(args, dev, world, rank, barrier, sets, env0):
-    """Same metric through the public host API with HOST pinned buffers: every step copies the
-    inputs host->device, runs g2048_step and copies every output device->host."""
+    """Same metric through the public host-buffer API (g2048.env.HostStepper) with HOST pinned buffers:
+    every step copies the inputs host->device, runs g2048_step and copies every output device->host
+    (chunks pipelined over 3 streams so the two PCIe directions and the kernel overlap)."""
     import torch
     import torch.distributed as dist
 
@@ -406,16 +407,10 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
                  points=torch.empty(N_TRANS, dtype=torch.int32).pin_memory(),
                  flags=torch.empty(N_TRANS, dtype=torch.uint8).pin_memory(),
                  shaping=torch.empty(N_TRANS, dtype=torch.int64).pin_memory())
-    d_in = dict(boards=torch.empty(N_TRANS, dtype=torch.int64, device=dev),
-                actions=torch.empty(N_TRANS, dtype=torch.uint8, device=dev))
-    d_out = sets[0]["out"]
+    stepper = env.HostStepper(N_TRANS, device=dev)
 
     def e2e_step(k):
-        d_in["boards"].copy_(h_boards, non_blocking=True)
-        d_in["actions"].copy_(h_actions, non_blocking=True)
-        env.step(d_in["boards"], d_in["actions"], seed=2048, env0=env0, ctr=1000 + k, shaping=True, out=d_out)
-        for key in h_out:
-            h_out[key].copy_(d_out[key], non_blocking=True)
+        stepper.step(h_boards, h_actions, h_out, seed=2048, env0=env0, ctr=1000 + k)
 
     e2e_steps = max(3, min(args.steps, 20))
     for w in range(3):

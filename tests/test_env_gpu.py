@@ -281,3 +281,21 @@ def test_augment_matches_reference_and_commutes_with_the_env(env, golden):
         want = torch.gather(logp, 1, torch.from_numpy(action).cuda().long()[:, None]).squeeze(1)
         assert torch.equal(got, want)
         assert torch.equal(r["logp"].sort(dim=1).values, logp.sort(dim=1).values)
+
+
+def test_host_stepper_matches_device_step(env):
+    n = (1 << 20) + 12345
+    boards = random_boards(n, 77)
+    actions = (np.arange(n) % 4).astype(np.uint8)
+    hb = torch.from_numpy(boards.view(np.int64).copy()).pin_memory()
+    ha = torch.from_numpy(actions).pin_memory()
+    h_out = dict(boards=torch.empty(n, dtype=torch.int64).pin_memory(), points=torch.empty(n, dtype=torch.int32).pin_memory(),
+                 flags=torch.empty(n, dtype=torch.uint8).pin_memory(), shaping=torch.empty(n, dtype=torch.int64).pin_memory())
+    st = env.HostStepper(n, device=0)
+    st.step(hb, ha, h_out, seed=3, env0=100, ctr=9)
+    torch.cuda.synchronize()
+    r = env.step(hb.cuda(), ha.cuda(), seed=3, env0=100, ctr=9)
+    for k in ("boards", "points", "flags", "shaping"):
+        assert torch.equal(h_out[k], r[k].cpu()), k
+    with pytest.raises(ValueError):
+        st.step(hb.cuda(), ha, h_out)
