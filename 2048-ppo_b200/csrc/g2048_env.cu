@@ -234,6 +234,137 @@ __global__ void __launch_bounds__(256) encode_kernel(const uint64_t* __restrict_
     o[2] = pos_feature(cell & 3);
 }
 
+// ------------------------------------------------------------------ float potentials (logged only)
+// adjacency_bonus game.py:402-442, monotonic_chain_score game.py:445-506, _choose_anchor_corner
+// game.py:634-668, topological_score game.py:803-921.  Not on the throughput path (their weights
+// never enter the reward, train.py:709-714): one thread per (board, pre-spawn successor) pair, plain
+// loops over the 16 cells, doubles with the Python operation order (no FMA contraction) so the
+// results are bit-identical to the reference's floats.  The chain score's DFS is replaced by the
+// equivalent dynamic programme over exponents (a chain descends by exactly one per step, so
+// best[cell] = exp + max best[neighbour with exp-1], filled in increasing exponent order).
+struct Cells {
+    int v[16];
+    __device__ __forceinline__ int at(int r, int c) const { return v[4 * r + c]; }
+};
+__device__ __forceinline__ Cells unpack_cells(uint64_t b) {
+    Cells c;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c.v[i] = int((b >> (4 * i)) & 15u);
+    return c;
+}
+__device__ double adjacency_bonus(const Cells& g) {
+    int mx = 0, mp = 0;
+    for (int i = 0; i < 16; ++i)
+        if (g.v[i] > mx) { mx = g.v[i]; mp = i; }
+    double bonus = 0.0;
+    const int r = mp >> 2, c = mp & 3;
+    if (r > 0 && g.at(r - 1, c) > 0) bonus = __dadd_rn(bonus, __dmul_rn(double(g.at(r - 1, c)), 0.5));
+    if (r < 3 && g.at(r + 1, c) > 0) bonus = __dadd_rn(bonus, __dmul_rn(double(g.at(r + 1, c)), 0.5));
+    if (c > 0 && g.at(r, c - 1) > 0) bonus = __dadd_rn(bonus, __dmul_rn(double(g.at(r, c - 1)), 0.5));
+    if (c < 3 && g.at(r, c + 1) > 0) bonus = __dadd_rn(bonus, __dmul_rn(double(g.at(r, c + 1)), 0.5));
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (g.at(i, j) >= 5) {
+                if (j < 3 && g.at(i, j + 1) >= 5) bonus = __dadd_rn(bonus, __dmul_rn(double(g.at(i, j) + g.at(i, j + 1)), 0.25));
+                if (i < 3 && g.at(i + 1, j) >= 5) bonus = __dadd_rn(bonus, __dmul_rn(double(g.at(i, j) + g.at(i + 1, j)), 0.25));
+            }
+    return bonus;
+}
+__device__ double chain_score(const Cells& g) {
+    int mx = 0;
+    for (int i = 0; i < 16; ++i) mx = max(mx, g.v[i]);
+    if (mx == 0) return 0.0;
+    int best[16];
+    for (int i = 0; i < 16; ++i) best[i] = 0;
+    for (int e = 1; e <= mx; ++e)
+        for (int i = 0; i < 16; ++i)
+            if (g.v[i] == e) {
+                const int r = i >> 2, c = i & 3;
+                int cont = 0;
+                if (r > 0 && g.v[i - 4] == e - 1) cont = max(cont, best[i - 4]);
+                if (r < 3 && g.v[i + 4] == e - 1) cont = max(cont, best[i + 4]);
+                if (c > 0 && g.v[i - 1] == e - 1) cont = max(cont, best[i - 1]);
+                if (c < 3 && g.v[i + 1] == e - 1) cont = max(cont, best[i + 1]);
+                best[i] = e + cont;
+            }
+    int out = 0;
+    for (int i = 0; i < 16; ++i)
+        if (g.v[i] == mx) out = max(out, best[i]);
+    return double(out);
+}
+__device__ int anchor_corner(const Cells& g) {
+    int mx = 0;
+    for (int i = 0; i < 16; ++i) mx = max(mx, g.v[i]);
+    if (mx == 0) return 0;
+    int first = -1;
+    for (int i = 0; i < 16; ++i)
+        if (g.v[i] == mx) {
+            if (first < 0) first = i;
+            if (i == 0 || i == 3 || i == 12 || i == 15) return i;       // first max tile that sits in a corner
+        }
+    const int r = first >> 2, c = first & 3;
+    const int corners[4] = {0, 3, 12, 15};
+    int bestc = 0, bd = 1 << 30;
+    for (int k = 0; k < 4; ++k) {
+        const int d = abs((corners[k] >> 2) - r) + abs((corners[k] & 3) - c);
+        if (d < bd) { bd = d; bestc = corners[k]; }
+    }
+    return bestc;
+}
+__device__ double topological_score(const Cells& g, int anchor) {
+    int mx = 0, ntiles = 0;
+    for (int i = 0; i < 16; ++i) { mx = max(mx, g.v[i]); ntiles += g.v[i] > 0; }
+    if (!ntiles) return 0.0;
+    const int cr = anchor >> 2, cc = anchor & 3, rd = cr == 0 ? 1 : -1, cd = cc == 0 ? 1 : -1;
+    int order[16], idx_of[16];
+    for (int i = 0, n = 0; i < 4; ++i)
+        for (int s = 0; s < 4; ++s, ++n) {
+            const int row = cr + i * rd, col = (i & 1) ? cc + 3 * cd - s * cd : cc + s * cd;
+            order[n] = 4 * row + col;
+            idx_of[4 * row + col] = n;
+        }
+    double score = 0.0;
+    for (int i = 0; i < 16; ++i)
+        if (g.v[i] > 0) score = __dadd_rn(score, __dmul_rn(double((16 - idx_of[i]) * g.v[i]), 0.1));
+    double bonus = 0.0, penalty = 0.0, prev = INFINITY;
+    for (int k = 0; k < 16; ++k) {
+        const int v = g.v[order[k]];
+        if (v == 0) continue;
+        if (double(v) <= prev) bonus = __dadd_rn(bonus, __dmul_rn(double(v), 0.2));
+        else penalty = __dadd_rn(penalty, __dmul_rn(__dsub_rn(double(v), prev), 0.5));
+        prev = double(v);
+    }
+    score = __dadd_rn(score, __dsub_rn(bonus, penalty));
+    if (g.v[anchor] == mx) score = __dadd_rn(score, __dmul_rn(double(mx), 2.0));
+    for (int i = 0; i < 16; ++i) {
+        const int v = g.v[i];
+        if (v < 4) continue;
+        const int r = i >> 2, c = i & 3;
+        int lower = 0, total = 0;
+        if (r > 0 && g.v[i - 4] > 0) { total++; lower += g.v[i - 4] < v - 2; }
+        if (r < 3 && g.v[i + 4] > 0) { total++; lower += g.v[i + 4] < v - 2; }
+        if (c > 0 && g.v[i - 1] > 0) { total++; lower += g.v[i - 1] < v - 2; }
+        if (c < 3 && g.v[i + 1] > 0) { total++; lower += g.v[i + 1] < v - 2; }
+        if (total >= 2 && lower >= total - 1 && idx_of[i] > 4) score = __dsub_rn(score, double(v));
+    }
+    return score;
+}
+__global__ void __launch_bounds__(128)
+potentials_ext_kernel(const uint64_t* __restrict__ before, const uint64_t* __restrict__ after, double* __restrict__ out, int64_t n) {
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Cells a = unpack_cells(before[i]), b = unpack_cells(after[i]);
+    const int anchor = anchor_corner(a);
+    double* o = out + 7 * i;
+    o[0] = adjacency_bonus(a);
+    o[1] = adjacency_bonus(b);
+    o[2] = chain_score(a);
+    o[3] = chain_score(b);
+    o[4] = topological_score(a, anchor);
+    o[5] = topological_score(b, anchor);
+    o[6] = double(anchor);
+}
+
 // Symmetry augmentation (train.py:774-881, game.py:508-590) of recorded steps: op 0 = mirror
 // horizontal, 1 = mirror vertical, 2/3/4 = rotate 90/180/270 clockwise.  Boards are transformed by
 // nibble permutations; the action, the legal mask and the four log-probs move with the direction
@@ -357,6 +488,15 @@ int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, in
     potentials_kernel<<<unsigned((n + 255) / 256), 256, 0, cudaStream_t(stream)>>>(static_cast<const uint32_t*>(d_lut),
                                                                                   boards, out, n);
     G2048_CHECK_LAUNCH("potentials_kernel");
+    return G2048_OK;
+}
+
+int g2048_potentials_ext(const uint64_t* before, const uint64_t* after, double* out, int64_t n, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_potentials_ext: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(before && after && out, "g2048_potentials_ext: NULL pointer argument");
+    potentials_ext_kernel<<<unsigned((n + 127) / 128), 128, 0, cudaStream_t(stream)>>>(before, after, out, n);
+    G2048_CHECK_LAUNCH("potentials_ext_kernel");
     return G2048_OK;
 }
 

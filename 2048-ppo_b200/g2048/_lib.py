@@ -27,6 +27,7 @@ _SIGNATURES = {
     "g2048_potentials": [vp, vp, vp, i64, vp],
     "g2048_encode": [vp, vp, i64, vp],
     "g2048_augment": [vp] * 11 + [i64, vp],
+    "g2048_potentials_ext": [vp, vp, vp, i64, vp],
 }
 
 

@@ -202,6 +202,17 @@ def potentials(boards: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def potentials_ext(before: torch.Tensor, after: torch.Tensor) -> torch.Tensor:
+    """float64 [n,7]: adjacency b/a, chain b/a, topological b/a (anchor of `before`), anchor (4*row+col);
+    `after` is the pre-spawn successor (game.py:981-1001)."""
+    before, after = _req(before, torch.int64, "before"), _req(after, torch.int64, "after")
+    dev = init(before.device)
+    with torch.cuda.device(dev):
+        out = torch.empty((before.numel(), 7), dtype=torch.float64, device=dev)
+        _lib.call("g2048_potentials_ext", _ptr(before), _ptr(after), _ptr(out), before.numel(), _stream())
+    return out
+
+
 def encode(boards: torch.Tensor) -> torch.Tensor:
     """game.py:92-101 to_model_format for a batch: float32 [n,48]."""
     boards = _req(boards, torch.int64, "boards")
@@ -345,6 +356,7 @@ class Game2048:
 
     def step(self, direction):  # game.py:952-1030
         a = torch.tensor([direction_index(direction)], dtype=torch.uint8, device=self.device)
+        before = self._b
         r = step(self._b, a, seed=self.seed, env0=self.env_id, ctr=self._ctr, shaping=True)
         flags = int(r["flags"].item())
         if flags & FLAG_OVERFLOW:
@@ -359,8 +371,15 @@ class Game2048:
             return self.grid, 0, done, info
         self._ctr += 1
         s = {k: int(v[0]) for k, v in decode_shaping(r["shaping"].cpu().numpy()).items()}
-        info = {  # game.py:1012-1029 (adjacency / chain / topological are out of scope: SURVEY section 8f N3)
+        pre_spawn = expand4(before)["succ"][0, direction_index(direction)].reshape(1)
+        ext = potentials_ext(before, pre_spawn)[0].tolist()
+        anchor = int(ext[6])
+        info = {  # game.py:1012-1029
             "invalid_move": False,
+            "adjacency_delta": ext[1] - ext[0],
+            "chain_delta": ext[3] - ext[2],
+            "topological_delta": ext[5] - ext[4],
+            "topological_anchor": (anchor // 4, anchor % 4),
             "smoothness_delta": float(s["smooth_after"] - s["smooth_before"]),
             "max_tile_created": s["max_tile_created"],
             "max_exponent_before": s["max_exp_before"],

@@ -94,6 +94,13 @@ int g2048_expand4(const void* d_lut, const uint64_t* boards, uint64_t* succ, int
  * smoothness (339-357), corner bonus (360-399), max exponent, legal mask (295-299). */
 int g2048_potentials(const void* d_lut, const uint64_t* boards, int32_t* out, int64_t n, void* stream);
 
+/* The float potentials Game2048.step also reports but the reward never uses (train.py:709-714):
+ * out f64[n,7] = adjacency_bonus before/after (game.py:402-442), monotonic_chain_score before/after
+ * (game.py:445-506), topological_score before/after with the anchor corner chosen on `before`
+ * (game.py:634-668, 803-921, 986-1001), anchor as 4*row+col.  `after` = the pre-spawn successor.
+ * Bit-identical to the reference's Python floats. */
+int g2048_potentials_ext(const uint64_t* before, const uint64_t* after, double* out, int64_t n, void* stream);
+
 /* game.py:92-101 to_model_format: out f32[n,48] = 16 x [exponent, row/3, col/3]. */
 int g2048_encode(const uint64_t* boards, float* out, int64_t n, void* stream);
 

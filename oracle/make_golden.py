@@ -408,6 +408,31 @@ def gen_urm(rng):
     print("model_urm:", {k: tuple(v.shape) for k, v in model.state_dict().items()})
 
 
+def gen_potentials_ext(rng):
+    """adjacency_bonus / monotonic_chain_score / topological_score(+anchor) of (board, pre-spawn successor)
+    pairs exactly as Game2048.step evaluates them (game.py:981-1001)."""
+    boards = random_boards(rng)
+    rows_b, rows_a, vals = [], [], []
+    for i, e in enumerate(boards):
+        grid = e.reshape(4, 4).tolist()
+        if max(max(r) for r in grid) > 14:
+            continue
+        for a in range(4):
+            if (i + a) % 2:
+                continue
+            after, _, _ = G.Game2048.simulate_move(grid, DIRS[a])
+            anchor = G.Game2048._choose_anchor_corner(grid)
+            vals.append([G.Game2048.adjacency_bonus(grid), G.Game2048.adjacency_bonus(after),
+                         G.Game2048.monotonic_chain_score(grid), G.Game2048.monotonic_chain_score(after),
+                         G.Game2048.topological_score(grid, anchor), G.Game2048.topological_score(after, anchor),
+                         4 * anchor[0] + anchor[1]])
+            rows_b.append(pack(grid))
+            rows_a.append(pack(after))
+    np.savez_compressed(os.path.join(OUT, "potentials_ext.npz"), before=np.array(rows_b, dtype=np.uint64),
+                        after=np.array(rows_a, dtype=np.uint64), values=np.array(vals, dtype=np.float64))
+    print("potentials_ext:", len(vals))
+
+
 def gen_augment(rng):
     """Reference mirror_grid / rotate_grid (game.py:508-590) on random boards: ops 0..4 =
     mirror horizontal, mirror vertical, rotate 90 / 180 / 270 clockwise."""
@@ -422,7 +447,10 @@ def gen_augment(rng):
 
 
 if __name__ == "__main__":
-    if "--augment-only" in sys.argv:
+    if "--ext-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        gen_potentials_ext(np.random.default_rng(19))
+    elif "--augment-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         gen_augment(np.random.default_rng(17))
     elif "--urm-only" in sys.argv:

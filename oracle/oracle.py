@@ -111,6 +111,15 @@ def potentials_batch(boards):
     return out
 
 
+def potentials_ext_batch(before, after):
+    """float64 [n,7]: adjacency b/a, chain b/a, topological b/a (anchor of `before`), anchor (4*row+col)."""
+    before = np.ascontiguousarray(before, dtype=np.uint64)
+    after = np.ascontiguousarray(after, dtype=np.uint64)
+    out = np.empty((before.shape[0], 7), dtype=np.float64)
+    lib().orc_potentials_ext_batch(_p(before), _p(after), C.c_int64(before.shape[0]), _p(out))
+    return out
+
+
 def row_table():
     out4 = np.empty((65536, 4), dtype=np.uint8)
     score = np.empty(65536, dtype=np.uint32)

@@ -579,3 +579,143 @@ void orc_rtg_adv(const int32_t* points, const uint8_t* mono_b, const uint8_t* mo
     }
     __builtin_free(G);
 }
+
+/* ------------------------------------------------------- N3: float potentials (logged only)
+ * adjacency_bonus game.py:402-442, monotonic_chain_score game.py:445-506,
+ * _choose_anchor_corner game.py:634-668, _get_snake_order game.py:611-632,
+ * topological_score game.py:803-921.  Doubles, same operation order as the Python floats. */
+
+double orc_adjacency_bonus(int g[GS][GS]) {
+    int mx = 0, mr = 0, mc = 0;
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j)
+            if (g[i][j] > mx) { mx = g[i][j]; mr = i; mc = j; }
+    double bonus = 0.0;
+    const int di[4] = {-1, 1, 0, 0}, dj[4] = {0, 0, -1, 1};
+    for (int d = 0; d < 4; ++d) {
+        int ni = mr + di[d], nj = mc + dj[d];
+        if (ni >= 0 && ni < GS && nj >= 0 && nj < GS && g[ni][nj] > 0) bonus += g[ni][nj] * 0.5;
+    }
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j)
+            if (g[i][j] >= 5) {
+                if (j < GS - 1 && g[i][j + 1] >= 5) bonus += (g[i][j] + g[i][j + 1]) * 0.25;
+                if (i < GS - 1 && g[i + 1][j] >= 5) bonus += (g[i][j] + g[i + 1][j]) * 0.25;
+            }
+    return bonus;
+}
+
+static double chain_dfs(int g[GS][GS], int i, int j, int expected, int visited[GS][GS]) {
+    if (i < 0 || i >= GS || j < 0 || j >= GS) return 0.0;
+    if (visited[i][j]) return 0.0;
+    if (g[i][j] != expected) return 0.0;
+    visited[i][j] = 1;
+    double best = 0.0;
+    const int di[4] = {-1, 1, 0, 0}, dj[4] = {0, 0, -1, 1};
+    for (int d = 0; d < 4; ++d) {
+        double c = chain_dfs(g, i + di[d], j + dj[d], expected - 1, visited);
+        if (c > best) best = c;
+    }
+    visited[i][j] = 0;
+    return (double)expected + best;
+}
+
+double orc_chain_score(int g[GS][GS]) {
+    int mx = orc_max_exponent(g);
+    if (mx == 0) return 0.0;
+    double best = 0.0;
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j)
+            if (g[i][j] == mx) {
+                int visited[GS][GS];
+                memset(visited, 0, sizeof(visited));
+                double s = chain_dfs(g, i, j, mx, visited);
+                if (s > best) best = s;
+            }
+    return best;
+}
+
+/* returns 4*row + col of the anchor corner */
+int orc_anchor_corner(int g[GS][GS]) {
+    const int cr[4] = {0, 0, GS - 1, GS - 1}, cc[4] = {0, GS - 1, 0, GS - 1};
+    int mx = 0, pr[16], pc[16], n = 0;
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j) {
+            if (g[i][j] > mx) { mx = g[i][j]; n = 0; pr[n] = i; pc[n] = j; n++; }
+            else if (g[i][j] == mx && mx > 0) { pr[n] = i; pc[n] = j; n++; }
+        }
+    if (n == 0) return 0;
+    for (int k = 0; k < n; ++k)
+        if (is_corner(pr[k], pc[k])) return 4 * pr[k] + pc[k];
+    int best = 0, bd = 1 << 30;
+    for (int k = 0; k < 4; ++k) {
+        int d = abs(cr[k] - pr[0]) + abs(cc[k] - pc[0]);
+        if (d < bd) { bd = d; best = k; }
+    }
+    return 4 * cr[best] + cc[best];
+}
+
+double orc_topological(int g[GS][GS], int anchor) {
+    int ntiles = 0, mx = 0;
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j)
+            if (g[i][j] > 0) { ntiles++; if (g[i][j] > mx) mx = g[i][j]; }
+    if (!ntiles) return 0.0;
+    const int cr = anchor / 4, cc = anchor % 4;
+    const int rd = cr == 0 ? 1 : -1, cd = cc == 0 ? 1 : -1;
+    int order_r[16], order_c[16], idx_of[GS][GS], n = 0;
+    for (int i = 0; i < GS; ++i) {           /* game.py:621-631 snake from the corner */
+        int row = cr + i * rd;
+        for (int s = 0; s < GS; ++s) {
+            int col = (i % 2 == 0) ? cc + s * cd : cc + (GS - 1) * cd - s * cd;
+            order_r[n] = row; order_c[n] = col; idx_of[row][col] = n; n++;
+        }
+    }
+    double score = 0.0;
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j)
+            if (g[i][j] > 0) score += (double)((16 - idx_of[i][j]) * g[i][j]) * 0.1;
+    double bonus = 0.0, penalty = 0.0, prev = INFINITY;
+    for (int k = 0; k < 16; ++k) {
+        int v = g[order_r[k]][order_c[k]];
+        if (v == 0) continue;
+        if ((double)v <= prev) bonus += v * 0.2;
+        else penalty += ((double)v - prev) * 0.5;
+        prev = (double)v;
+    }
+    score += bonus - penalty;
+    if (g[cr][cc] == mx) score += mx * 2.0;
+    const int di[4] = {-1, 1, 0, 0}, dj[4] = {0, 0, -1, 1};
+    for (int i = 0; i < GS; ++i)
+        for (int j = 0; j < GS; ++j) {
+            int v = g[i][j];
+            if (v < 4) continue;
+            int lower = 0, total = 0;
+            for (int d = 0; d < 4; ++d) {
+                int ni = i + di[d], nj = j + dj[d];
+                if (ni >= 0 && ni < GS && nj >= 0 && nj < GS && g[ni][nj] > 0) {
+                    total++;
+                    if (g[ni][nj] < v - 2) lower++;
+                }
+            }
+            if (total >= 2 && lower >= total - 1 && idx_of[i][j] > 4) score -= v * 1.0;
+        }
+    return score;
+}
+
+/* out[i] = {adjacency_before, adjacency_after, chain_before, chain_after, topological_before,
+ * topological_after (same anchor, game.py:986-1001), anchor (4*row+col)} for (board, pre-spawn successor) */
+void orc_potentials_ext_batch(const uint64_t* before, const uint64_t* after, int64_t n, double* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        int a[GS][GS], b[GS][GS];
+        orc_unpack(before[i], a);
+        orc_unpack(after[i], b);
+        int anchor = orc_anchor_corner(a);
+        double* o = out + 7 * i;
+        o[0] = orc_adjacency_bonus(a); o[1] = orc_adjacency_bonus(b);
+        o[2] = orc_chain_score(a);     o[3] = orc_chain_score(b);
+        o[4] = orc_topological(a, anchor); o[5] = orc_topological(b, anchor);
+        o[6] = (double)anchor;
+    }
+}

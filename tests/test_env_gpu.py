@@ -299,3 +299,25 @@ def test_host_stepper_matches_device_step(env):
         assert torch.equal(h_out[k], r[k].cpu()), k
     with pytest.raises(ValueError):
         st.step(hb.cuda(), ha, h_out)
+
+
+def test_float_potentials_match_reference_fixture_and_oracle(env, golden):
+    g = golden("potentials_ext")
+    got = env.potentials_ext(dev_boards(g["before"]), dev_boards(g["after"])).cpu().numpy()
+    np.testing.assert_array_equal(got, g["values"])          # float64, bit-identical to the Python floats
+    boards = random_boards(200000, 5, hi=16, p_empty=0.2)
+    succ = host_u64(env.expand4(dev_boards(boards))["succ"])
+    after = succ[np.arange(len(boards)), np.arange(len(boards)) % 4]
+    np.testing.assert_array_equal(env.potentials_ext(dev_boards(boards), dev_boards(after)).cpu().numpy(),
+                                  O.potentials_ext_batch(boards, after))
+
+
+def test_facade_info_dict_is_complete(env):
+    from g2048.env import Direction, Game2048
+    g = Game2048([[1, 2, 3, 4], [8, 7, 6, 5], [9, 10, 11, 12], [0, 0, 0, 13]], seed=1)
+    _, _, _, info = g.step(Direction.DOWN)
+    assert set(info) == {"invalid_move", "smoothness_delta", "max_tile_created", "max_exponent_before",
+                         "max_exponent_after", "corner_delta", "adjacency_delta", "chain_delta",
+                         "monotonicity_before", "monotonicity_after", "emptiness_before", "emptiness_after",
+                         "topological_delta", "topological_anchor"}
+    assert info["topological_anchor"] == (3, 3) and info["monotonicity_before"] == 30

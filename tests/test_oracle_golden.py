@@ -179,3 +179,9 @@ def test_rtg_advantage_matches_reference(golden):
             want = np.concatenate([adv[name + "__" + ref][sel] for _, _, sel in order])
             np.testing.assert_allclose(got, want.astype(np.float32), rtol=1e-6, atol=1e-6, err_msg=name + key)
         np.testing.assert_allclose([r["rtg_mu"], r["rtg_m2"]], adv[name + "__moments_out"], rtol=1e-12)
+
+
+def test_float_potentials_match_reference(golden):
+    g = golden("potentials_ext")
+    got = O.potentials_ext_batch(g["before"], g["after"])
+    np.testing.assert_array_equal(got, g["values"])          # doubles, bit-identical
