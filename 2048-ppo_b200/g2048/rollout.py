@@ -182,6 +182,8 @@ def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, devic
     game_state = env.encode(boards.reshape(-1)).reshape(T, B, 48)
     ex = env.expand4(boards.reshape(-1))
     pts_possible = ex["points"].reshape(T, B, 4).cpu().numpy()
+    pre_spawn = torch.gather(ex["succ"], 1, cat("actions").reshape(-1, 1).long()).reshape(-1)
+    ext = env.potentials_ext(boards.reshape(-1), pre_spawn).reshape(T, B, 7).cpu().numpy()   # game.py:983-1001
     h = {k: cat(k).cpu().numpy() for k in ("actions", "legal", "logp", "value", "points", "shaping", "entropy")}
     boards_h, flags_h, final_h = boards.cpu().numpy(), flags.cpu().numpy(), final_boards.cpu().numpy()
     sh = {k: v.reshape(T, B) for k, v in env.decode_shaping(h["shaping"].reshape(-1)).items()}
@@ -210,7 +212,9 @@ def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, devic
                 "max_exponent_before": int(sh["max_exp_before"][t, b]),
                 "max_exponent_after": int(sh["max_exp_after"][t, b]),
                 "corner_delta": float(sh["corner_after"][t, b] - sh["corner_before"][t, b]),
-                "adjacency_delta": 0.0, "chain_delta": 0.0, "topological_delta": 0.0,   # not computed
+                "adjacency_delta": float(ext[t, b, 1] - ext[t, b, 0]),
+                "chain_delta": float(ext[t, b, 3] - ext[t, b, 2]),
+                "topological_delta": float(ext[t, b, 5] - ext[t, b, 4]),
                 "monotonicity_after": int(sh["mono_after"][t, b]) if not done else 0.0,   # train.py:318-319
                 "monotonicity_before": int(sh["mono_before"][t, b]),
                 "emptiness_before": int(sh["empt_before"][t, b]),

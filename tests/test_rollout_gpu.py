@@ -173,6 +173,7 @@ def test_play_games_batched_drop_in_schema(golden):
         for i, m in enumerate(moves):
             assert m["game_state"].shape == (48,) and m["game_state"].is_cuda
             assert len(m["policy_logprobs"]) == 4 and len(m["action_mask"]) == 4
+            assert {"adjacency_delta", "chain_delta", "topological_delta", "smoothness_delta", "corner_delta"} <= set(m)
             assert not m["action_mask"][m["selected_direction"]]
             assert np.isfinite(m["policy_logprobs"][m["selected_direction"]])
             if i + 1 < len(moves):
