@@ -66,9 +66,8 @@ __device__ __forceinline__ uint32_t put(uint32_t acc, uint32_t x) {
 //   [27:26] le = #adjacent pairs, both non-zero, left <= right
 //   [31:28] max exponent in the row
 // 65536 entries = 256 KiB in global memory (L2 resident).  Kernels that are
-// throughput-bound on it stage the first LUT_SMEM_ROWS entries (224 KiB, every
-// row whose cell 3 is below exponent 14) in shared memory and read the rare
-// remaining rows through L2.
+// throughput-bound on it stage the first LUT_SMEM_ROWS entries (224 KiB) in shared
+// memory; boards holding a 4096+ tile (has_big_tile) read the table through L2.
 constexpr int LUT_ROWS = 65536;
 constexpr int LUT_SMEM_ROWS = 0xE000;
 constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
@@ -173,11 +172,6 @@ __device__ __forceinline__ uint32_t nz_flags32(uint32_t x) {
 }
 // bit 4i set <=> nibble i is zero
 __device__ __forceinline__ uint32_t z_flags32(uint32_t x) { return nz_flags32(x) ^ 0x11111111u; }
-
-__device__ __forceinline__ uint32_t row_of(Board b, int r) {
-    uint32_t w = r < 2 ? b.lo : b.hi;
-    return (r & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
 
 // The four line entries of a board (its rows, in order).
 struct Lines {

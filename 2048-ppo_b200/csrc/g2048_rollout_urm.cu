@@ -121,7 +121,6 @@ __global__ void pack_kernel(PackSrc s, int L, float* __restrict__ out) {
 }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 __device__ __forceinline__ void sync128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // write 8 consecutive K-elements [k0, k0+8) of this thread's A row (k0 % 8 == 0) as bf16

@@ -392,6 +392,43 @@ class Game2048:
         }
         return self.grid, int(r["points"].item()), done, info
 
+    # -- small helpers of the reference API
+    @staticmethod
+    def calculate_grid_score(grid) -> int:  # game.py:162-165
+        return sum(2 ** k for row in grid for k in row if k > 0)
+
+    @staticmethod
+    def create_random_board(generator: torch.Generator | None = None):  # game.py:76-90
+        board = torch.zeros((4, 4))
+        for idx in torch.randperm(16, generator=generator)[:2]:
+            board[idx // 4, idx % 4] = 1
+        return board.tolist()
+
+    @staticmethod
+    def _symmetry(grid, op: int, device=None):
+        dev = init(device)
+        b = torch.tensor([pack_grid(grid)], dtype=torch.int64, device=dev)
+        z8 = torch.zeros(1, dtype=torch.uint8, device=dev)
+        r = augment(b, b, z8, z8, torch.zeros((1, 4), dtype=torch.float32, device=dev),
+                    torch.tensor([op], dtype=torch.uint8, device=dev))
+        return unpack_board(r["before"].item())
+
+    @staticmethod
+    def mirror_grid(grid, direction: str):  # game.py:508-535
+        if direction not in ("horizontal", "vertical"):
+            raise ValueError(f"Invalid direction: {direction}. Must be 'horizontal' or 'vertical'")
+        return Game2048._symmetry(grid, MIRROR_H if direction == "horizontal" else MIRROR_V)
+
+    @staticmethod
+    def rotate_grid(grid, rotation):  # game.py:537-590
+        degrees = {"north": 0, "up": 0, 0: 0, "east": 90, "right": 90, 90: 90, "south": 180, "down": 180, 180: 180,
+                   "west": 270, "left": 270, 270: 270}.get(rotation)
+        if degrees is None:
+            raise ValueError(f"Invalid rotation: {rotation}")
+        if degrees == 0:
+            return [row[:] for row in grid]
+        return Game2048._symmetry(grid, {90: ROT90, 180: ROT180, 270: ROT270}[degrees])
+
     # -- potentials (static in the reference: game.py:339-399, 671-800)
     @staticmethod
     def _pot_of(grid, idx, device=None):

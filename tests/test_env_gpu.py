@@ -249,6 +249,12 @@ def test_facade_matches_reference_semantics(env):
     assert Game2048.corner_bonus(B) == 13.0 and Game2048.emptiness(B) == 3
     assert Game2048.simulate_move([[1, 1, 1, 1]] + [[0] * 4] * 3, Direction.LEFT) == \
         ([[2, 2, 0, 0]] + [[0] * 4] * 3, 8, 2)
+    q = [[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12], [13, 14, 15, 0]]
+    assert Game2048.mirror_grid(q, "horizontal")[0] == [4, 3, 2, 1] and Game2048.mirror_grid(q, "vertical")[0] == [13, 14, 15, 0]
+    assert Game2048.rotate_grid(q, 90)[0] == [13, 9, 5, 1] and Game2048.rotate_grid(q, "south")[3] == [4, 3, 2, 1]
+    assert Game2048.rotate_grid(q, 0) == q and Game2048.calculate_grid_score([[1, 2, 0, 0]] + [[0] * 4] * 3) == 6
+    with pytest.raises(ValueError):
+        Game2048.mirror_grid(q, "diagonal")
     g2 = Game2048(seed=2048, env_id=0)
     grid = g2.reset()
     assert sum(1 for r in grid for c in r if c) == 2
