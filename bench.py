@@ -125,6 +125,7 @@ class ClockSampler(threading.Thread):
 def cpu_baseline(min_seconds: float = 10.0):
     """C port of Game2048.step (oracle/) on all host threads, bounded sample of the C2 workload."""
     from oracle import oracle as O
+    O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1; the baseline gets every core
     boards, actions = c2_transitions(2048)
     n = 1 << 21
     b, a = boards[:n].view(np.uint64), actions[:n]
@@ -149,6 +150,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as O
+    O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every core
     boards, actions = c2_transitions(2048)
     n = 1 << 20   # bounded sample of the 4M-transition step
     idx = (np.arange(n) % MOVES) * N_BOARDS + (np.arange(n) // MOVES)
