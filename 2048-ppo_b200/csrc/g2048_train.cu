@@ -229,16 +229,17 @@ int g2048_rtg_advantage(const int32_t* points, const uint64_t* shaping, const ui
                         double mu_corrected, double stddev, float* reward_out, float* g_raw_out, float* g_norm_out,
                         float* adv_out, double* stats_out, void* workspace, void* stream) {
     G2048_REQUIRE(T >= 0 && B >= 0, "g2048_rtg_advantage: negative shape");
-    G2048_REQUIRE(points && shaping && flags && value && g_norm_out && adv_out && stats_out && workspace,
-                  "g2048_rtg_advantage: NULL pointer argument");
+    G2048_REQUIRE(stats_out != nullptr, "g2048_rtg_advantage: stats_out is NULL");
     cudaStream_t st = cudaStream_t(stream);
-    const int threads = 128;
-    const int64_t blocks = (B + threads - 1) / threads;
-    double* partials = static_cast<double*>(workspace);
-    if (T == 0 || B == 0) {
+    if (T == 0 || B == 0) {       // empty rollout: nothing to read (the data pointers may be NULL)
         G2048_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, 3 * sizeof(double), st));
         return G2048_OK;
     }
+    G2048_REQUIRE(points && shaping && flags && value && g_norm_out && adv_out && workspace,
+                  "g2048_rtg_advantage: NULL pointer argument");
+    const int threads = 128;
+    const int64_t blocks = (B + threads - 1) / threads;
+    double* partials = static_cast<double*>(workspace);
     if (blocks > MAX_REDUCE_BLOCKS)
         return fail(G2048_EINVAL, "g2048_rtg_advantage: B=%lld exceeds the %lld-column limit of one call", (long long)B,
                     (long long)(MAX_REDUCE_BLOCKS * threads));
@@ -256,15 +257,15 @@ int g2048_ppo_loss(const float* logits, const float* value, const float* old_log
                    const float* g_norm, int64_t n, float clip_eps, float c_v, float beta_ent, float inv_n,
                    float* dlogits, float* dvalue, double* stats_out, void* workspace, void* stream) {
     G2048_REQUIRE(n >= 0, "g2048_ppo_loss: n < 0");
-    G2048_REQUIRE(logits && value && old_logp && actions && legal && adv && g_norm && dlogits && dvalue && stats_out &&
-                      workspace,
-                  "g2048_ppo_loss: NULL pointer argument");
+    G2048_REQUIRE(stats_out != nullptr, "g2048_ppo_loss: stats_out is NULL");
     G2048_REQUIRE(old_logp_stride == 1 || old_logp_stride == 4, "g2048_ppo_loss: old_logp_stride must be 1 or 4");
     cudaStream_t st = cudaStream_t(stream);
-    if (n == 0) {
+    if (n == 0) {                 // empty batch: the data pointers may be NULL
         G2048_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, 4 * sizeof(double), st));
         return G2048_OK;
     }
+    G2048_REQUIRE(logits && value && old_logp && actions && legal && adv && g_norm && dlogits && dvalue && workspace,
+                  "g2048_ppo_loss: NULL pointer argument");
     const int threads = 256;
     int64_t blocks = (n + threads - 1) / threads;
     const int64_t cap = int64_t(num_sms()) * 8;

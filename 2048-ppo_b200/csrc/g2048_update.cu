@@ -197,10 +197,11 @@ int g2048_ln_relu_res_bwd(const float* z, const float* gamma, const float* beta,
                           const float* gout, float* dz, float* dgamma, float* dbeta, float* workspace, int64_t n,
                           int32_t h, void* stream) {
     G2048_REQUIRE(n >= 0, "g2048_ln_relu_res_bwd: n < 0");
-    G2048_REQUIRE(z && gamma && beta && mean && rstd && gout && dz && dgamma && dbeta && workspace,
-                  "g2048_ln_relu_res_bwd: NULL pointer argument");
+    G2048_REQUIRE(dgamma && dbeta, "g2048_ln_relu_res_bwd: NULL gradient output");
     if (h < 4 || h > 256 || (h & 3)) return fail(G2048_ESHAPE, "g2048_ln_relu_res_bwd: h=%d must be a multiple of 4 in [4,256]", h);
     cudaStream_t st = cudaStream_t(stream);
+    G2048_REQUIRE(n == 0 || (z && gamma && beta && mean && rstd && gout && dz && workspace),
+                  "g2048_ln_relu_res_bwd: NULL pointer argument");
     if (n == 0) {
         G2048_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * h, st));
         G2048_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * h, st));

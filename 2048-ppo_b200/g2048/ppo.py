@@ -92,7 +92,7 @@ class _PPOLoss(torch.autograd.Function):
             dlogits = torch.empty_like(logits_c)
             dvalue = torch.empty_like(value_c)
             stats = torch.empty(4, dtype=torch.float64, device=dev)
-            inv_n = 1.0 / float(n_total if n_total else n)
+            inv_n = 1.0 / float(n_total if n_total else max(n, 1))
             _lib.call("g2048_ppo_loss", _ptr(logits_c), _ptr(value_c), _ptr(old_logp), stride,
                       _ptr(_req(actions, torch.uint8, "actions")), _ptr(_req(legal, torch.uint8, "legal")),
                       _ptr(None if flags is None else _req(flags, torch.uint8, "flags")),
@@ -101,7 +101,7 @@ class _PPOLoss(torch.autograd.Function):
                       _ptr(stats), _ptr(_workspace(dev)), _stream())
         ctx.save_for_backward(dlogits, dvalue)
         ctx.value_shape = value.shape
-        s = stats * inv_n                                   # means of ppo, smooth-l1, entropy
+        s = stats * inv_n                                   # means of ppo, smooth-l1, entropy (all 0 for an empty batch)
         loss = (-(s[0] - c_v * s[1] + beta_ent * s[2])).to(torch.float32)
         ctx.mark_non_differentiable(stats)
         return loss, stats
