@@ -59,7 +59,7 @@ __global__ void build_lut_kernel(uint32_t* lut) {
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row < uint32_t(LUT_ROWS)) {
         lut[row] = lut_entry_for_row(row);
-        lut[MOVE_LUT_OFFSET + row] = move_entry_for_row(row);
+        lut[MOVE_LUT_OFFSET + move_slot(row)] = move_entry_for_row(row);
     }
 }
 
@@ -157,7 +157,7 @@ __device__ __forceinline__ void expand4_loop(const uint32_t* slut, const uint32_
         int p[4], mt[4];
         if (STAGED && !has_big_tile(b)) {
             // every cell <= 11: the staged move table gives result, points and created tile directly
-            f = lookup_moves(b, LutShared{slut});
+            f = lookup_moves(b, MoveLutShared{slut});
             move_stats(f.up, p[0], mt[0]);
             move_stats(f.down, p[1], mt[1]);
             move_stats(f.left, p[2], mt[2]);

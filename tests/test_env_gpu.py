@@ -57,7 +57,9 @@ def check_step(env, boards, actions, draws, n_expected=None):
 
 def test_row_table_matches_oracle(env):
     both = env.lut(0).cpu().numpy().view(np.uint32)
-    lut, mv = both[:65536], both[65536:]
+    lut, mv_slots = both[:65536], both[65536:]
+    rows = np.arange(65536)
+    mv = mv_slots[rows ^ ((rows >> 8) & 31)]          # the move table is stored bank-hashed
     out4, score, mt = O.row_table()
     # move table of the 4-move expansion: exact for rows whose cells are all <= 11
     idx = np.arange(65536)
