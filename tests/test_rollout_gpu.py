@@ -271,3 +271,35 @@ def test_tensor_core_rollout(h, L, B, T):
     err_v = float((buf.value.reshape(-1) - v32).abs().max())
     print(f"bf16 tensor-core rollout vs fp32 policy: max |dlogp| = {err_lp:.4f}, max |dV| = {err_v:.4f}")
     assert err_lp < 0.1 and err_v < 0.1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_rollout_properties(precision):
+    """C3-sized env batch (65 536 envs): size-independent properties instead of a CPU replay --
+    the rollout kernel's inlined env agrees with the standalone g2048_step kernel fed the recorded
+    actions and the same Philox counters (boards, points, shaping, flags), every sampled action is
+    legal, auto-reset boards hold exactly two tiles, and a second run is bit-identical."""
+    from g2048 import env, rollout
+    model = random_model(196, 2, seed=3)
+    pol = rollout.pack_policy(model)
+    B, T, seed = 65536, 12, 2048
+    boards = env.reset(B, device=0, seed=seed, env0=0, ctr=0)
+    start = boards.clone()
+    buf = rollout.rollout(pol, boards, T, seed=seed, env0=0, ctr0=1, auto_reset=True, precision=precision)
+    again = rollout.rollout(pol, start.clone(), T, seed=seed, env0=0, ctr0=1, auto_reset=True, precision=precision)
+    for name in ("boards", "actions", "points", "shaping", "flags", "logp", "value"):
+        assert torch.equal(getattr(buf, name), getattr(again, name)), name
+    assert torch.equal(buf.boards[0], start)
+    assert bool(((buf.legal.long() >> buf.actions.long()) & 1).all())
+    assert bool((buf.flags & 0x80).all())
+    for t in range(T):
+        r = env.step(buf.boards[t], buf.actions[t], seed=seed, env0=0, ctr=1 + t)
+        assert torch.equal(r["points"], buf.points[t]) and torch.equal(r["shaping"], buf.shaping[t])
+        assert torch.equal(r["flags"] | 0x80, buf.flags[t])
+        nxt = buf.boards[t + 1] if t + 1 < T else boards
+        done = (r["flags"] & 0x10) != 0
+        assert torch.equal(r["boards"][~done], nxt[~done])
+        if bool(done.any()):   # auto-reset: a fresh board with exactly two tiles
+            fresh = nxt[done]
+            tiles = sum(((fresh >> (4 * k)) & 15) != 0 for k in range(16))
+            assert bool((tiles == 2).all())
