@@ -38,7 +38,7 @@ class TrainConfig:
     total_steps: int = 20000
     epochs: int = 1
     minibatches: int = 1           # optimizer steps per epoch (1 = full batch)
-    chunk: int = 1 << 20           # samples per forward/backward chunk (memory bound only)
+    chunk: int = 1 << 22           # samples per forward/backward chunk (measured: 4M is 7.6 % faster than 1M; ~26 GB live)
     seed: int = 2048
     zero_heads: bool = True        # train.py:1559-1567
     dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
