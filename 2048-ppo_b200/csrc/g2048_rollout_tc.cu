@@ -2,14 +2,17 @@
 // large env batch.  Same records and env semantics as g2048_rollout.cu; the stem and residual-block
 // GEMMs run as bf16 x bf16 -> fp32 tcgen05.mma with the accumulator in tensor memory.
 //
-// Mapping: a CTA owns tiles of 128 envs; env m of the tile IS TMEM lane m.  Eight env warps: warp w
-// reads lane quarter (w & 3) -- the hardware restriction of tcgen05.ld -- and column half (w >> 2),
-// keeping its half row in registers, so LayerNorm needs one 2-value exchange per row through
-// shared memory and everything else (ReLU, residual, heads, masked softmax, sampling, env step) is
-// thread-local.  Env thread 0 doubles as the MMA issuer (between its a_ready arrive and its mma_done
-// wait it has nothing else to do) and streams the pre-swizzled bf16 weight images L2 -> SMEM with
-// bulk async copies; 256 threads keep the full 255-register budget.  Hand-off is by mbarriers only:
-//   a_ready : 256 env threads -> issuer   (A operand written, TMEM reads of D finished)
+// Mapping: a CTA owns tiles of 128 envs; env m of the tile IS TMEM lane m.  Sixteen env warps: warp w
+// reads lane quarter (w & 3) -- the hardware restriction of tcgen05.ld -- and column part (w >> 2)
+// of TC_SPLIT = 4, walking its 48..56 columns in groups of 8 straight from TMEM, so LayerNorm needs
+// one 2-value exchange per row through shared memory and everything else (ReLU, residual, heads,
+// masked softmax, sampling, env step) is thread-local.  The epilogue is issue-bound (measured:
+// tools/tmem_bw.cu shows TMEM reads at ~900 B/clk/SM are nowhere near the limit), so it uses packed
+// fp32 math (FFMA2 / FADD2, two columns per instruction) and shared-space loads throughout.  Env
+// thread 0 doubles as the MMA issuer (between its a_ready arrive and its mma_done wait it has
+// nothing else to do) and streams the pre-swizzled bf16 weight images L2 -> SMEM with bulk async
+// copies.  Hand-off is by mbarriers only:
+//   a_ready : 512 env threads -> issuer   (A operand written, TMEM reads of D finished)
 //   mma_done: tcgen05.commit  -> env threads + issuer (D complete, B buffer reusable)
 //   b_full  : bulk copy tx    -> issuer   (weights of the next block landed)
 // TMEM: columns [0,HP) = accumulator D, [256,256+HP) = the fp32 residual stream X.
@@ -21,7 +24,8 @@
 
 namespace g2048 {
 
-constexpr int TC_ENV_THREADS = 256;     // 8 warps: warp w owns lane quarter (w & 3) and column half (w >> 2)
+constexpr int TC_SPLIT = 4;              // threads per env row (column quarters)
+constexpr int TC_ENV_THREADS = 128 * TC_SPLIT;   // 16 warps: warp w owns lane quarter (w & 3) and column quarter (w >> 2)
 constexpr int TC_THREADS = TC_ENV_THREADS;   // env thread 0 doubles as the MMA issuer / weight producer
 constexpr uint32_t TC_X_COL = 256;      // TMEM column of the residual stream
 
@@ -37,18 +41,19 @@ struct TcSmem {
     alignas(16) float ln_g[8][HP];
     alignas(16) float ln_b[8][HP];
     alignas(16) float headw[5 * HP + 8];
-    float red[2][2][128];                           // [sum | sq][column half][row]
-    float headp[128][5];
+    float red[2][TC_SPLIT][128];                    // [sum | sq][column part][row]
+    float headp[TC_SPLIT - 1][128][5];             // partial head dots of parts 1..TC_SPLIT-1
     uint64_t a_ready, mma_done, b_full, stem_full;
     uint32_t tmem_base;
 };
+static_assert(sizeof(TcSmem<208>) + 1024 <= 232448, "TcSmem exceeds the 227 KB per-CTA shared memory limit");
 
 __device__ __forceinline__ void env_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TC_ENV_THREADS) : "memory"); }
 
-// LayerNorm (eps 1e-5) + ReLU (+ residual) of one env row, split over the two threads that share
-// the row (column halves, NH = HP/2 columns each, walked in groups of 8 straight from TMEM so the
-// code stays compact); result -> residual stream X (TMEM, fp32) and next A operand (SMEM, bf16
-// swizzled); optionally the 5 head dot products (partial over this half).  Mean and variance come
+// LayerNorm (eps 1e-5) + ReLU (+ residual) of one env row, split over the TC_SPLIT threads that share
+// the row (contiguous column ranges, walked in groups of 8 straight from TMEM so the code stays
+// compact); result -> residual stream X (TMEM, fp32) and next A operand (SMEM, bf16
+// swizzled); optionally the 5 head dot products (partial over this part).  Mean and variance come
 // from one pass (sum, sum of squares in fp32): ample for a path whose GEMM operands are bf16.
 // game.py:1038-1046, 1069-1073, 1199-1203.
 template <int HP, bool STEM, bool HEADS>
@@ -57,16 +62,19 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
                                          const float* __restrict__ beta, float (&o)[5]) {
     // Columns >= h are padding: their weights, biases, gamma and beta are zero in the packed buffer,
     // so they produce z = 0 and x = 0 without any masking here.
-    constexpr int NH = HP / 2;
-    const int c0 = half * NH;
+    // this thread's column range: HP/8 groups of 8 columns dealt round-robin-contiguously to the TC_SPLIT parts
+    constexpr int G = HP / 8;
+    const int g0 = (G * half) / TC_SPLIT, g1 = (G * (half + 1)) / TC_SPLIT, ng = g1 - g0;
+    const int c0 = 8 * g0;
     const uint32_t tD = tmem_lane + uint32_t(c0), tX = tmem_lane + TC_X_COL + uint32_t(c0);
     const float inv_h = 1.0f / float(h);
     const float4* bias4 = reinterpret_cast<const float4*>(bias + (STEM ? c0 : 0));
     const float4* gamma4 = reinterpret_cast<const float4*>(gamma + c0);
     const float4* beta4 = reinterpret_cast<const float4*>(beta + c0);
-    float sum = 0.f, sq = 0.f;
+    // packed fp32 math (FADD2 / FFMA2): two columns per instruction
+    float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll 1
-    for (int g = 0; g < NH / 8; ++g) {
+    for (int g = 0; g < ng; ++g) {
         float v[8];
         tc::tmem_ld8(tD + uint32_t(8 * g), v);
         if (STEM) {
@@ -75,21 +83,31 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
             v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sum += v[j];
-            sq = fmaf(v[j], v[j], sq);
+        for (int j = 0; j < 4; ++j) {
+            const float2 vv = make_float2(v[2 * j], v[2 * j + 1]);
+            sum2 = __fadd2_rn(sum2, vv);
+            sq2 = __ffma2_rn(vv, vv, sq2);
         }
     }
-    S.red[0][half][row] = sum;
-    S.red[1][half][row] = sq;
+    S.red[0][half][row] = sum2.x + sum2.y;
+    S.red[1][half][row] = sq2.x + sq2.y;
     env_sync();
-    const float mean = (S.red[0][0][row] + S.red[0][1][row]) * inv_h;
-    const float var = fmaxf((S.red[1][0][row] + S.red[1][1][row]) * inv_h - mean * mean, 0.f);
+    float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+    for (int q = 0; q < TC_SPLIT; ++q) {
+        tsum += S.red[0][q][row];
+        tsq += S.red[1][q][row];
+    }
+    const float mean = tsum * inv_h;
+    const float var = fmaxf(tsq * inv_h - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-    const float shift = -mean * rstd;
+    const float2 rstd2 = make_float2(rstd, rstd), shift2 = make_float2(-mean * rstd, -mean * rstd);
+    float2 o2[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) o2[q] = make_float2(0.f, 0.f);
     uint8_t* arow = S.A + uint32_t(row >> 3) * 1024u + uint32_t(row & 7) * 128u;
 #pragma unroll 1
-    for (int g = 0; g < NH / 8; ++g) {
+    for (int g = 0; g < ng; ++g) {
         float v[8], x[8];
         tc::tmem_ld8(tD + uint32_t(8 * g), v);
         if (!STEM) tc::tmem_ld8(tX + uint32_t(8 * g), x);
@@ -99,20 +117,27 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
             v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
         }
         const float4 ga = gamma4[2 * g], gb = gamma4[2 * g + 1], ea = beta4[2 * g], eb = beta4[2 * g + 1];
-        const float gm[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        const float bt[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+        const float2 gm[4] = {make_float2(ga.x, ga.y), make_float2(ga.z, ga.w), make_float2(gb.x, gb.y), make_float2(gb.z, gb.w)};
+        const float2 bt[4] = {make_float2(ea.x, ea.y), make_float2(ea.z, ea.w), make_float2(eb.x, eb.y), make_float2(eb.z, eb.w)};
+        float2 xx[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float y = fmaxf(fmaf(fmaf(v[j], rstd, shift), gm[j], bt[j]), 0.f);
-            x[j] = STEM ? y : x[j] + y;
+        for (int j = 0; j < 4; ++j) {
+            float2 y = __ffma2_rn(__ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), rstd2, shift2), gm[j], bt[j]);
+            y.x = fmaxf(y.x, 0.f);
+            y.y = fmaxf(y.y, 0.f);
+            xx[j] = STEM ? y : __fadd2_rn(make_float2(x[2 * j], x[2 * j + 1]), y);
+            x[2 * j] = xx[j].x;
+            x[2 * j + 1] = xx[j].y;
         }
         if (HEADS) {
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 const float4* hw = reinterpret_cast<const float4*>(S.headw + q * HP + c0 + 8 * g);
                 const float4 ha = hw[0], hb = hw[1];
-                o[q] = fmaf(ha.x, x[0], fmaf(ha.y, x[1], fmaf(ha.z, x[2], fmaf(ha.w, x[3], o[q]))));
-                o[q] = fmaf(hb.x, x[4], fmaf(hb.y, x[5], fmaf(hb.z, x[6], fmaf(hb.w, x[7], o[q]))));
+                o2[q] = __ffma2_rn(make_float2(ha.x, ha.y), xx[0], o2[q]);
+                o2[q] = __ffma2_rn(make_float2(ha.z, ha.w), xx[1], o2[q]);
+                o2[q] = __ffma2_rn(make_float2(hb.x, hb.y), xx[2], o2[q]);
+                o2[q] = __ffma2_rn(make_float2(hb.z, hb.w), xx[3], o2[q]);
             }
         }
         tc::tmem_st8(tX + uint32_t(8 * g), x);
@@ -125,16 +150,24 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
         const uint32_t col = uint32_t(c0 + 8 * g), blk = col >> 6, unit = ((col & 63u) >> 3) ^ uint32_t(row & 7);
         *reinterpret_cast<uint4*>(arow + blk * (128u * 128u) + unit * 16u) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if (HEADS) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) o[q] = o2[q].x + o2[q].y;
+    }
     tc::tmem_st_wait();
     if (HEADS) {
-        if (half == 1) {
+        if (half != 0) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) S.headp[row][q] = o[q];
+            for (int q = 0; q < 5; ++q) S.headp[half - 1][row][q] = o[q];
         }
         env_sync();
         if (half == 0) {
 #pragma unroll
-            for (int q = 0; q < 5; ++q) o[q] += S.headp[row][q] + S.headw[5 * HP + q];
+            for (int q = 0; q < 5; ++q) {
+#pragma unroll
+                for (int part = 1; part < TC_SPLIT; ++part) o[q] += S.headp[part - 1][row][q];
+                o[q] += S.headw[5 * HP + q];
+            }
         }
     }
 }
@@ -178,7 +211,7 @@ template <int HP>
 __global__ void __launch_bounds__(TC_THREADS, 1) rollout_mlp_tc_kernel(RolloutParams p) {
     using SM = TcSmem<HP>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    SM& S = *reinterpret_cast<SM*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    SM& S = *reinterpret_cast<SM*>(smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5;
     const int L = p.layers, h = p.hidden;
     const int64_t ntiles = (p.B + 127) / 128;

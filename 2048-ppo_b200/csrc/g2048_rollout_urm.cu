@@ -158,7 +158,9 @@ constexpr uint32_t T_E = 320;
 
 __global__ void __launch_bounds__(THREADS, 1) rollout_urm_kernel(RolloutParams p, int loops) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic on the __shared__ array (not through an integer) so that the
+    // compiler keeps the shared address space and emits LDS/STS instead of generic loads
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.layers;
     const int cell = tid & 15;                                   // token = cell of env (tid >> 4) of the tile
