@@ -45,6 +45,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// ---- 32-byte-swizzled tiles (used by the update GEMMs, g2048_linear.cu) --------------------------
+// A block is R rows of 32 bytes = 16 bf16 = exactly one k-step; 8 rows form a 256-byte atom and the
+// 16-byte unit u of row r sits at unit u ^ ((r >> 2) & 1) (Swizzle<1,4,3>: address bit 4 ^= bit 7).
+// The same bytes are a K-major operand (rows = M/N index, 16 K-elements per row; SBO = 256) and an
+// MN-major operand (rows = K index, 16 MN-elements per row; SBO = 256 between 8-row K groups, LBO =
+// distance between consecutive blocks = the next 16 MN-elements).
+__host__ __device__ __forceinline__ uint32_t sw32_offset(int r, int k) {
+    return uint32_t(r) * 32u + uint32_t((((k >> 3) ^ (r >> 2)) & 1) << 4) + uint32_t(k & 7) * 2u;
+}
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((saddr >> 4) & 0x3FFFu);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= uint64_t(1) << 46;                  // descriptor version (Blackwell)
+    d |= uint64_t(6) << 61;                  // SWIZZLE_32B
+    return d;
+}
+// kind::f16 instruction descriptor with explicit operand majors (bit 15: A is MN-major, bit 16: B)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_major(int M, int N, bool a_mn, bool b_mn) {
+    return make_idesc_bf16(M, N) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16);
+}
+
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_dst)), "r"(ncols)
                  : "memory");

@@ -223,6 +223,28 @@ int g2048_ln_relu_res_bwd(const float* z, const float* gamma, const float* beta,
                           const float* gout, float* dz, float* dgamma, float* dbeta, float* workspace, int64_t n,
                           int32_t h, void* stream);
 
+/* ---- policy update: fp32-grade Linear GEMMs on tcgen05 (csrc/g2048_linear.cu) ----------------
+ * The Linear layers of GameMLP (game.py:1038-1046, 1069-1073) inside model_optimize_step's forward
+ * and loss.backward() (train.py:497-556), which the reference runs as fp32 torch matmuls.  Operands
+ * are split in-kernel into two bf16 terms (x = hi + lo) and every product is Alo*Bhi + Ahi*Blo + Ahi*Bhi
+ * with fp32 accumulation in tensor memory: fp32-grade results (about 1e-6 relative) at tensor-core rate.
+ * Activations are row-major fp32 [M, features], features a multiple of 4 in [4, 208]; all pointers
+ * 16-byte aligned.
+ *   g2048_x3_pack   weight W [R, C] (torch Linear layout [out, in]) -> operand image for x3_gemm;
+ *                   transpose = 0: image of W   (forward  Y = X W^T,  N = R, K = C)
+ *                   transpose = 1: image of W^T (dgrad   dX = dY W,   N = C, K = R)
+ *                   `image` holds g2048_x3_image_bytes(N, K) bytes.
+ *   g2048_x3_gemm   C[M, N] = A[M, K] * B[N, K]^T, B given as a packed image.
+ *   g2048_x3_wgrad  dW[N, K] = dY[M, N]^T * X[M, K] (sum over samples; per-SM partials are added in a
+ *                   fixed order, so the result is deterministic); `workspace` holds
+ *                   g2048_x3_wgrad_workspace_bytes() bytes. */
+int64_t g2048_x3_image_bytes(int32_t rows, int32_t cols);
+int g2048_x3_pack(const float* W, int32_t R, int32_t C, int32_t transpose, void* image, void* stream);
+int g2048_x3_gemm(const float* A, const void* image, float* C, int64_t M, int32_t N, int32_t K, void* stream);
+int64_t g2048_x3_wgrad_workspace_bytes(void);
+int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
+                   void* stream);
+
 /* tcgen05 building-block self-test (not part of the reference's interface): C[128,N] =
  * A[128,K] * W[N,K]^T with bf16-rounded operands and fp32 accumulation in tensor memory.
  * K, N multiples of 16, <= 256.  Pins the UMMA descriptor / swizzle conventions on hardware. */

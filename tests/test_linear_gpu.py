@@ -1,0 +1,89 @@
+"""Split-bf16 ("x3") tcgen05 GEMMs of the policy update (csrc/g2048_linear.cu) against float64 matmuls.
+
+Tolerance: every product a*b is evaluated as alo*bhi + ahi*blo + ahi*bhi with bf16 terms, so the
+per-product error is bounded by ~3 * 2^-17 |a||b|; the tests require the result within
+2e-5 * (|A| |B|^T) elementwise of the float64 product (a bound, typical errors are a few 1e-6 relative)
+and no worse than 4x the error of torch's own fp32 matmul plus that slack.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, generator=g, device="cuda") * scale
+
+
+def _check(got, a64, b64, label):
+    ref = a64 @ b64
+    bound = 2e-5 * (a64.abs() @ b64.abs()) + 1e-30
+    err = (got.double() - ref).abs()
+    worst = float((err / bound).max())
+    assert worst < 1.0, f"{label}: error {worst:.2f}x the 2e-5 |A||B| bound"
+    return float(err.max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 196, 196), (1000, 196, 48), (4096 + 77, 196, 196), (300, 64, 208), (129, 4, 196),
+                                   (50000, 196, 196)])
+def test_gemm_matches_float64(M, N, K):
+    from g2048 import linear
+    a, w = _rand((M, K), M + N), _rand((N, K), K + 7, 0.3)
+    out = linear.gemm(a, linear.pack_weight(w), N)
+    torch.cuda.synchronize()
+    rel = _check(out, a.double(), w.double().T, "forward")
+    assert rel < 1.5e-5
+    # dgrad form: dy [M,N] @ W [N,K]
+    dy = _rand((M, N), 3 * M + 1, 1e-3)
+    dx = linear.gemm(dy, linear.pack_weight(w, transpose=True), K)
+    torch.cuda.synchronize()
+    _check(dx, dy.double(), w.double(), "dgrad")
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 196, 196), (1000, 196, 48), (4096 + 77, 196, 196), (70000, 196, 196), (333, 64, 208),
+                                   (5000, 128, 16), (600000, 196, 196)])
+def test_wgrad_matches_float64(M, N, K):
+    from g2048 import linear
+    dy, x = _rand((M, N), M + 11, 1e-2), _rand((M, K), M + 13)
+    dw = linear.wgrad(dy, x)
+    torch.cuda.synchronize()
+    _check(dw, dy.double().T, x.double(), "wgrad")
+    again = linear.wgrad(dy, x)
+    assert torch.equal(dw, again), "wgrad must be deterministic"
+
+
+def test_gemm_handles_special_rows():
+    from g2048 import linear
+    a = _rand((256, 196), 5)
+    a[3] = 0.0
+    a[7] = 1e-30          # lo terms underflow to zero: still exact enough
+    a[9] = 3e4
+    w = _rand((196, 196), 6, 0.1)
+    out = linear.gemm(a, linear.pack_weight(w), 196)
+    assert torch.isfinite(out).all()
+    assert torch.equal(out[3], torch.zeros_like(out[3]))
+    _check(out, a.double(), w.double().T, "special rows")
+
+
+def test_linear_autograd_matches_torch_fp64():
+    from g2048 import linear
+    x = _rand((3000, 196), 21).requires_grad_(True)
+    w = _rand((196, 196), 22, 0.2).requires_grad_(True)
+    g = _rand((3000, 196), 23, 1e-2)
+    y = linear.linear(x, w)
+    y.backward(g)
+    x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    (x64 @ w64.T).backward(g.double())
+    # max-norm relative error of a 196-term x3 dot product is ~1e-5 of the output scale (fp32 SGEMM: ~1e-6)
+    for got, ref in ((y.detach(), x64.detach() @ w64.detach().T), (x.grad, x64.grad), (w.grad, w64.grad)):
+        scale = float(ref.abs().max())
+        assert float((got.double() - ref).abs().max()) < 4e-5 * scale
+
+
+def test_linear_rejects_unsupported_inputs():
+    from g2048 import linear
+    with pytest.raises(ValueError):
+        linear.linear(torch.zeros(4, 210, device="cuda"), torch.zeros(8, 210, device="cuda"))
+    with pytest.raises(ValueError):
+        linear.gemm(torch.zeros(4, 16), torch.zeros(16, dtype=torch.uint8), 16)
