@@ -73,16 +73,27 @@ def ln_relu_res(z, gamma, beta, res=None, eps: float = 1e-5):
     return _LNReLURes.apply(z, gamma, beta, res, eps)
 
 
-def mlp_forward(model, x48: torch.Tensor):
-    """GameMLP.forward (game.py:1145-1220) with fused block epilogues; same parameters, same outputs."""
+def mlp_forward(model, x48: torch.Tensor, matmul: str = "cublas"):
+    """GameMLP.forward (game.py:1145-1220) with fused block epilogues; same parameters, same outputs.
+    matmul = "x3": the stem / block Linears (forward, dgrad, wgrad) run on the split-bf16 tcgen05 kernels
+    of g2048.linear instead of cuBLAS; the two tiny heads (N = 4, 1) stay in torch."""
     h = model.stem[0].weight.shape[0]
     if not supported(h) or any(blk.mlp[3].p > 0 and model.training for blk in model.backbone):
+        if matmul == "x3":
+            raise ValueError("mlp_forward(matmul='x3') needs dropout off and hidden % 4 == 0, hidden <= 208")
         return model(x48)
+    if matmul == "x3":
+        from . import linear as _lx
+        if not _lx.supported(h, h):
+            raise ValueError(f"mlp_forward(matmul='x3'): hidden {h} unsupported")
+        lin = _lx.linear
+    else:
+        lin = torch.nn.functional.linear
     ln = model.stem[1]
-    x = ln_relu_res(torch.nn.functional.linear(x48, model.stem[0].weight), ln.weight, ln.bias, None, ln.eps)
+    x = ln_relu_res(lin(x48, model.stem[0].weight), ln.weight, ln.bias, None, ln.eps)
     for blk in model.backbone:
         ln = blk.mlp[1]
-        x = ln_relu_res(torch.nn.functional.linear(x, blk.mlp[0].weight), ln.weight, ln.bias, x, ln.eps)
+        x = ln_relu_res(lin(x, blk.mlp[0].weight), ln.weight, ln.bias, x, ln.eps)
     logits = model.action_head(x)
     value = model.value_head(x.detach() if model.decouple_critic else x)
     return logits, value

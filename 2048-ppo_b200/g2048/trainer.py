@@ -43,7 +43,8 @@ class TrainConfig:
     zero_heads: bool = True        # train.py:1559-1567
     dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
     rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
-    update_matmul: str = "fp32"       # cuBLAS mode of the update's Linear GEMMs: "fp32" (reference precision) or "tf32"
+    update_matmul: str = "x3"         # the update's Linear GEMMs: "x3" = split-bf16 tcgen05 kernels (g2048.linear, fp32-grade),
+                                      # "fp32" = cuBLAS SGEMM, "tf32" = cuBLAS TF32 (below the reference's precision)
 
 
 def cosine_with_warmup(warmup: int, total: int):
@@ -156,7 +157,8 @@ class Trainer:
                 tot = torch.zeros(4, dtype=torch.float64, device=self.device)
                 for c0 in range(m0, m1, c.chunk):
                     sl = slice(c0, min(m1, c0 + c.chunk)) if order is None else order[c0:min(m1, c0 + c.chunk)]
-                    logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]))
+                    logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
+                                                  matmul="x3" if c.update_matmul == "x3" else "cublas")
                     loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],
                                                clip_eps=c.clip_eps, critic_strength=c.critic_strength,
                                                entropy_strength=c.entropy_strength, n_total=n_mb_global)

@@ -214,7 +214,8 @@ def rollout_section(args, dev, world, rank, barrier):
     ro_fp32_ms = time_rollout("fp32")
     ro_ms = time_rollout("bf16")
     cfg.rollout_precision = "auto"
-    # rollout + update (fp32 cuBLAS GEMMs = the reference's precision; tf32 reported beside it)
+    # rollout + update: the headline uses the split-bf16 tcgen05 GEMMs (g2048.linear); the cuBLAS fp32 and
+    # TF32 updates are reported beside it
     def time_train(matmul):
         cfg.update_matmul = matmul
         t.train_step()
@@ -227,11 +228,12 @@ def rollout_section(args, dev, world, rank, barrier):
         return ev0.elapsed_time(ev1) / reps, st, t.times
 
     tf32_ms, _, _ = time_train("tf32")
-    step_ms, stats, times = time_train("fp32")
+    fp32_ms, _, _ = time_train("fp32")
+    step_ms, stats, times = time_train("x3")
     if world > 1:
-        v = torch.tensor([step_ms, tf32_ms], device=dev)
+        v = torch.tensor([step_ms, tf32_ms, fp32_ms], device=dev)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        step_ms, tf32_ms = (float(x) for x in v.tolist())
+        step_ms, tf32_ms, fp32_ms = (float(x) for x in v.tolist())
     # ---- C5: GameURM rollout (default config), a few steps at the configured env count
     urm = None
     if args.urm_envs > 0:
@@ -269,8 +271,9 @@ def rollout_section(args, dev, world, rank, barrier):
                               "kernel": "rollout_mlp_kernel<208>"},
         "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
         "train_step_ms": step_ms,
-        "update": "torch autograd + cuBLAS fp32 SGEMM for the Linear layers, fused g2048 LayerNorm/ReLU/residual and PPO-loss kernels, Muon+AdamW",
-        "tf32_update_variant": {"train_step_ms": tf32_ms, "rollout_update_steps_per_sec": world * n_local / (tf32_ms * 1e-3)},
+        "update": "torch autograd graph; Linear forward/dgrad/wgrad = g2048 split-bf16 (x3) tcgen05 kernels, fused g2048 LayerNorm/ReLU/residual and PPO-loss kernels, Muon+AdamW",
+        "cublas_fp32_update_variant": {"train_step_ms": fp32_ms, "rollout_update_steps_per_sec": world * n_local / (fp32_ms * 1e-3)},
+        "cublas_tf32_update_variant": {"train_step_ms": tf32_ms, "rollout_update_steps_per_sec": world * n_local / (tf32_ms * 1e-3)},
         "phase_ms_rank0": {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
                            "moments_allreduce": times.allreduce_ms},
         "model_flops_per_env_step": flops,
