@@ -13,6 +13,7 @@
 #include <cmath>
 #include "g2048_device.cuh"
 #include "g2048_host.h"
+#include "g2048_loss.cuh"
 
 namespace g2048 {
 
@@ -136,76 +137,14 @@ ppo_loss_kernel(const float4* __restrict__ logits, const float* __restrict__ val
         }
         const float4 l4 = logits[i];
         const float l[4] = {l4.x, l4.y, l4.z, l4.w};
-        const uint32_t m = legal[i] & 15u, a = actions[i] & 3u;
-        // masked log-softmax
-        float mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if ((m >> k) & 1u) mx = fmaxf(mx, l[k]);
-        float se = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if ((m >> k) & 1u) se += expf(l[k] - mx);
-        const float lse = mx + logf(se);
-        float p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = ((m >> k) & 1u) ? expf(l[k] - lse) : 0.f;
-        const float la = a == 0 ? l[0] : a == 1 ? l[1] : a == 2 ? l[2] : l[3];
-        const float lp_new = la - lse;
+        const uint32_t a = actions[i] & 3u;
         const float lp_old = old_logp[i * old_logp_stride + (old_logp_stride == 4 ? a : 0)];
-        const float A = adv[i];
-        // ratio and clipped surrogate
-        const float x = lp_new - lp_old;
-        const float xc = fminf(fmaxf(x, -20.f), 20.f);
-        const float rho = expf(xc);
-        const float rc = fminf(fmaxf(rho, 1.f - clip_eps), 1.f + clip_eps);
-        const float t1 = A * rho, t2 = A * rc;
-        const float ppo = fminf(t1, t2);
-        // d ppo / d rho following torch.minimum (ties split) and clamp (inclusive bounds)
-        const bool in_clip = rho >= 1.f - clip_eps && rho <= 1.f + clip_eps;
-        float dppo_drho;
-        if (t1 < t2) dppo_drho = A;
-        else if (t1 > t2) dppo_drho = in_clip ? A : 0.f;
-        else dppo_drho = 0.5f * A + (in_clip ? 0.5f * A : 0.f);
-        const float dppo_dlp = (x >= -20.f && x <= 20.f) ? dppo_drho * rho : 0.f;
-        // entropy over the clamped logits
-        float z[4], zmx = -INFINITY;
+        float gl[4], dv_unit, ppo, vl, H;
+        ppo_sample(l, legal[i] & 15u, a, lp_old, adv[i], value[i], g_norm[i], clip_eps, beta_ent, ppo, vl, H, gl, dv_unit);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            z[k] = ((m >> k) & 1u) ? fminf(fmaxf(l[k], -20.f), 20.f) : -20.f;
-            zmx = fmaxf(zmx, z[k]);
-        }
-        float zs = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) zs += expf(z[k] - zmx);
-        const float zlse = zmx + logf(zs);
-        float q[4], lq[4], H = 0.f, S = 0.f;   // S = sum_{legal} q (1 + log q)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            lq[k] = z[k] - zlse;
-            q[k] = expf(lq[k]);
-            if ((m >> k) & 1u) {
-                H -= q[k] * lq[k];
-                S += q[k] * (1.f + lq[k]);
-            }
-        }
-        // critic
-        const float V = value[i], R = g_norm[i];
-        const float d = V - R, ad = fabsf(d);
-        const float vl = ad < 1.f ? 0.5f * d * d : ad - 0.5f;
-        const float dvl = ad < 1.f ? d : (d > 0.f ? 1.f : -1.f);
-        // gradients of loss = -(1/N) sum u
-        float gl[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool leg = (m >> k) & 1u;
-            const float dlp = leg ? ((k == int(a) ? 1.f : 0.f) - p[k]) : 0.f;          // d lp[a] / d l_k
-            const bool pass = leg && l[k] >= -20.f && l[k] <= 20.f;                      // clamp passes gradient
-            const float dH = pass ? (-(1.f + lq[k]) * q[k] + q[k] * S) : 0.f;            // d H / d l_k
-            gl[k] = -inv_n * (dppo_dlp * dlp + beta_ent * dH);
-        }
+        for (int k = 0; k < 4; ++k) gl[k] *= -inv_n;
         dlogits[i] = make_float4(gl[0], gl[1], gl[2], gl[3]);
-        dvalue[i] = inv_n * c_v * dvl;
+        dvalue[i] = inv_n * c_v * dv_unit;
         acc[0] += double(ppo);
         acc[1] += double(vl);
         acc[2] += double(H);

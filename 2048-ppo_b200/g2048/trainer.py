@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import dp, env, fused, ppo, rollout
+from . import dp, env, fused, ppo, rollout, update
 from .policy import GameMLP, MLPConfig
 
 
@@ -43,8 +43,10 @@ class TrainConfig:
     zero_heads: bool = True        # train.py:1559-1567
     dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
     rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
-    update_matmul: str = "x3"         # the update's Linear GEMMs: "x3" = split-bf16 tcgen05 kernels (g2048.linear, fp32-grade),
-                                      # "fp32" = cuBLAS SGEMM, "tf32" = cuBLAS TF32 (below the reference's precision)
+    update_matmul: str = "fused"      # the update's forward/backward: "fused" = one tcgen05 kernel for forward + loss + backward-data
+                                      # and x3 tensor-core weight gradients (g2048.update; split-bf16, ~1e-5), "x3" = torch autograd graph
+                                      # with the x3 GEMM kernels (g2048.linear), "fp32" = autograd + cuBLAS SGEMM (reference
+                                      # precision), "tf32" = autograd + cuBLAS TF32
 
 
 def cosine_with_warmup(warmup: int, total: int):
@@ -155,10 +157,17 @@ class Trainer:
                 n_mb_global = n_global if c.minibatches == 1 else (m1 - m0) * self.world
                 self.opt.zero_grad()
                 tot = torch.zeros(4, dtype=torch.float64, device=self.device)
+                use_fused = c.update_matmul == "fused" and update.supported(self.model)
+                packed = update.pack(self.model) if use_fused else None
                 for c0 in range(m0, m1, c.chunk):
                     sl = slice(c0, min(m1, c0 + c.chunk)) if order is None else order[c0:min(m1, c0 + c.chunk)]
+                    if use_fused:
+                        tot += update.loss_and_grads(self.model, boards[sl], actions[sl], legal[sl], logp[sl], a[sl], g[sl],
+                                                     flags=flags[sl], clip_eps=c.clip_eps, critic_strength=c.critic_strength,
+                                                     entropy_strength=c.entropy_strength, n_total=n_mb_global, packed=packed)
+                        continue
                     logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
-                                                  matmul="x3" if c.update_matmul == "x3" else "cublas")
+                                                  matmul="x3" if c.update_matmul in ("x3", "fused") else "cublas")
                     loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],
                                                clip_eps=c.clip_eps, critic_strength=c.critic_strength,
                                                entropy_strength=c.entropy_strength, n_total=n_mb_global)

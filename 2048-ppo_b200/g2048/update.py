@@ -1,0 +1,153 @@
+"""The policy update's forward + loss + backward as hand-written kernels (no autograd graph).
+
+`loss_and_grads(model, ...)` is what train.model_optimize_step does between `optimizer.zero_grad()` and
+`clip_grad_norm_` (train.py:491-556) for a GameMLP with dropout off: it ADDS d loss / d parameter into every
+`p.grad` and returns the loss sums.  One fused tcgen05 kernel (g2048_update_mlp_fwd_bwd) runs the forward,
+the PPO-clip / critic / entropy terms and the backward-data chain per 128-sample tile; the weight gradients
+are split-bf16 tcgen05 reductions over samples (g2048_x3_wgrad).  There is no fallback: unsupported model
+shapes raise (use g2048.fused.mlp_forward + g2048.ppo.ppo_loss with autograd for those).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, env, linear
+from .env import _ptr, _req, _stream, init
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class _UpdateMlp(C.Structure):   # include/g2048.h: G2048UpdateMlp
+    _fields_ = [("n", i64), ("hidden", i32), ("layers", i32), ("decouple_critic", i32), ("backward", i32),
+                ("boards", vp), ("actions", vp), ("legal", vp), ("flags", vp), ("old_logp", vp),
+                ("old_logp_stride", i32), ("reserved_", i32), ("adv", vp), ("g_norm", vp),
+                ("clip_eps", f32), ("critic_strength", f32), ("entropy_strength", f32), ("inv_n", f32),
+                ("packed", vp), ("workspace", vp), ("h_out", vp), ("dz_out", vp), ("dhead", vp), ("logits", vp),
+                ("value", vp), ("ln_grad", vp), ("head_bias_grad", vp), ("stats", vp)]
+
+
+_lib.register("g2048_update_mlp_pack", [i32, i32] + [vp] * 12)
+_lib.register("g2048_update_mlp_fwd_bwd", [C.POINTER(_UpdateMlp), vp])
+for _name in ("g2048_update_mlp_pack_bytes", "g2048_update_mlp_workspace_bytes"):
+    getattr(_lib.lib(), _name).restype = i64
+    getattr(_lib.lib(), _name).argtypes = [i32, i32]
+
+_WS: dict[tuple[int, int, int], torch.Tensor] = {}
+
+
+def supported(model) -> bool:
+    h, L = model.stem[0].weight.shape[0], len(model.backbone)
+    no_dropout = all(blk.mlp[3].p == 0 or not model.training for blk in model.backbone)
+    return 16 <= h <= 208 and h % 4 == 0 and 1 <= L <= 2 and no_dropout and model.stem[0].weight.shape[1] == 48
+
+
+def _shape(model):
+    return model.stem[0].weight.shape[0], len(model.backbone)
+
+
+def _workspace(dev, h, L):
+    key = (dev.index, h, L)
+    if key not in _WS:
+        _WS[key] = torch.empty(int(_lib.lib().g2048_update_mlp_workspace_bytes(h, L)), dtype=torch.uint8, device=dev)
+    return _WS[key]
+
+
+def pack(model) -> torch.Tensor:
+    """Kernel-side image of the model's current parameters (re-pack after every optimizer step)."""
+    if not supported(model):
+        raise ValueError("g2048.update: GameMLP with hidden % 4 == 0 in [16, 208], 1-2 blocks and dropout off required")
+    h, L = _shape(model)
+    dev = init(model.stem[0].weight.device)
+    f = lambda t: _req(t.detach(), torch.float32, "parameter")
+    keep = [f(model.stem[0].weight), f(model.stem[1].weight), f(model.stem[1].bias)]
+    bw = [f(b.mlp[0].weight) for b in model.backbone]
+    bg = [f(b.mlp[1].weight) for b in model.backbone]
+    bb = [f(b.mlp[1].bias) for b in model.backbone]
+    heads = [f(model.action_head.weight), f(model.action_head.bias), f(model.value_head.weight), f(model.value_head.bias)]
+    arr = lambda ts: (vp * len(ts))(*[t.data_ptr() for t in ts])
+    with torch.cuda.device(dev):
+        packed = torch.empty(int(_lib.lib().g2048_update_mlp_pack_bytes(h, L)), dtype=torch.uint8, device=dev)
+        _lib.call("g2048_update_mlp_pack", h, L, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]),
+                  C.cast(arr(bw), vp), C.cast(arr(bg), vp), C.cast(arr(bb), vp),
+                  _ptr(heads[0]), _ptr(heads[1]), _ptr(heads[2]), _ptr(heads[3]), _ptr(packed), _stream())
+    return packed
+
+
+def forward(model, boards: torch.Tensor, packed: torch.Tensor | None = None):
+    """(logits [n,4], value [n,1]) of GameMLP on packed boards through the fused kernel (forward only)."""
+    h, L = _shape(model)
+    boards = _req(boards.reshape(-1), torch.int64, "boards")
+    n = boards.numel()
+    dev = init(boards.device)
+    packed = pack(model) if packed is None else packed
+    with torch.cuda.device(dev):
+        logits = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        value = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        u = _UpdateMlp(n=n, hidden=h, layers=L, decouple_critic=int(model.decouple_critic), backward=0,
+                       boards=boards.data_ptr(), packed=packed.data_ptr(), workspace=_workspace(dev, h, L).data_ptr(),
+                       logits=logits.data_ptr(), value=value.data_ptr())
+        _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
+    return logits, value
+
+
+def _acc(p: torch.nn.Parameter, g: torch.Tensor) -> None:
+    g = g.reshape(p.shape)
+    if p.grad is None:
+        p.grad = g.clone()
+    else:
+        p.grad.add_(g)
+
+
+def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flags=None, clip_eps=0.2,
+                   critic_strength=1.0, entropy_strength=0.1, n_total: int | None = None,
+                   packed: torch.Tensor | None = None, keep: dict | None = None) -> torch.Tensor:
+    """Adds the gradients of the minibatch-mean loss (train.py:554) over these samples into `p.grad` of every
+    parameter and returns float64[4] = {sum ppo, sum smooth_l1, sum entropy, count} (device tensor).
+    `n_total`: divisor of the mean when this call is a chunk / shard of a larger minibatch.
+    `keep`: optional dict that receives the intermediate tensors (tests)."""
+    h, L = _shape(model)
+    boards = _req(boards.reshape(-1), torch.int64, "boards")
+    n = boards.numel()
+    dev = init(boards.device)
+    packed = pack(model) if packed is None else packed
+    old_logp = _req(old_logp, torch.float32, "old_logp")
+    stride = 4 if old_logp.numel() == 4 * n else 1
+    assert old_logp.numel() == stride * n
+    with torch.cuda.device(dev):
+        h_out = torch.empty((L + 1, n, h), dtype=torch.float32, device=dev)
+        dz_out = torch.empty((L + 1, n, h), dtype=torch.float32, device=dev)
+        dhead = torch.empty((n, 8), dtype=torch.float32, device=dev)
+        ln_grad = torch.empty((L + 1, 2, h), dtype=torch.float32, device=dev)
+        hb_grad = torch.empty(5, dtype=torch.float32, device=dev)
+        stats = torch.empty(4, dtype=torch.float64, device=dev)
+        u = _UpdateMlp(n=n, hidden=h, layers=L, decouple_critic=int(model.decouple_critic), backward=1,
+                       boards=boards.data_ptr(), actions=_req(actions, torch.uint8, "actions").data_ptr(),
+                       legal=_req(legal, torch.uint8, "legal").data_ptr(),
+                       flags=None if flags is None else _req(flags, torch.uint8, "flags").data_ptr(),
+                       old_logp=old_logp.data_ptr(), old_logp_stride=stride,
+                       adv=_req(adv, torch.float32, "adv").data_ptr(), g_norm=_req(g_norm, torch.float32, "g_norm").data_ptr(),
+                       clip_eps=clip_eps, critic_strength=critic_strength, entropy_strength=entropy_strength,
+                       inv_n=1.0 / float(n_total if n_total else max(n, 1)),
+                       packed=packed.data_ptr(), workspace=_workspace(dev, h, L).data_ptr(),
+                       h_out=h_out.data_ptr(), dz_out=dz_out.data_ptr(), dhead=dhead.data_ptr(),
+                       ln_grad=ln_grad.data_ptr(), head_bias_grad=hb_grad.data_ptr(), stats=stats.data_ptr())
+        _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
+        if n > 0:
+            # weight gradients: reductions over samples on the tensor cores
+            _acc(model.stem[0].weight, linear.wgrad(dz_out[0], env.encode(boards)))
+            for l, blk in enumerate(model.backbone):
+                _acc(blk.mlp[0].weight, linear.wgrad(dz_out[l + 1], h_out[l]))
+            dwh = linear.wgrad(dhead, h_out[L])
+            _acc(model.action_head.weight, dwh[:4])
+            _acc(model.value_head.weight, dwh[4:5])
+            lns = [model.stem[1]] + [blk.mlp[1] for blk in model.backbone]
+            for l, ln in enumerate(lns):
+                _acc(ln.weight, ln_grad[l, 0])
+                _acc(ln.bias, ln_grad[l, 1])
+            _acc(model.action_head.bias, hb_grad[:4])
+            _acc(model.value_head.bias, hb_grad[4:5])
+    if keep is not None:
+        keep.update(h_out=h_out, dz_out=dz_out, dhead=dhead, ln_grad=ln_grad, head_bias_grad=hb_grad)
+    return stats

@@ -214,8 +214,8 @@ def rollout_section(args, dev, world, rank, barrier):
     ro_fp32_ms = time_rollout("fp32")
     ro_ms = time_rollout("bf16")
     cfg.rollout_precision = "auto"
-    # rollout + update: the headline uses the split-bf16 tcgen05 GEMMs (g2048.linear); the cuBLAS fp32 and
-    # TF32 updates are reported beside it
+    # rollout + update: the headline is the fused tcgen05 update (g2048.update); the autograd variants with the
+    # x3 GEMM kernels, cuBLAS fp32 and cuBLAS TF32 are reported beside it
     def time_train(matmul):
         cfg.update_matmul = matmul
         t.train_step()
@@ -229,11 +229,12 @@ def rollout_section(args, dev, world, rank, barrier):
 
     tf32_ms, _, _ = time_train("tf32")
     fp32_ms, _, _ = time_train("fp32")
-    step_ms, stats, times = time_train("x3")
+    x3_ms, _, _ = time_train("x3")
+    step_ms, stats, times = time_train("fused")
     if world > 1:
-        v = torch.tensor([step_ms, tf32_ms, fp32_ms], device=dev)
+        v = torch.tensor([step_ms, tf32_ms, fp32_ms, x3_ms], device=dev)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        step_ms, tf32_ms, fp32_ms = (float(x) for x in v.tolist())
+        step_ms, tf32_ms, fp32_ms, x3_ms = (float(x) for x in v.tolist())
     # ---- C5: GameURM rollout (default config), a few steps at the configured env count
     urm = None
     if args.urm_envs > 0:
@@ -271,7 +272,8 @@ def rollout_section(args, dev, world, rank, barrier):
                               "kernel": "rollout_mlp_kernel<208>"},
         "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
         "train_step_ms": step_ms,
-        "update": "torch autograd graph; Linear forward/dgrad/wgrad = g2048 split-bf16 (x3) tcgen05 kernels, fused g2048 LayerNorm/ReLU/residual and PPO-loss kernels, Muon+AdamW",
+        "update": "update_mlp_kernel (one tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-bf16 x3 GEMMs) + x3_wgrad_kernel weight gradients, Muon+AdamW",
+        "x3_autograd_update_variant": {"train_step_ms": x3_ms, "rollout_update_steps_per_sec": world * n_local / (x3_ms * 1e-3)},
         "cublas_fp32_update_variant": {"train_step_ms": fp32_ms, "rollout_update_steps_per_sec": world * n_local / (fp32_ms * 1e-3)},
         "cublas_tf32_update_variant": {"train_step_ms": tf32_ms, "rollout_update_steps_per_sec": world * n_local / (tf32_ms * 1e-3)},
         "phase_ms_rank0": {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,

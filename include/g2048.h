@@ -245,6 +245,58 @@ int64_t g2048_x3_wgrad_workspace_bytes(void);
 int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                    void* stream);
 
+/* ---- policy update: fused forward + loss + backward-data of GameMLP (csrc/g2048_update_fused.cu) ----
+ * One persistent tcgen05 kernel runs, per 128-sample tile and without leaving the SM, what
+ * model_optimize_step does between `model(x)` and the weight gradients (train.py:491-556): the GameMLP
+ * forward (game.py:1145-1220) from packed boards, the PPO-clip + critic + entropy terms (train.py:497-554)
+ * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-bf16 ("x3", fp32-grade).
+ * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], each
+ * [n, hidden] fp32, plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0); then
+ *     d stem.0.weight        = g2048_x3_wgrad(dz_out[0], g2048_encode(boards))        [hidden, 48]
+ *     d backbone.l.mlp.0.w   = g2048_x3_wgrad(dz_out[l+1], h_out[l])                  [hidden, hidden]
+ *     d (action|value) head  = g2048_x3_wgrad(dhead, h_out[L]) rows 0..3 | 4          [8, hidden]
+ * and returns the small gradients itself: ln_grad [L+1][2][hidden] (d LayerNorm weight | bias per layer,
+ * stem first), head_bias_grad [5] (action_head.bias, value_head.bias) and stats double[4] = {sum ppo,
+ * sum smooth_l1, sum entropy, count} as g2048_ppo_loss.  All per-SM partial sums are combined in a fixed
+ * order (deterministic).  hidden: multiple of 4 in [16, 208]; layers 1..2; dropout must be off.
+ * backward = 0: forward only (writes logits [n,4] and/or value [n]; used by the parity tests). */
+int64_t g2048_update_mlp_pack_bytes(int32_t hidden, int32_t layers);
+int g2048_update_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
+                          const float* const* block_w, const float* const* block_ln_w, const float* const* block_ln_b,
+                          const float* action_w, const float* action_b, const float* value_w, const float* value_b,
+                          void* packed, void* stream);
+int64_t g2048_update_mlp_workspace_bytes(int32_t hidden, int32_t layers);
+
+typedef struct G2048UpdateMlp {
+    int64_t n;                     /* samples */
+    int32_t hidden, layers;
+    int32_t decouple_critic;       /* MLPConfig.decouple_critic: the value head's gradient stops at h_L (game.py:1208) */
+    int32_t backward;              /* 0 = forward only */
+    const uint64_t* boards;        /* [n] state_before of every sample */
+    const uint8_t* actions;        /* [n] */
+    const uint8_t* legal;          /* [n] legal-move bits */
+    const uint8_t* flags;          /* [n] or NULL; samples without G2048_FLAG_VALID contribute nothing */
+    const float* old_logp;         /* [n, old_logp_stride] rollout log-probs (stride 4: all actions, 1: the chosen one) */
+    int32_t old_logp_stride;
+    int32_t reserved_;
+    const float* adv;              /* [n] */
+    const float* g_norm;           /* [n] normalised return-to-go */
+    float clip_eps, critic_strength, entropy_strength;
+    float inv_n;                   /* 1 / (global sample count of the minibatch): the loss is a mean (train.py:554) */
+    const void* packed;            /* g2048_update_mlp_pack output */
+    void* workspace;               /* g2048_update_mlp_workspace_bytes bytes */
+    float* h_out;                  /* [layers+1][n][hidden] */
+    float* dz_out;                 /* [layers+1][n][hidden] */
+    float* dhead;                  /* [n][8] */
+    float* logits;                 /* [n][4] or NULL */
+    float* value;                  /* [n] or NULL */
+    float* ln_grad;                /* [layers+1][2][hidden] */
+    float* head_bias_grad;         /* [5] */
+    double* stats;                 /* [4] */
+} G2048UpdateMlp;
+
+int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* params, void* stream);
+
 /* tcgen05 building-block self-test (not part of the reference's interface): C[128,N] =
  * A[128,K] * W[N,K]^T with bf16-rounded operands and fp32 accumulation in tensor memory.
  * K, N multiples of 16, <= 256.  Pins the UMMA descriptor / swizzle conventions on hardware. */
