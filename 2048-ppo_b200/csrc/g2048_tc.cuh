@@ -120,6 +120,23 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 8-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld8x2(uint32_t ta, float* a, uint32_t tb, float* b) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(ta), "r"(tb)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = __uint_as_float(r[i]);
+        b[i] = __uint_as_float(r[8 + i]);
+    }
+}
 // Split-phase 16-column load for register-resident rows: issue any number of loads, then
 // tmem_ld_wait_all(), then pass every destination register through tmem_ld_pin() -- an empty
 // volatile asm that keeps the compiler from scheduling a use of the register above the wait.

@@ -164,28 +164,32 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
     const float inv_h = 1.0f / float(h);
     const float* gam = S.gamma[l] + c.c0;
     const float* bet = S.beta[l] + c.c0;
-    float sum = 0.f;
+    // one pass: sum and sum of squares of the row (padded columns hold z = 0 and add nothing)
+    float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-    for (int g = 0; g < c.ng; ++g) {
-        float v[8];
-        tc::tmem_ld8(c.tD + uint32_t(8 * g), v);
+    for (int g = 0; g < c.ng; g += 2) {
+        float v[8], w[8];
+        if (g + 1 < c.ng) {
+            tc::tmem_ld8x2(c.tD + uint32_t(8 * g), v, c.tD + uint32_t(8 * g + 8), w);
+        } else {
+            tc::tmem_ld8(c.tD + uint32_t(8 * g), v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += STEM ? v[j] + S.b0[c.c0 + 8 * g + j] : v[j];
-    }
-    const float mean = exchange(S, 0, c.part, c.row, sum) * inv_h;
-    float sq = 0.f;
-#pragma unroll 1
-    for (int g = 0; g < c.ng; ++g) {
-        float v[8];
-        tc::tmem_ld8(c.tD + uint32_t(8 * g), v);
+            for (int j = 0; j < 8; ++j) w[j] = 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float d = (STEM ? v[j] + S.b0[c.c0 + 8 * g + j] : v[j]) - mean;
-            sq = fmaf(d, d, sq);
+            const float a = STEM ? v[j] + S.b0[c.c0 + 8 * g + j] : v[j];
+            const float b = (STEM && g + 1 < c.ng) ? w[j] + S.b0[c.c0 + 8 * g + 8 + j] : w[j];
+            sum += a + b;
+            sq = fmaf(a, a, fmaf(b, b, sq));
         }
     }
-    // padded columns hold z = 0 and each contributed mean^2: take them out
-    const float var = fmaxf((exchange(S, 1, c.part, c.row, sq) - float(HP - h) * mean * mean) * inv_h, 0.f);
+    S.red[0][c.part][c.row] = sum;
+    S.red[1][c.part][c.row] = sq;
+    row_sync();
+    const float mean = ((S.red[0][0][c.row] + S.red[0][1][c.row]) + (S.red[0][2][c.row] + S.red[0][3][c.row])) * inv_h;
+    const float msq = ((S.red[1][0][c.row] + S.red[1][1][c.row]) + (S.red[1][2][c.row] + S.red[1][3][c.row])) * inv_h;
+    const float var = fmaxf(msq - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
     if (c.part == 0) {
         S.stats[l][0][c.row] = mean;
@@ -199,8 +203,8 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
     for (int g = 0; g < c.ng; ++g) {
         const int col = c.c0 + 8 * g;
         float z[8], x[8];
-        tc::tmem_ld8(c.tD + uint32_t(8 * g), z);
-        if (!STEM) tc::tmem_ld8(c.tX + uint32_t(8 * g), x);
+        if (STEM) tc::tmem_ld8(c.tD + uint32_t(8 * g), z);
+        else tc::tmem_ld8x2(c.tD + uint32_t(8 * g), z, c.tX + uint32_t(8 * g), x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (STEM) z[j] += S.b0[col + j];
@@ -274,10 +278,9 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
             }
         } else {
             const float4 z0 = *reinterpret_cast<const float4*>(zrow + col), z1 = *reinterpret_cast<const float4*>(zrow + col + 4);
-            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
             float d[8];
-            tc::tmem_ld8(c.tX + uint32_t(8 * g), dh);
-            tc::tmem_ld8(c.tD + uint32_t(8 * g), d);
+            tc::tmem_ld8x2(c.tX + uint32_t(8 * g), dh, c.tD + uint32_t(8 * g), d);
+            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dh[j] += d[j];
         }
@@ -306,8 +309,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
     for (int g = 0; g < c.ng; ++g) {
         const int col = c.c0 + 8 * g;
         float xh[8], dh[8], dz[8];
-        tc::tmem_ld8(c.tD + uint32_t(8 * g), xh);
-        tc::tmem_ld8(c.tX + uint32_t(8 * g), dh);
+        tc::tmem_ld8x2(c.tD + uint32_t(8 * g), xh, c.tX + uint32_t(8 * g), dh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaf(xh[j], gam[8 * g + j], bet[8 * g + j]);
