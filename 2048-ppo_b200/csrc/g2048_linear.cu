@@ -226,7 +226,7 @@ struct WgradBars {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ partial, int64_t M, int N,
-                int K) {
+                int K, int dy_hp, int x_hp) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sW = align1024(smem_raw);
     WgradBars& S = *reinterpret_cast<WgradBars*>(sW + W_STAGES * W_STAGE);
@@ -264,11 +264,16 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
             for (int i = 0; i < PER_WARP; ++i) {
                 const int u = warp + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
                 const int row = rg * 8 + (lane >> 2), f = lane & 3, col = b * 16 + f * 4;
-                const int ld = mat ? K : N;
+                const int ld = mat ? K : N, hp = mat ? x_hp : dy_hp;
                 const float* src = mat ? X : dY;
                 const int64_t s = sample0 + row;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (s < M && col < ld) v[i] = __ldg(reinterpret_cast<const float4*>(src + s * ld + col));
+                if (s < M && col < ld) {
+                    // hp > 0: the update kernel's tiled layout [tile][col / 8][row][8] with hp padded columns
+                    const float* a = hp ? src + (((s >> 7) * (hp >> 3) + (col >> 3)) * 128 + (s & 127)) * 8 + (col & 7)
+                                        : src + s * ld + col;
+                    v[i] = __ldg(reinterpret_cast<const float4*>(a));
+                }
             }
             const int slot = q % W_STAGES;
             tc::mbar_wait(&S.empty[slot], (uint32_t(q / W_STAGES) & 1u) ^ 1u);
@@ -415,7 +420,14 @@ int g2048_x3_gemm(const float* A, const void* image, float* C, int64_t M, int32_
 int64_t g2048_x3_wgrad_workspace_bytes(void) { return int64_t(num_sms()) * MAXF * MAXF * 4; }
 
 int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K, void* stream) {
+    return g2048_x3_wgrad_tiled(dY, X, dW, workspace, M, N, K, 0, 0, stream);
+}
+
+int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
+                         int32_t dy_hp, int32_t x_hp, void* stream) {
     G2048_REQUIRE(M >= 0, "g2048_x3_wgrad: M < 0");
+    G2048_REQUIRE((dy_hp == 0 || (dy_hp % 16 == 0 && dy_hp >= N && dy_hp <= MAXF)) && (x_hp == 0 || (x_hp % 16 == 0 && x_hp >= K && x_hp <= MAXF)),
+                  "g2048_x3_wgrad: tiled operands need a padded width that is a multiple of 16 in [features, 208]");
     G2048_REQUIRE(dW != nullptr, "g2048_x3_wgrad: dW is NULL");
     if (!feat_ok(N) || !feat_ok(K)) return fail(G2048_ESHAPE, "g2048_x3_wgrad: N=%d, K=%d must be multiples of 4 in [4,208]", N, K);
     cudaStream_t st = cudaStream_t(stream);
@@ -430,7 +442,7 @@ int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, 
     G2048_CHECK_CUDA(ensure_smem(x3_wgrad_kernel, smem));
     const int64_t stages = (M + W_ROWS - 1) / W_ROWS;
     const int grid = int(stages < num_sms() ? stages : num_sms());
-    x3_wgrad_kernel<<<grid, NUM_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K);
+    x3_wgrad_kernel<<<grid, NUM_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
     G2048_CHECK_LAUNCH("x3_wgrad_kernel");
     x3_wgrad_reduce_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), dW, N, K, grid);
     G2048_CHECK_LAUNCH("x3_wgrad_reduce_kernel");

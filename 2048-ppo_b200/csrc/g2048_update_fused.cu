@@ -14,10 +14,10 @@
 // g2048_linear.cu); LayerNorm, ReLU, residual stream, heads, loss and LayerNorm-backward are fp32 on the
 // CUDA cores, thread-per-row (4 threads share a row, one column quarter each).  The residual stream
 // h (forward) / dh (backward) lives in TMEM columns [256, 256+HP), the accumulator in [0, HP).
-// Weight k-blocks (hi|lo, HP x 32 B each) stream L2 -> SMEM through a 5-slot ring filled by a
-// producer warp with bulk async copies, in the fixed order the chain consumes them.
+// Weight k-blocks (hi|lo, HP x 32 B each) stream L2 -> SMEM through a 5-slot ring of bulk async copies in
+// the fixed order the chain consumes them; one thread refills it while the MMAs of a stage drain it.
 //
-// What leaves the SM per sample: h_0..h_L and dz_0..dz_L (fp32 rows, the operands of the weight-gradient
+// What leaves the SM per sample: h_0..h_L and dz_0..dz_L (fp32, tiled; the operands of the weight-gradient
 // GEMMs dW_l = dz_l^T h_{l-1}, run afterwards by x3_wgrad_kernel), the 5 head gradients, and nothing
 // else: z_l, LN statistics, logits, per-sample loss terms never touch HBM (z_0..z_{L-1} round-trip
 // through a per-CTA scratch that stays in L2).  LayerNorm-parameter gradients are column sums over
@@ -35,7 +35,8 @@ namespace uf {
 constexpr int MAXH = 208, MAXL = 2, MAXKB = MAXH / 16;
 constexpr int SPLIT = 4;
 constexpr int ROW_THREADS = 128 * SPLIT;        // 16 warps: warp w -> lane quarter (w & 3), column part (w >> 2)
-constexpr int THREADS = ROW_THREADS + 32;       // + weight producer warp
+constexpr int THREADS = ROW_THREADS;            // thread 0 issues the MMAs, thread 32 streams the weights while both wait
+                                                // for a stage (4 warps per scheduler -> 128 registers per thread)
 constexpr int RING = 5;
 constexpr uint32_t X_COL = 256;
 constexpr uint32_t A_PART = MAXKB * 4096;       // one operand part: 13 k-blocks of 128 rows x 32 B
@@ -43,7 +44,7 @@ constexpr uint32_t B_SLOT = MAXH * 64;          // one weight k-block, hi | lo
 constexpr uint32_t ROLL_VALID = 0x80u;
 
 struct Params {
-    int64_t n;
+    int64_t n, ntiles;
     int h, HP, L, decouple;
     int backward;                 // 0: forward only (logits / value out), 1: forward + loss + backward-data
     const uint64_t* boards;
@@ -54,12 +55,12 @@ struct Params {
     float clip_eps, c_v, beta_ent, inv_n;
     const float* pf;              // fp32 section of the pack
     const uint8_t* img;           // weight k-blocks in consumption order
-    float* h_out;                 // [L+1][n][h]
-    float* dz_out;                // [L+1][n][h]
+    float* h_out;                 // [L+1][ntiles][HP/8][128][8]  (tiled, see st256)
+    float* dz_out;                // same layout
     float* dhead;                 // [n][8]: d loss / d (logits, V), 3 zero pads
     float* logits;                // [n][4] or NULL
     float* value;                 // [n] or NULL
-    float* zscratch;              // [grid][L][128][HP]
+    float* zscratch;              // [grid][L][HP/8][128][8]
     float* ln_part;               // [grid][4][L+1][2][HP]  (zeroed by the caller)
     float* head_part;             // [grid][8]: d head biases (5) + pad
     double* loss_part;            // [grid][4]
@@ -118,9 +119,19 @@ __device__ __forceinline__ void store_operand(Smem& S, int row, int col, const f
     *reinterpret_cast<uint4*>(S.A[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-__device__ __forceinline__ void store8_guarded(float* rowptr, int col, int h, const float* v) {
-    if (col < h) *reinterpret_cast<float4*>(rowptr + col) = make_float4(v[0], v[1], v[2], v[3]);
-    if (col + 4 < h) *reinterpret_cast<float4*>(rowptr + col + 4) = make_float4(v[4], v[5], v[6], v[7]);
+// 32-byte (one sector) global accesses: the activation / gradient tensors this kernel writes are TILED,
+// [tile][column group of 8][row 0..127][8 floats], so that the 32 rows of a warp store 1 KiB contiguously
+// (row-major rows are 784 B apart: 32 separate sectors per store instruction, measured 2x sector traffic)
+__device__ __forceinline__ void st256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld256(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
 }
 
 // sum over the 4 column parts of a row (each part contributes one value per slot)
@@ -152,6 +163,7 @@ struct RowCtx {
     int row, part, lane, warp, c0, ng;      // this thread's row, column part, first column, number of 8-column groups
     uint32_t tD, tX;                         // TMEM addresses of (lane quarter, column c0) in D and X
     int64_t grow;                            // global sample index
+    int64_t tile;                            // global tile index (grow / 128)
     bool valid;                              // grow < n
 };
 
@@ -191,12 +203,14 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
     const float msq = ((S.red[1][0][c.row] + S.red[1][1][c.row]) + (S.red[1][2][c.row] + S.red[1][3][c.row])) * inv_h;
     const float var = fmaxf(msq - mean * mean, 0.f);
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float shift = -mean * rstd;       // xhat = z * rstd + shift, the same expression in the backward pass
     if (c.part == 0) {
         S.stats[l][0][c.row] = mean;
         S.stats[l][1][c.row] = rstd;
     }
-    float* hrow = p.h_out + (size_t(l) * p.n + c.grow) * h;
-    float* zrow = last ? nullptr : p.zscratch + ((size_t(blockIdx.x) * L + l) * 128 + c.row) * HP;
+    // tiled addresses of (this row, column group 0); + 1024 floats per column group
+    float* hrow = p.h_out + ((size_t(l) * p.ntiles + c.tile) * (HP / 8) * 128 + c.row) * 8;
+    float* zrow = last ? nullptr : p.zscratch + ((size_t(blockIdx.x) * L + l) * (HP / 8) * 128 + c.row) * 8;
 #pragma unroll
     for (int q = 0; q < 5; ++q) o[q] = 0.f;
 #pragma unroll 1
@@ -208,17 +222,14 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (STEM) z[j] += S.b0[col + j];
-            const float y = fmaf((z[j] - mean) * rstd, gam[8 * g + j], bet[8 * g + j]);
+            const float y = fmaf(fmaf(z[j], rstd, shift), gam[8 * g + j], bet[8 * g + j]);
             const float r = fmaxf(y, 0.f);
             x[j] = STEM ? r : x[j] + r;
         }
         tc::tmem_st8(c.tX + uint32_t(8 * g), x);
         store_operand(S, c.row, col, x);
-        if (c.valid && p.backward) store8_guarded(hrow, col, h, x);
-        if (zrow && p.backward) {
-            *reinterpret_cast<float4*>(zrow + col) = make_float4(z[0], z[1], z[2], z[3]);
-            *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(z[4], z[5], z[6], z[7]);
-        }
+        if (c.valid && p.backward) st256(hrow + size_t(col) * 128, x);
+        if (zrow && p.backward) st256(zrow + size_t(col) * 128, z);
         if (last) {
 #pragma unroll
             for (int q = 0; q < 5; ++q)
@@ -252,10 +263,10 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
 __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, bool first) {
     const int HP = p.HP, h = p.h, L = p.L;
     const float inv_h = 1.0f / float(h);
-    const float mean = S.stats[l][0][c.row], rstd = S.stats[l][1][c.row];
+    const float mean = S.stats[l][0][c.row], rstd = S.stats[l][1][c.row], shift = -mean * rstd;
     const float* gam = S.gamma[l] + c.c0;
     const float* bet = S.beta[l] + c.c0;
-    const float* zrow = first ? nullptr : p.zscratch + ((size_t(blockIdx.x) * L + l) * 128 + c.row) * HP;
+    const float* zrow = first ? nullptr : p.zscratch + ((size_t(blockIdx.x) * L + l) * (HP / 8) * 128 + c.row) * 8;
     float dh5[5];
 #pragma unroll
     for (int q = 0; q < 5; ++q) dh5[q] = S.dhead[c.row][q];
@@ -277,16 +288,15 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
                 dh[j] = a;
             }
         } else {
-            const float4 z0 = *reinterpret_cast<const float4*>(zrow + col), z1 = *reinterpret_cast<const float4*>(zrow + col + 4);
+            ld256(zrow + size_t(col) * 128, z);
             float d[8];
             tc::tmem_ld8x2(c.tX + uint32_t(8 * g), dh, c.tD + uint32_t(8 * g), d);
-            z[0] = z0.x; z[1] = z0.y; z[2] = z0.z; z[3] = z0.w; z[4] = z1.x; z[5] = z1.y; z[6] = z1.z; z[7] = z1.w;
 #pragma unroll
             for (int j = 0; j < 8; ++j) dh[j] += d[j];
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float xh = (z[j] - mean) * rstd;
+            const float xh = fmaf(z[j], rstd, shift);
             const float y = fmaf(xh, gam[8 * g + j], bet[8 * g + j]);
             const float gj = y > 0.f ? dh[j] : 0.f;
             const float t = gj * gam[8 * g + j];
@@ -304,7 +314,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
     tc::tmem_st_wait();
     const float m1 = exchange(S, 0, c.part, c.row, s1) * inv_h;
     const float m2 = exchange(S, 1, c.part, c.row, s2) * inv_h;
-    float* dzrow = p.dz_out + (size_t(l) * p.n + c.grow) * h;
+    float* dzrow = p.dz_out + ((size_t(l) * p.ntiles + c.tile) * (HP / 8) * 128 + c.row) * 8;
 #pragma unroll 1
     for (int g = 0; g < c.ng; ++g) {
         const int col = c.c0 + 8 * g;
@@ -316,7 +326,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
             const float t = (y > 0.f ? dh[j] : 0.f) * gam[8 * g + j];
             dz[j] = (col + j < h) ? rstd * (t - m1 - xh[j] * m2) : 0.f;
         }
-        if (c.valid) store8_guarded(dzrow, col, h, dz);
+        if (c.valid) st256(dzrow + size_t(col) * 128, dz);
         if (l > 0) store_operand(S, c.row, col, dz);
     }
 }
@@ -326,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
     Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HP = p.HP, L = p.L, KB = HP / 16;
-    const int64_t ntiles = (p.n + 127) / 128;
+    const int64_t ntiles = p.ntiles;
     const int my_tiles = ntiles > blockIdx.x ? int((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const int nblk = blocks_per_tile(HP, L, p.backward != 0);
     const uint32_t blk_bytes = uint32_t(HP) * 64u;
@@ -357,19 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
     tc::fence_after_sync();
     const uint32_t tmem_base = S.tmem_base;
 
-    if (warp == ROW_THREADS / 32) {
-        // ---------------- weight producer: k-blocks in consumption order, tile after tile
-        if (lane == 0) {
-            uint32_t q = 0;
-            for (int t = 0; t < my_tiles; ++t)
-                for (int b = 0; b < nblk; ++b, ++q) {
-                    const uint32_t slot = q % RING;
-                    tc::mbar_wait(&S.b_empty[slot], ((q / RING) & 1u) ^ 1u);
-                    tc::mbar_expect_tx(&S.b_full[slot], blk_bytes);
-                    tc::bulk_g2s(S.B[slot], p.img + size_t(b) * blk_bytes, blk_bytes, &S.b_full[slot]);
-                }
-        }
-    } else {
+    {
         // ---------------- row threads
         RowCtx c;
         c.warp = warp;
@@ -381,7 +379,21 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
         c.ng = g1 - g0;
         c.tD = tmem_base + (uint32_t((warp & 3) * 32) << 16) + uint32_t(c.c0);
         c.tX = c.tD + X_COL;
-        const bool issuer = tid == 0;
+        const bool issuer = tid == 0, producer = tid == 32;
+        // weight producer state: block pq of the launch-wide sequence goes to slot pq % RING
+        const uint32_t total_blocks = uint32_t(my_tiles) * uint32_t(nblk);
+        uint32_t pq = 0, pb = 0;
+        auto refill = [&]() {        // non-blocking: issue every copy whose slot is free
+            while (pq < total_blocks) {
+                const uint32_t slot = pq % RING;
+                if (pq >= RING && !tc::mbar_test(&S.b_empty[slot], ((pq / RING) & 1u) ^ 1u)) break;
+                tc::mbar_expect_tx(&S.b_full[slot], blk_bytes);
+                tc::bulk_g2s(S.B[slot], p.img + size_t(pb) * blk_bytes, blk_bytes, &S.b_full[slot]);
+                ++pq;
+                if (++pb == uint32_t(nblk)) pb = 0;
+            }
+        };
+        if (producer) refill();
         const uint32_t idesc = tc::make_idesc_bf16_major(128, HP, false, false);
         const uint32_t a_hi = tc::smem_addr(S.A[0]), a_lo = tc::smem_addr(S.A[1]), b_base = tc::smem_addr(S.B[0]);
         uint32_t stage = 0, bq = 0;                 // running MMA-stage and weight-block counters (issuer)
@@ -411,13 +423,18 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
                 }
                 tc::mma_commit(&S.mma_done);
             }
+            if (producer) {
+                while (!tc::mbar_test(&S.mma_done, stage & 1u)) refill();
+                refill();            // every slot of this stage is free now: prefetch the next stage's first blocks
+            }
             tc::mbar_wait(&S.mma_done, stage & 1u);
             tc::fence_after_sync();
             ++stage;
         };
 
         for (int t = 0; t < my_tiles; ++t) {
-            c.grow = (int64_t(blockIdx.x) + int64_t(t) * gridDim.x) * 128 + c.row;
+            c.tile = int64_t(blockIdx.x) + int64_t(t) * gridDim.x;
+            c.grow = c.tile * 128 + c.row;
             c.valid = c.grow < p.n;
             // model input: the 16 exponents are exact in bf16 (k-block 0, hi part; row / column features
             // are folded into b0)
@@ -662,7 +679,7 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* u, void* stream) {
     const int64_t ntiles = (u->n + 127) / 128;
     const int grid = int(ntiles < num_sms() ? ntiles : num_sms());
     Params p{};
-    p.n = u->n; p.h = h; p.HP = HP; p.L = L; p.decouple = u->decouple_critic; p.backward = bw;
+    p.n = u->n; p.ntiles = ntiles; p.h = h; p.HP = HP; p.L = L; p.decouple = u->decouple_critic; p.backward = bw;
     p.boards = u->boards; p.actions = u->actions; p.legal = u->legal; p.flags = u->flags;
     p.old_logp = u->old_logp; p.old_stride = u->old_logp_stride; p.adv = u->adv; p.g_norm = u->g_norm;
     p.clip_eps = u->clip_eps; p.c_v = u->critic_strength; p.beta_ent = u->entropy_strength; p.inv_n = u->inv_n;

@@ -22,6 +22,8 @@ from .env import _ptr, _stream, init
 _lib.register("g2048_x3_pack", [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p])
 _lib.register("g2048_x3_gemm", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p])
 _lib.register("g2048_x3_wgrad", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p])
+_lib.register("g2048_x3_wgrad_tiled", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p])
 _lib.lib().g2048_x3_image_bytes.restype = C.c_int64
 _lib.lib().g2048_x3_image_bytes.argtypes = [C.c_int32, C.c_int32]
 _lib.lib().g2048_x3_wgrad_workspace_bytes.restype = C.c_int64
@@ -77,6 +79,18 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
             _WS[dev.index] = torch.empty(int(_lib.lib().g2048_x3_wgrad_workspace_bytes()), dtype=torch.uint8, device=dev)
         out = torch.empty((n, k), dtype=torch.float32, device=dev)
         _lib.call("g2048_x3_wgrad", _ptr(dy), _ptr(x), _ptr(out), _ptr(_WS[dev.index]), m, n, k, _stream())
+    return out
+
+
+def wgrad_tiled(dy: torch.Tensor, x: torch.Tensor, m: int, n: int, k: int, dy_hp: int = 0, x_hp: int = 0) -> torch.Tensor:
+    """dy^T x over m samples where either operand may be in the fused update kernel's tiled layout
+    (`*_hp` = its padded column count, 0 = row-major [m, features])."""
+    dev = init(dy.device)
+    with torch.cuda.device(dev):
+        if dev.index not in _WS:
+            _WS[dev.index] = torch.empty(int(_lib.lib().g2048_x3_wgrad_workspace_bytes()), dtype=torch.uint8, device=dev)
+        out = torch.empty((n, k), dtype=torch.float32, device=dev)
+        _lib.call("g2048_x3_wgrad_tiled", _ptr(dy), _ptr(x), _ptr(out), _ptr(_WS[dev.index]), m, n, k, dy_hp, x_hp, _stream())
     return out
 
 

@@ -116,8 +116,9 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
     stride = 4 if old_logp.numel() == 4 * n else 1
     assert old_logp.numel() == stride * n
     with torch.cuda.device(dev):
-        h_out = torch.empty((L + 1, n, h), dtype=torch.float32, device=dev)
-        dz_out = torch.empty((L + 1, n, h), dtype=torch.float32, device=dev)
+        hp, per_layer = (h + 15) // 16 * 16, (n + 127) // 128 * 128 * ((h + 15) // 16 * 16)
+        h_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)    # tiled, see untile()
+        dz_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)
         dhead = torch.empty((n, 8), dtype=torch.float32, device=dev)
         ln_grad = torch.empty((L + 1, 2, h), dtype=torch.float32, device=dev)
         hb_grad = torch.empty(5, dtype=torch.float32, device=dev)
@@ -136,10 +137,10 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
         _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
         if n > 0:
             # weight gradients: reductions over samples on the tensor cores
-            _acc(model.stem[0].weight, linear.wgrad(dz_out[0], env.encode(boards)))
+            _acc(model.stem[0].weight, linear.wgrad_tiled(dz_out[0], env.encode(boards), n, h, 48, dy_hp=hp))
             for l, blk in enumerate(model.backbone):
-                _acc(blk.mlp[0].weight, linear.wgrad(dz_out[l + 1], h_out[l]))
-            dwh = linear.wgrad(dhead, h_out[L])
+                _acc(blk.mlp[0].weight, linear.wgrad_tiled(dz_out[l + 1], h_out[l], n, h, h, dy_hp=hp, x_hp=hp))
+            dwh = linear.wgrad_tiled(dhead, h_out[L], n, 8, h, x_hp=hp)
             _acc(model.action_head.weight, dwh[:4])
             _acc(model.value_head.weight, dwh[4:5])
             lns = [model.stem[1]] + [blk.mlp[1] for blk in model.backbone]
@@ -149,5 +150,13 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
             _acc(model.action_head.bias, hb_grad[:4])
             _acc(model.value_head.bias, hb_grad[4:5])
     if keep is not None:
-        keep.update(h_out=h_out, dz_out=dz_out, dhead=dhead, ln_grad=ln_grad, head_bias_grad=hb_grad)
+        keep.update(h_out=torch.stack([untile(t, n, h) for t in h_out]), dz_out=torch.stack([untile(t, n, h) for t in dz_out]),
+                    dhead=dhead, ln_grad=ln_grad, head_bias_grad=hb_grad)
     return stats
+
+
+def untile(t: torch.Tensor, n: int, h: int) -> torch.Tensor:
+    """[n, h] view-copy of a tensor in the kernel's tiled layout [tile][column group of 8][row 0..127][8]."""
+    hp = (h + 15) // 16 * 16
+    tiles = (n + 127) // 128
+    return t.view(tiles, hp // 8, 128, 8).permute(0, 2, 1, 3).reshape(tiles * 128, hp)[:n, :h].contiguous()

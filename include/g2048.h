@@ -244,17 +244,23 @@ int g2048_x3_gemm(const float* A, const void* image, float* C, int64_t M, int32_
 int64_t g2048_x3_wgrad_workspace_bytes(void);
 int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                    void* stream);
+/* same, with either operand in the tiled layout g2048_update_mlp_fwd_bwd writes (h_out / dz_out):
+ * [tile of 128 samples][column group of 8][sample in tile][8 floats], `*_hp` = padded column count of that
+ * operand (hidden rounded up to 16), 0 = plain row-major. */
+int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
+                         int32_t dy_hp, int32_t x_hp, void* stream);
 
 /* ---- policy update: fused forward + loss + backward-data of GameMLP (csrc/g2048_update_fused.cu) ----
  * One persistent tcgen05 kernel runs, per 128-sample tile and without leaving the SM, what
  * model_optimize_step does between `model(x)` and the weight gradients (train.py:491-556): the GameMLP
  * forward (game.py:1145-1220) from packed boards, the PPO-clip + critic + entropy terms (train.py:497-554)
  * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-bf16 ("x3", fp32-grade).
- * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], each
- * [n, hidden] fp32, plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0); then
- *     d stem.0.weight        = g2048_x3_wgrad(dz_out[0], g2048_encode(boards))        [hidden, 48]
- *     d backbone.l.mlp.0.w   = g2048_x3_wgrad(dz_out[l+1], h_out[l])                  [hidden, hidden]
- *     d (action|value) head  = g2048_x3_wgrad(dhead, h_out[L]) rows 0..3 | 4          [8, hidden]
+ * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], fp32 in the
+ * tiled layout of g2048_x3_wgrad_tiled (ceil(n/128) * 128 * HP floats per l, HP = hidden rounded up to 16),
+ * plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0), row-major; then (g2048_x3_wgrad_tiled)
+ *     d stem.0.weight        = wgrad(dz_out[0], g2048_encode(boards))        [hidden, 48]
+ *     d backbone.l.mlp.0.w   = wgrad(dz_out[l+1], h_out[l])                  [hidden, hidden]
+ *     d (action|value) head  = wgrad(dhead, h_out[L]) rows 0..3 | 4          [8, hidden]
  * and returns the small gradients itself: ln_grad [L+1][2][hidden] (d LayerNorm weight | bias per layer,
  * stem first), head_bias_grad [5] (action_head.bias, value_head.bias) and stats double[4] = {sum ppo,
  * sum smooth_l1, sum entropy, count} as g2048_ppo_loss.  All per-SM partial sums are combined in a fixed
@@ -285,8 +291,8 @@ typedef struct G2048UpdateMlp {
     float inv_n;                   /* 1 / (global sample count of the minibatch): the loss is a mean (train.py:554) */
     const void* packed;            /* g2048_update_mlp_pack output */
     void* workspace;               /* g2048_update_mlp_workspace_bytes bytes */
-    float* h_out;                  /* [layers+1][n][hidden] */
-    float* dz_out;                 /* [layers+1][n][hidden] */
+    float* h_out;                  /* [layers+1][ceil(n/128)*128*HP] tiled */
+    float* dz_out;                 /* same */
     float* dhead;                  /* [n][8] */
     float* logits;                 /* [n][4] or NULL */
     float* value;                  /* [n] or NULL */
