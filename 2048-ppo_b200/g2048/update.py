@@ -102,11 +102,13 @@ def _acc(p: torch.nn.Parameter, g: torch.Tensor) -> None:
 
 def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flags=None, clip_eps=0.2,
                    critic_strength=1.0, entropy_strength=0.1, n_total: int | None = None,
-                   packed: torch.Tensor | None = None, keep: dict | None = None) -> torch.Tensor:
+                   packed: torch.Tensor | None = None, keep: dict | None = None,
+                   logits_out: torch.Tensor | None = None) -> torch.Tensor:
     """Adds the gradients of the minibatch-mean loss (train.py:554) over these samples into `p.grad` of every
     parameter and returns float64[4] = {sum ppo, sum smooth_l1, sum entropy, count} (device tensor).
     `n_total`: divisor of the mean when this call is a chunk / shard of a larger minibatch.
-    `keep`: optional dict that receives the intermediate tensors (tests)."""
+    `keep`: optional dict that receives the intermediate tensors (tests); `logits_out`: optional float32 [n, 4]
+    CUDA tensor that receives the forward's action logits."""
     h, L = _shape(model)
     boards = _req(boards.reshape(-1), torch.int64, "boards")
     n = boards.numel()
@@ -134,6 +136,9 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
                        packed=packed.data_ptr(), workspace=_workspace(dev, h, L).data_ptr(),
                        h_out=h_out.data_ptr(), dz_out=dz_out.data_ptr(), dhead=dhead.data_ptr(),
                        ln_grad=ln_grad.data_ptr(), head_bias_grad=hb_grad.data_ptr(), stats=stats.data_ptr())
+        if logits_out is not None:
+            assert logits_out.shape == (n, 4) and logits_out.is_contiguous()
+            u.logits = _req(logits_out, torch.float32, "logits_out").data_ptr()
         _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
         if n > 0:
             # weight gradients: reductions over samples on the tensor cores

@@ -377,7 +377,50 @@ def gen_loss(episodes_with_adv):
     print("loss:", n, "samples; stats", out["readme__stats"])
 
 
+class SgdStack:
+    """The optimizer interface model_optimize_step expects (train.py:1232-1281 MultiOptimizer) over plain SGD."""
+
+    def __init__(self, model, lr):
+        self.opt = torch.optim.SGD(model.parameters(), lr=lr)
+
+    def step(self):
+        self.opt.step()
+
+    def zero_grad(self):
+        self.opt.zero_grad(set_to_none=True)
+
+    def scheduler_step(self):
+        pass
+
+
+def gen_optimize(episodes_with_adv):
+    """train.model_optimize_step (train.py:414-642) as the train loop calls it: shuffled minibatches, two epochs,
+    a real optimizer (SGD lr 0.005), dropout = 0.  Records the returned statistics and the final weights."""
+    base, cfg = load_best_model()
+    model = G.GameMLP(G.MLPConfig(hidden_dim=cfg["hidden_dim"], num_layers=cfg["num_layers"], dropout=0.0))
+    model.load_state_dict(base.state_dict())
+    with torch.no_grad():
+        model.action_head.weight.mul_(1.3)
+        model.value_head.bias.add_(0.3)
+    keys = ["loss", "policy_loss", "entropy_loss", "value_loss", "grad_norm", "entropy", "kl_total", "kl_average", "kl_max", "lr"]
+    torch.manual_seed(777)
+    stats = TR.model_optimize_step(model=model, episodes=episodes_with_adv, optimizer=SgdStack(model, 0.005), lr_scheduler=None,
+                                   kl_strength=0.02, critic_strength=0.2, device=None, batch_size=128, epochs=2)
+    out = {"stats": np.array([stats[k] for k in keys], dtype=np.float64), "seed": np.int64(777), "lr": np.float64(0.005),
+           "batch_size": np.int64(128), "epochs": np.int64(2), "coef": np.array([0.02, 0.2])}
+    for k, t in model.state_dict().items():
+        out["final__" + k.replace(".", "__")] = t.numpy()
+    np.savez_compressed(os.path.join(OUT, "optimize.npz"), **out)
+    print("optimize:", dict(zip(keys, out["stats"].round(6))))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "optimize":     # only tests/golden/optimize.npz (the other fixtures stay untouched)
+        save, np.savez_compressed = np.savez_compressed, lambda *a, **k: None
+        eps_adv = gen_advantage(gen_rollout(gen_model(np.random.default_rng(11))))
+        np.savez_compressed = save
+        gen_optimize(eps_adv)
+        return
     os.makedirs(OUT, exist_ok=True)
     rng = np.random.default_rng(2048)
     gen_best_game()
@@ -387,6 +430,7 @@ def main():
     episodes = gen_rollout(model)
     eps_adv = gen_advantage(episodes)
     gen_loss(eps_adv)
+    gen_optimize(eps_adv)
     gen_urm(np.random.default_rng(13))
 
 

@@ -64,7 +64,7 @@ def _grad_check(got, ref, label, fro_tol=2e-4):
     """Relative Frobenius error of a gradient tensor.  With x3 GEMMs (pre-activations good to ~1e-5 of their
     scale) the bulk agrees to ~3e-5.  A unit whose LayerNorm output is within that error of zero can take the
     other ReLU branch than the float64 reference (measured: tools/debug_fused_golden.py -- one unit with
-    |y| = 9.8e-7 in the 876-sample fixture), which moves that SAMPLE's contribution by O(1/n): tests on small or
+    |y| = 9.8e-7 in the 1163-sample fixture), which moves that SAMPLE's contribution by O(1/n): tests on small or
     adversarial batches pass a larger `fro_tol` and say so."""
     got, ref = got.double().cpu(), torch.as_tensor(ref).double().cpu().reshape(got.shape)
     fro = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
@@ -177,7 +177,7 @@ def test_matches_reference_optimize_step(golden):
                                    [want[0], want[1], want[2], want[3], want[5]], rtol=1e-5)
         np.testing.assert_allclose(float(gnorm), want[4], rtol=1e-3)
         for k, p in m.named_parameters():
-            # fixture = the reference's CLIPPED gradients (unit total norm): rescale ours the same way; 876
+            # fixture = the reference's CLIPPED gradients (unit total norm): rescale ours the same way; 1163
             # samples, one unit of sample 325 at a ReLU threshold (|y| = 9.8e-7) -> 1e-2
             _grad_check(p.grad, gl[name + "__grad__" + k.replace(".", "__")], name + " " + k, fro_tol=1e-2)
 
