@@ -10,8 +10,13 @@
 //   dh_L = heads^T (dlogits, dV) ; for l = L..0:  g = dh_l * [LN_l(z_l) > 0], dz_l = LN_l-backward(g),
 //   dh_{l-1} = dh_l + dz_l W_l                                             (what autograd would run)
 //
-// Every GEMM is a split-bf16 ("x3") tensor-core product with fp32 accumulation in tensor memory (see
-// g2048_linear.cu); LayerNorm, ReLU, residual stream, heads, loss and LayerNorm-backward are fp32 on the
+// Every GEMM is a split-bf16 tensor-core product with fp32 accumulation in tensor memory (g2048_linear.cu).
+// The FORWARD products, which decide every ReLU branch and the loss, use three bf16 terms per operand
+// (x = hi + lo + r, 24 mantissa bits) and six products, hi*hi + hi*lo + lo*hi + lo*lo + r*hi + hi*r ("x6",
+// fp32-grade: measured ~1e-6 of scale): a first MMA phase on (hi, lo), then the row threads overwrite the lo
+// operand with r (recomputed from the fp32 residual stream in TMEM) and a second phase adds the r terms.
+// The backward products (smooth in their inputs) use two terms and three products ("x3", ~1e-5).
+// LayerNorm, ReLU, residual stream, heads, loss and LayerNorm-backward are fp32 on the
 // CUDA cores, thread-per-row (4 threads share a row, one column quarter each).  The residual stream
 // h (forward) / dh (backward) lives in TMEM columns [256, 256+HP), the accumulator in [0, HP).
 // Weight k-blocks (hi|lo, HP x 32 B each) stream L2 -> SMEM through a 5-slot ring of bulk async copies in
@@ -37,10 +42,10 @@ constexpr int SPLIT = 4;
 constexpr int ROW_THREADS = 128 * SPLIT;        // 16 warps: warp w -> lane quarter (w & 3), column part (w >> 2)
 constexpr int THREADS = ROW_THREADS;            // thread 0 issues the MMAs, thread 32 streams the weights while both wait
                                                 // for a stage (4 warps per scheduler -> 128 registers per thread)
-constexpr int RING = 5;
+constexpr int RING = 4;
 constexpr uint32_t X_COL = 256;
 constexpr uint32_t A_PART = MAXKB * 4096;       // one operand part: 13 k-blocks of 128 rows x 32 B
-constexpr uint32_t B_SLOT = MAXH * 64;          // one weight k-block, hi | lo
+constexpr uint32_t B_SLOT = MAXH * 96;          // one weight k-block: hi | lo | r (forward) or hi | lo (backward)
 constexpr uint32_t ROLL_VALID = 0x80u;
 
 struct Params {
@@ -74,9 +79,13 @@ __host__ __device__ inline int64_t pf_headw(int HP, int L) { return int64_t(3 + 
 __host__ __device__ inline int64_t pf_headb(int HP, int L) { return int64_t(8 + 2 * L) * HP; }
 __host__ __device__ inline int64_t pf_floats(int HP, int L) { return pf_headb(HP, L) + 8; }
 __host__ __device__ inline int64_t img_offset_bytes(int HP, int L) { return (pf_floats(HP, L) * 4 + 1023) / 1024 * 1024; }
-__host__ __device__ inline int blocks_per_tile(int HP, int L, bool backward) { return 1 + (backward ? 2 : 1) * L * (HP / 16); }
+// weight image: forward blocks (stem, then W_1..W_L, 3 parts each), then the transposed blocks W_L^T..W_1^T (2 parts).
+// A tile consumes: stem | per block l: the KB forward blocks TWICE (the two MMA phases of the x6 product) | the
+// transposed blocks in order.
+__host__ __device__ inline int fwd_blocks(int HP, int L) { return 1 + L * (HP / 16); }
+__host__ __device__ inline int blocks_per_tile(int HP, int L, bool backward) { return 1 + (backward ? 3 : 2) * L * (HP / 16); }
 __host__ __device__ inline int64_t pack_bytes(int HP, int L) {
-    return img_offset_bytes(HP, L) + int64_t(blocks_per_tile(HP, L, true)) * HP * 64;
+    return img_offset_bytes(HP, L) + int64_t(fwd_blocks(HP, L)) * HP * 96 + int64_t(L) * (HP / 16) * HP * 64;
 }
 
 struct Smem {
@@ -117,6 +126,23 @@ __device__ __forceinline__ void store_operand(Smem& S, int row, int col, const f
     const uint32_t off = uint32_t(col >> 4) * 4096u + uint32_t(row) * 32u + uint32_t(((((col >> 3) & 1) ^ (row >> 2)) & 1) << 4);
     *reinterpret_cast<uint4*>(S.A[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(S.A[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// third split term r = x - hi - lo of 8 consecutive columns -> the lo operand buffer (second MMA phase)
+__device__ __forceinline__ void store_operand_r(Smem& S, int row, int col, const float* x) {
+    uint32_t rr[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+        const float2 f = __bfloat1622float2(h2);
+        const float e0 = x[2 * q] - f.x, e1 = x[2 * q + 1] - f.y;
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(e0, e1);
+        const float2 g = __bfloat1622float2(l2);
+        const __nv_bfloat162 r2 = __floats2bfloat162_rn(e0 - g.x, e1 - g.y);
+        rr[q] = *reinterpret_cast<const uint32_t*>(&r2);
+    }
+    const uint32_t off = uint32_t(col >> 4) * 4096u + uint32_t(row) * 32u + uint32_t(((((col >> 3) & 1) ^ (row >> 2)) & 1) << 4);
+    *reinterpret_cast<uint4*>(S.A[1] + off) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
 }
 
 // 32-byte (one sector) global accesses: the activation / gradient tensors this kernel writes are TILED,
@@ -339,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
     const int64_t ntiles = p.ntiles;
     const int my_tiles = ntiles > blockIdx.x ? int((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
     const int nblk = blocks_per_tile(HP, L, p.backward != 0);
-    const uint32_t blk_bytes = uint32_t(HP) * 64u;
+    const uint32_t part_bytes = uint32_t(HP) * 32u;
 
     if (warp == 0) tc::tmem_alloc(&S.tmem_base, 512);
     if (tid == 0) {
@@ -387,8 +413,19 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             while (pq < total_blocks) {
                 const uint32_t slot = pq % RING;
                 if (pq >= RING && !tc::mbar_test(&S.b_empty[slot], ((pq / RING) & 1u) ^ 1u)) break;
-                tc::mbar_expect_tx(&S.b_full[slot], blk_bytes);
-                tc::bulk_g2s(S.B[slot], p.img + size_t(pb) * blk_bytes, blk_bytes, &S.b_full[slot]);
+                // position pb of the tile's sequence -> block of the image
+                const uint32_t nfwd = 1u + 2u * uint32_t(L * KB);
+                uint32_t off, bytes;
+                if (pb < nfwd) {
+                    const uint32_t t2 = pb - 1u, id = pb == 0 ? 0u : 1u + (t2 / uint32_t(2 * KB)) * uint32_t(KB) + t2 % uint32_t(KB);
+                    off = id * 3u * part_bytes;
+                    bytes = 3u * part_bytes;
+                } else {
+                    off = uint32_t(fwd_blocks(HP, L)) * 3u * part_bytes + (pb - nfwd) * 2u * part_bytes;
+                    bytes = 2u * part_bytes;
+                }
+                tc::mbar_expect_tx(&S.b_full[slot], bytes);
+                tc::bulk_g2s(S.B[slot], p.img + off, bytes, &S.b_full[slot]);
                 ++pq;
                 if (++pb == uint32_t(nblk)) pb = 0;
             }
@@ -400,8 +437,13 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
         double lacc[4] = {0.0, 0.0, 0.0, 0.0};
         float hb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 
-        // one MMA stage: D = A (kblocks k-blocks, `terms` split terms) x next weight blocks
-        auto run_stage = [&](int kblocks, bool exact_a) {
+        // One MMA stage over `kblocks` k-blocks of A against the next weight blocks of the ring.
+        //   ST_STEM: A exact in bf16 (hi only)            D  = hi*r + hi*lo + hi*hi
+        //   ST_FWD1: A = (hi, lo)                          D  = lo*lo + lo*hi + hi*lo + hi*hi
+        //   ST_FWD2: the lo buffer now holds r             D += r*hi + hi*r
+        //   ST_BWD : A = (hi, lo), 2-part weight blocks    D  = lo*hi + hi*lo + hi*hi
+        enum { ST_STEM, ST_FWD1, ST_FWD2, ST_BWD };
+        auto run_stage = [&](int kblocks, int kind) {
             tc::fence_async_smem();
             tc::fence_before_sync();
             tc::mbar_arrive(&S.a_ready);
@@ -412,13 +454,28 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
                     const uint32_t slot = bq % RING;
                     tc::mbar_wait(&S.b_full[slot], (bq / RING) & 1u);
                     tc::fence_after_sync();
-                    const uint32_t bh = b_base + slot * B_SLOT, bl = bh + uint32_t(HP) * 32u;
-                    const uint64_t dah = tc::make_desc_sw32(a_hi + uint32_t(j) * 4096u, 16, 256);
-                    if (!exact_a)
-                        tc::mma_bf16_ss(tmem_base, tc::make_desc_sw32(a_lo + uint32_t(j) * 4096u, 16, 256),
-                                        tc::make_desc_sw32(bh, 16, 256), idesc, j > 0);
-                    tc::mma_bf16_ss(tmem_base, dah, tc::make_desc_sw32(bl, 16, 256), idesc, !exact_a || j > 0);
-                    tc::mma_bf16_ss(tmem_base, dah, tc::make_desc_sw32(bh, 16, 256), idesc, true);
+                    const uint32_t bb = b_base + slot * B_SLOT;
+                    const uint64_t bh = tc::make_desc_sw32(bb, 16, 256), bl = tc::make_desc_sw32(bb + part_bytes, 16, 256),
+                                   br = tc::make_desc_sw32(bb + 2u * part_bytes, 16, 256);
+                    const uint64_t ah = tc::make_desc_sw32(a_hi + uint32_t(j) * 4096u, 16, 256),
+                                   al = tc::make_desc_sw32(a_lo + uint32_t(j) * 4096u, 16, 256);
+                    if (kind == ST_STEM) {
+                        tc::mma_bf16_ss(tmem_base, ah, br, idesc, j > 0);
+                        tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
+                        tc::mma_bf16_ss(tmem_base, ah, bh, idesc, true);
+                    } else if (kind == ST_FWD1) {
+                        tc::mma_bf16_ss(tmem_base, al, bl, idesc, j > 0);
+                        tc::mma_bf16_ss(tmem_base, al, bh, idesc, true);
+                        tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
+                        tc::mma_bf16_ss(tmem_base, ah, bh, idesc, true);
+                    } else if (kind == ST_FWD2) {
+                        tc::mma_bf16_ss(tmem_base, al, bh, idesc, true);
+                        tc::mma_bf16_ss(tmem_base, ah, br, idesc, true);
+                    } else {
+                        tc::mma_bf16_ss(tmem_base, al, bh, idesc, j > 0);
+                        tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
+                        tc::mma_bf16_ss(tmem_base, ah, bh, idesc, true);
+                    }
                     tc::mma_commit(&S.b_empty[slot]);
                 }
                 tc::mma_commit(&S.mma_done);
@@ -430,6 +487,15 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             tc::mbar_wait(&S.mma_done, stage & 1u);
             tc::fence_after_sync();
             ++stage;
+        };
+        // between the two forward phases: r = x - hi - lo of this thread's columns, x = the residual stream in TMEM
+        auto write_residual_terms = [&]() {
+#pragma unroll 1
+            for (int g = 0; g < c.ng; ++g) {
+                float x[8];
+                tc::tmem_ld8(c.tX + uint32_t(8 * g), x);
+                store_operand_r(S, c.row, c.c0 + 8 * g, x);
+            }
         };
 
         for (int t = 0; t < my_tiles; ++t) {
@@ -449,10 +515,12 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
                 }
             }
             float o[5];
-            run_stage(1, true);
+            run_stage(1, ST_STEM);
             fwd_epilogue<true>(S, p, c, 0, o);
             for (int l = 1; l <= L; ++l) {
-                run_stage(KB, false);
+                run_stage(KB, ST_FWD1);
+                write_residual_terms();
+                run_stage(KB, ST_FWD2);
                 fwd_epilogue<false>(S, p, c, l, o);
             }
             // ---- heads -> loss terms and their gradients (one thread per row)
@@ -490,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             // ---- backward-data
             bwd_epilogue(S, p, c, L, true);
             for (int l = L; l >= 1; --l) {
-                run_stage(KB, false);                  // D = dz_l W_l
+                run_stage(KB, ST_BWD);                 // D = dz_l W_l
                 bwd_epilogue(S, p, c, l - 1, false);
             }
         }
@@ -556,7 +624,7 @@ struct PackSrc {
 
 __global__ void update_pack_kernel(PackSrc s, int h, int HP, int L, float* __restrict__ pf, uint8_t* __restrict__ img) {
     const int KB = HP / 16;
-    const int nblk = 1 + 2 * L * KB;
+    const int nfwd = fwd_blocks(HP, L), nblk = nfwd + L * KB;
     const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     // ---- fp32 section
     if (idx < pf_floats(HP, L)) {
@@ -582,24 +650,27 @@ __global__ void update_pack_kernel(PackSrc s, int h, int HP, int L, float* __res
         }
         pf[i] = v;
     }
-    // ---- weight k-blocks: block 0 = stem exponent columns, then W_1..W_L, then W_L^T..W_1^T
+    // ---- weight k-blocks: block 0 = stem exponent columns, then W_1..W_L (hi | lo | r), then W_L^T..W_1^T (hi | lo)
     if (idx < int64_t(nblk) * HP * 16) {
         const int b = int(idx / (HP * 16)), rem = int(idx % (HP * 16)), n = rem / 16, kk = rem % 16;
         float v = 0.f;
         if (b == 0) {
             if (n < h) v = s.stem_w[n * 48 + 3 * kk];
-        } else if (b < 1 + L * KB) {
+        } else if (b < nfwd) {
             const int l = (b - 1) / KB, k = ((b - 1) % KB) * 16 + kk;
             if (n < h && k < h) v = s.w[l][size_t(n) * h + k];
         } else {
-            const int t = b - 1 - L * KB, l = L - 1 - t / KB, k = (t % KB) * 16 + kk;
+            const int t = b - nfwd, l = L - 1 - t / KB, k = (t % KB) * 16 + kk;
             if (n < h && k < h) v = s.w[l][size_t(k) * h + n];
         }
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        uint8_t* blk = img + size_t(b) * HP * 64;
+        const float e = v - __bfloat162float(hi);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(e);
+        const size_t part = size_t(HP) * 32;
+        uint8_t* blk = b < nfwd ? img + size_t(b) * 3 * part : img + size_t(nfwd) * 3 * part + size_t(b - nfwd) * 2 * part;
         *reinterpret_cast<__nv_bfloat16*>(blk + tc::sw32_offset(n, kk)) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blk + size_t(HP) * 32 + tc::sw32_offset(n, kk)) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(blk + part + tc::sw32_offset(n, kk)) = lo;
+        if (b < nfwd) *reinterpret_cast<__nv_bfloat16*>(blk + 2 * part + tc::sw32_offset(n, kk)) = __float2bfloat16_rn(e - __bfloat162float(lo));
     }
 }
 
@@ -638,7 +709,7 @@ int g2048_update_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, c
     }
     s.action_w = action_w; s.action_b = action_b; s.value_w = value_w; s.value_b = value_b;
     const int HP = padded(hidden);
-    const int64_t work = int64_t(blocks_per_tile(HP, layers, true)) * HP * 16;
+    const int64_t work = int64_t(fwd_blocks(HP, layers) + layers * (HP / 16)) * HP * 16;
     uint8_t* base = static_cast<uint8_t*>(packed);
     update_pack_kernel<<<unsigned((work + 255) / 256), 256, 0, cudaStream_t(stream)>>>(
         s, hidden, HP, layers, reinterpret_cast<float*>(base), base + img_offset_bytes(HP, layers));
