@@ -254,7 +254,8 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
  * One persistent tcgen05 kernel runs, per 128-sample tile and without leaving the SM, what
  * model_optimize_step does between `model(x)` and the weight gradients (train.py:491-556): the GameMLP
  * forward (game.py:1145-1220) from packed boards, the PPO-clip + critic + entropy terms (train.py:497-554)
- * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-bf16 ("x3", fp32-grade).
+ * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-bf16: three terms per
+ * operand in the forward (fp32-grade pre-activations, ~1e-6), two in the backward (~1e-5).
  * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], fp32 in the
  * tiled layout of g2048_x3_wgrad_tiled (ceil(n/128) * 128 * HP floats per l, HP = hidden rounded up to 16),
  * plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0), row-major; then (g2048_x3_wgrad_tiled)
