@@ -100,3 +100,48 @@ def test_urm_mirror_matches_reference_forward(golden):
     np.testing.assert_array_equal(logits.numpy(), g["logits"])
     np.testing.assert_array_equal(v.numpy(), g["value"])
     assert m.layers[0].mlp.inter == 120
+
+
+def test_optimize_epoch_order_is_the_dataloader_shuffle():
+    """g2048.optimize._epoch_order consumes torch's global RNG exactly like DataLoader(shuffle=True)
+    (train.py:438-443): same permutation, same RNG state afterwards, epoch after epoch."""
+    from torch.utils.data import DataLoader, Dataset
+
+    from g2048 import optimize
+
+    class D(Dataset):
+        def __len__(self):
+            return 1163
+
+        def __getitem__(self, i):
+            return i
+
+    torch.manual_seed(777)
+    want = [[int(i) for b in DataLoader(D(), batch_size=128, shuffle=True, collate_fn=lambda b: b) for i in b] for _ in range(3)]
+    tail_want = float(torch.rand(1))
+    torch.manual_seed(777)
+    got = [optimize._epoch_order(1163).tolist() for _ in range(3)]
+    assert got == want and float(torch.rand(1)) == tail_want
+
+
+def test_optimize_collation_matches_reference_fields(golden):
+    """episodes_to_batch = MyDataset + collate_fn (train.py:360-411) for the whole dataset: boards re-packed from
+    game_state, legal bits = complement of action_mask, float32 advantage / future_reward / log-probs."""
+    from g2048 import optimize
+    gr, ga = golden("rollout"), golden("advantage")
+    pos = np.arange(16)
+    moves = []
+    for k in range(64):
+        exps = (gr["board"][k] >> (4 * pos).astype(np.uint64)) & np.uint64(15)
+        x = np.stack([exps.astype(np.float32), (pos // 4 / 3).astype(np.float32), (pos % 4 / 3).astype(np.float32)], 1)
+        moves.append({"game_state": torch.from_numpy(x.reshape(48)), "selected_direction": int(gr["action"][k]),
+                      "action_mask": [not (int(gr["legal"][k]) >> d) & 1 for d in range(4)],
+                      "advantage": float(ga["readme__adv"][k]), "future_reward": float(ga["readme__g_norm"][k]),
+                      "policy_logprobs": [float(v) for v in gr["logp"][k]]})
+    b = optimize.episodes_to_batch([{"moves": moves[:40]}, {"moves": moves[40:]}], torch.device("cpu"))
+    np.testing.assert_array_equal(b["boards"].numpy().view(np.uint64), gr["board"][:64])
+    np.testing.assert_array_equal(b["actions"].numpy(), gr["action"][:64])
+    np.testing.assert_array_equal(b["legal"].numpy(), gr["legal"][:64])
+    np.testing.assert_array_equal(b["adv"].numpy(), ga["readme__adv"][:64].astype(np.float32))
+    np.testing.assert_array_equal(b["g_norm"].numpy(), ga["readme__g_norm"][:64].astype(np.float32))
+    np.testing.assert_array_equal(b["logp"].numpy(), gr["logp"][:64])
