@@ -334,6 +334,38 @@ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
     }
     return {c0, c1, c2, c3};
 }
+// The ten round keys of a launch are the same for every thread: kernels that are bound by the integer ALU pipe take
+// them precomputed as a by-value kernel parameter (constant bank operands of the XORs) instead of re-deriving them
+// per thread (20 integer adds per call).
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+__host__ __device__ inline PhiloxKeys philox_round_keys(uint64_t seed) {
+    PhiloxKeys rk;
+    uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk.k0[r] = k0;
+        rk.k1[r] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return rk;
+}
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ rk.k0[r];
+        c1 = l1;
+        c2 = h0 ^ c3 ^ rk.k1[r];
+        c3 = l0;
+    }
+    return {c0, c1, c2, c3};
+}
+__device__ __forceinline__ U4 env_draws(const PhiloxKeys& rk, uint64_t env_id, uint64_t ctr) {
+    return philox4x32_10(uint32_t(env_id), uint32_t(env_id >> 32), uint32_t(ctr), uint32_t(ctr >> 32), rk);
+}
 // counter = (env_id, ctr), key = seed: one call per env step
 __device__ __forceinline__ U4 env_draws(uint64_t seed, uint64_t env_id, uint64_t ctr) {
     return philox4x32_10(uint32_t(env_id), uint32_t(env_id >> 32), uint32_t(ctr), uint32_t(ctr >> 32),

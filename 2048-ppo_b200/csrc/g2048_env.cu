@@ -85,7 +85,7 @@ __device__ __forceinline__ void step_loop(const uint32_t* slut, const uint32_t* 
                                           const uint8_t* __restrict__ actions, uint64_t* __restrict__ out,
                                           int32_t* __restrict__ points, uint8_t* __restrict__ flags,
                                           uint64_t* __restrict__ shaping, int64_t n,
-                                          const uint32_t* __restrict__ replay, uint64_t seed, uint64_t env0,
+                                          const uint32_t* __restrict__ replay, const PhiloxKeys& seed, uint64_t env0,
                                           uint64_t ctr) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -115,7 +115,7 @@ template <bool SHAPING>
 __global__ void __launch_bounds__(STEP_THREADS, 1)
 step_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
                    int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
-                   uint64_t seed, uint64_t env0, uint64_t ctr) {
+                   const PhiloxKeys seed, uint64_t env0, uint64_t ctr) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
@@ -127,7 +127,7 @@ template <bool SHAPING>
 __global__ void __launch_bounds__(256)
 step_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
                    int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
-                   uint64_t seed, uint64_t env0, uint64_t ctr) {
+                   const PhiloxKeys seed, uint64_t env0, uint64_t ctr) {
     step_loop<SHAPING, false>(nullptr, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
 }
 
@@ -451,12 +451,12 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
         auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;
         G2048_CHECK_CUDA(ensure_smem(kern, LUT_SMEM_BYTES));
         kern<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,
-                                                              shaping, n, replay, seed, env0, ctr);
+                                                              shaping, n, replay, philox_round_keys(seed), env0, ctr);
         G2048_CHECK_LAUNCH("step_kernel_staged");
     } else {
         auto kern = shaping ? step_kernel_direct<true> : step_kernel_direct<false>;
         kern<<<unsigned((n + 255) / 256), 256, 0, st>>>(lut, boards_in, actions, boards_out, points, flags, shaping, n,
-                                                        replay, seed, env0, ctr);
+                                                        replay, philox_round_keys(seed), env0, ctr);
         G2048_CHECK_LAUNCH("step_kernel_direct");
     }
     return G2048_OK;
