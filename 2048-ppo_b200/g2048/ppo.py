@@ -121,6 +121,29 @@ def ppo_loss(logits, value, old_logp, actions, legal, adv, g_norm, *, flags=None
                           critic_strength, entropy_strength, n_total)
 
 
+def sample_augmentation(valid: torch.Tensor, upsample_ratio: float, generator: torch.Generator | None = None):
+    """The sampling policy of the reference's symmetry augmentation (train.py:776-863) on the device:
+    int(N * ratio) of the N recorded steps are drawn without replacement; each drawn step independently yields a
+    mirrored copy with probability 1/2 (axis uniform) and a rotated copy with probability 1/2 (90/180/270 uniform).
+    `valid`: bool [n] mask of recorded steps.  Returns (source indices int64 [m], ops uint8 [m]) for env.augment.
+    (The reference draws from Python's `random`; the distribution is the same, the draws are torch's.)"""
+    from .env import MIRROR_H, ROT90
+    idx = torch.nonzero(valid.reshape(-1), as_tuple=False).reshape(-1)
+    n = idx.numel()
+    k = min(int(n * upsample_ratio), n)
+    dev = valid.device
+    if k <= 0:
+        return idx[:0], torch.empty(0, dtype=torch.uint8, device=dev)
+    pick = idx[torch.randperm(n, device=dev, generator=generator)[:k]]
+    u = torch.rand((4, k), device=dev, generator=generator)
+    mirror, rotate = u[0] < 0.5, u[2] < 0.5
+    m_op = (MIRROR_H + (u[1] >= 0.5).to(torch.uint8)).to(torch.uint8)                       # horizontal | vertical
+    r_op = (ROT90 + torch.clamp((u[3] * 3).to(torch.uint8), max=2)).to(torch.uint8)         # 90 | 180 | 270
+    src = torch.cat([pick[mirror], pick[rotate]])
+    ops = torch.cat([m_op[mirror], r_op[rotate]])
+    return src, ops
+
+
 def loss_stats(stats: torch.Tensor, critic_strength: float, entropy_strength: float) -> dict:
     """The scalars model_optimize_step logs (train.py:528,541,546,554,618)."""
     s1, s2, s3, n = (float(x) for x in stats.tolist())

@@ -42,6 +42,8 @@ class TrainConfig:
     seed: int = 2048
     zero_heads: bool = True        # train.py:1559-1567
     dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
+    upsample_ratio: float = 0.0    # symmetry augmentation (train.py:774-881; the README recipe uses 0.25): that share of the
+                                   # recorded steps is drawn and mirrored / rotated copies join the update batch
     rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
     update_matmul: str = "fused"      # the update's forward/backward: "fused" = one tcgen05 kernel for forward + loss + backward-data
                                       # and x3 tensor-core weight gradients (g2048.update; split-bf16, ~1e-5), "x3" = torch autograd graph
@@ -120,6 +122,9 @@ class Trainer:
         self.buf = rollout.RolloutBuffers.allocate(cfg.horizon, self.B, self.device)
         self.times = StepTimes()
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        self._aug_gen = torch.Generator(device=self.device)
+        self._aug_gen.manual_seed(cfg.seed * 1000003 + self.rank)
+        self.n_update_samples = 0
 
     # -- phases ---------------------------------------------------------------------------
     def collect(self) -> rollout.RolloutBuffers:
@@ -143,6 +148,16 @@ class Trainer:
         flat = lambda t, *s: t.reshape(n_local, *s)
         boards, actions, legal, flags = flat(buf.boards), flat(buf.actions), flat(buf.legal), flat(buf.flags)
         logp, a, g = flat(buf.logp, 4), flat(adv["adv"]), flat(adv["g_norm"])
+        if c.upsample_ratio > 0:
+            # augmented copies keep the ORIGINAL advantage / return / value of their source step (train.py:829,858) and
+            # are appended like the reference's "augmented" pseudo-episode (train.py:1710-1718)
+            src, ops = ppo.sample_augmentation((flags & 0x80) != 0, c.upsample_ratio, self._aug_gen)
+            if src.numel() > 0:
+                aug = env.augment(boards[src], boards[src], actions[src], legal[src], logp[src], ops)
+                boards, actions, legal = torch.cat([boards, aug["before"]]), torch.cat([actions, aug["action"]]), torch.cat([legal, aug["legal"]])
+                logp, a, g, flags = torch.cat([logp, aug["logp"]]), torch.cat([a, a[src]]), torch.cat([g, g[src]]), torch.cat([flags, flags[src]])
+                n_local = boards.numel()
+        self.n_update_samples = n_local
         counts = torch.tensor([float(n_local)], dtype=torch.float64, device=self.device)
         n_global = int(dp.allreduce_stats(counts).item())
         self.model.train()

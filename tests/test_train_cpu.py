@@ -145,3 +145,25 @@ def test_optimize_collation_matches_reference_fields(golden):
     np.testing.assert_array_equal(b["adv"].numpy(), ga["readme__adv"][:64].astype(np.float32))
     np.testing.assert_array_equal(b["g_norm"].numpy(), ga["readme__g_norm"][:64].astype(np.float32))
     np.testing.assert_array_equal(b["logp"].numpy(), gr["logp"][:64])
+
+
+def test_augmentation_sampling_policy():
+    """ppo.sample_augmentation follows train.py:776-863: int(N * ratio) distinct recorded steps; each yields a
+    mirror copy w.p. 1/2 (two axes, uniform) and a rotation copy w.p. 1/2 (three angles, uniform)."""
+    from g2048 import ppo
+    from g2048.env import MIRROR_H, MIRROR_V, ROT90, ROT180, ROT270
+    n = 200000
+    valid = torch.ones(n, dtype=torch.bool)
+    valid[::7] = False
+    gen = torch.Generator().manual_seed(5)
+    src, ops = ppo.sample_augmentation(valid, 0.25, gen)
+    k = int(int(valid.sum()) * 0.25)
+    assert valid[src].all() and ops.dtype == torch.uint8 and src.numel() == ops.numel()
+    is_m = ops <= MIRROR_V
+    for part in (src[is_m], src[~is_m]):                       # at most one mirror and one rotation per drawn step
+        assert part.unique().numel() == part.numel()
+    assert torch.cat([src[is_m], src[~is_m]]).unique().numel() <= k
+    frac = lambda c: float((ops == c).sum()) / k
+    for c, want in ((MIRROR_H, 0.25), (MIRROR_V, 0.25), (ROT90, 1 / 6), (ROT180, 1 / 6), (ROT270, 1 / 6)):
+        assert abs(frac(c) - want) < 0.01, (c, frac(c))
+    assert ppo.sample_augmentation(valid, 0.0, gen)[0].numel() == 0

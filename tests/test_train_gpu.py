@@ -171,3 +171,19 @@ def test_ppo_loss_and_grads_match_reference_optimize_step(golden):
             ref = gl[name + "__grad__" + k.replace(".", "__")]
             np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=1e-3, atol=1e-5 * max(1.0, np.abs(ref).max()),
                                        err_msg=k)
+
+
+def test_trainer_with_symmetry_augmentation():
+    """README recipe (--upsample-ratio 0.25): the update batch grows by the mirrored / rotated copies and the step
+    still produces finite statistics through the fused update kernel."""
+    from g2048 import trainer as tr
+    cfg = tr.TrainConfig(hidden_dim=64, num_layers=2, envs=512, horizon=16, zero_heads=False, upsample_ratio=0.25)
+    t = tr.Trainer(cfg, torch.device("cuda:0"))
+    s = t.train_step()
+    n = 512 * 16
+    assert n * 1.20 < t.n_update_samples < n * 1.30              # + 0.25 * (1/2 + 1/2) on average
+    assert all(np.isfinite(s[k]) for k in ("loss", "policy_loss", "value_loss", "entropy", "grad_norm"))
+    cfg0 = tr.TrainConfig(hidden_dim=64, num_layers=2, envs=512, horizon=16, zero_heads=False)
+    t0 = tr.Trainer(cfg0, torch.device("cuda:0"))
+    t0.train_step()
+    assert t0.n_update_samples == n
