@@ -86,11 +86,15 @@ __device__ __forceinline__ void step_loop(const uint32_t* slut, const uint32_t* 
                                           int32_t* __restrict__ points, uint8_t* __restrict__ flags,
                                           uint64_t* __restrict__ shaping, int64_t n,
                                           const uint32_t* __restrict__ replay, const PhiloxKeys& seed, uint64_t env0,
-                                          uint64_t ctr) {
+                                          uint64_t ctr, uint64_t next_board, uint32_t next_action) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Board b = make_board(__ldg(in + i));
-        uint32_t a = __ldg(actions + i) & 3u;
+        Board b = make_board(next_board);
+        uint32_t a = next_action & 3u;
+        if (i + stride < n) {                         // next transition's inputs in flight while this one is computed
+            next_board = __ldg(in + i + stride);
+            next_action = __ldg(actions + i + stride);
+        }
         uint32_t u0, u1;
         if (replay) {
             uint2 r = __ldg(reinterpret_cast<const uint2*>(replay) + i);
@@ -119,8 +123,11 @@ step_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* in, const 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
+    const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t b0 = i0 < n ? __ldg(in + i0) : 0ull;                   // issued before the table staging wait
+    const uint32_t a0 = i0 < n ? __ldg(actions + i0) : 0u;
     stage_lut(slut, glut, &bar);
-    step_loop<SHAPING, true>(slut, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
+    step_loop<SHAPING, true>(slut, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr, b0, a0);
 }
 
 template <bool SHAPING>
@@ -128,7 +135,9 @@ __global__ void __launch_bounds__(256)
 step_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
                    int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
                    const PhiloxKeys seed, uint64_t env0, uint64_t ctr) {
-    step_loop<SHAPING, false>(nullptr, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr);
+    const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    step_loop<SHAPING, false>(nullptr, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr,
+                              i0 < n ? __ldg(in + i0) : 0ull, i0 < n ? uint32_t(__ldg(actions + i0)) : 0u);
 }
 
 struct FourLines {
@@ -149,10 +158,12 @@ template <bool STAGED>
 __device__ __forceinline__ void expand4_loop(const uint32_t* slut, const uint32_t* __restrict__ glut,
                                              const uint64_t* __restrict__ boards,
                                              uint64_t* __restrict__ succ, int32_t* __restrict__ points,
-                                             uint8_t* __restrict__ legal, uint8_t* __restrict__ max_tile, int64_t n) {
+                                             uint8_t* __restrict__ legal, uint8_t* __restrict__ max_tile, int64_t n,
+                                             uint64_t prefetched) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Board b = make_board(__ldg(boards + i));
+        Board b = make_board(prefetched);
+        if (i + stride < n) prefetched = __ldg(boards + i + stride);     // next board in flight while this one is expanded
         FourLines f;
         int p[4], mt[4];
         if (STAGED && !has_big_tile(b)) {
@@ -194,14 +205,17 @@ expand4_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* boards,
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
+    const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t first = i0 < n ? __ldg(boards + i0) : 0ull;            // issued before the table staging wait
     stage_lut<uint32_t(MOVE_SMEM_BYTES)>(slut, glut + MOVE_LUT_OFFSET, &bar);
-    expand4_loop<true>(slut, glut, boards, succ, points, legal, max_tile, n);
+    expand4_loop<true>(slut, glut, boards, succ, points, legal, max_tile, n, first);
 }
 
 __global__ void __launch_bounds__(256)
 expand4_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* boards, uint64_t* succ, int32_t* points,
                       uint8_t* legal, uint8_t* max_tile, int64_t n) {
-    expand4_loop<false>(nullptr, glut, boards, succ, points, legal, max_tile, n);
+    const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    expand4_loop<false>(nullptr, glut, boards, succ, points, legal, max_tile, n, i0 < n ? __ldg(boards + i0) : 0ull);
 }
 
 __global__ void __launch_bounds__(256)
