@@ -20,7 +20,7 @@
 // stays resident in shared memory for the whole launch and two accumulators alternate so the
 // epilogue of tile i overlaps the MMAs of tile i+1.  The wgrad kernel uses the SAME operand bytes with
 // MN-major descriptors (rows = samples = the MMA's K index), accumulates a CTA's whole sample range in
-// tensor memory (flushed to an fp32 partial every 2048 samples to bound the accumulation error) and a
+// tensor memory (flushed to an fp32 partial every 8192 samples to bound the accumulation error) and a
 // second kernel adds the per-CTA partials in a fixed order (deterministic).
 #include "g2048_host.h"
 #include "g2048_tc.cuh"
@@ -216,7 +216,7 @@ constexpr int W_ROWS = 32;                        // samples per stage
 constexpr uint32_t W_BLOCK = W_ROWS * 32;         // one 16-feature block of a stage: 1 KiB
 constexpr uint32_t W_PART = MAXB * W_BLOCK;       // one operand part (13 blocks)
 constexpr uint32_t W_STAGE = 4 * W_PART;          // dY hi | dY lo | X hi | X lo
-constexpr int W_FLUSH = 64;                       // stages between accumulator flushes (2048 samples)
+constexpr int W_FLUSH = 256;                      // stages between accumulator flushes (8192 samples)
 constexpr int W_UNITS = 2 * MAXB * (W_ROWS / 8);  // (matrix, block, 8-row group) load units per stage = 104
 
 struct WgradBars {
@@ -327,7 +327,9 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
     } else if (lane == 0) {
         // ---------------- MMA issuer
         const uint32_t idesc = tc::make_idesc_bf16_major(128, KPB * 16, true, true);
-        const uint32_t w_addr = tc::smem_addr(sW);
+        // one descriptor for the ring base; every operand of every MMA is that plus a byte offset (>> 4) in the
+        // address field: the issuing thread's descriptor arithmetic is one 64-bit add per operand
+        const uint64_t d0 = tc::make_desc_sw32(tc::smem_addr(sW), W_BLOCK, 256);
         const int nhalf = N > 128 ? 2 : 1;
         bool acc = false;
         int since = 0;
@@ -336,15 +338,16 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
             const int slot = q % W_STAGES;
             tc::mbar_wait(&S.full[slot], uint32_t(q / W_STAGES) & 1u);
             tc::fence_after_sync();
-            const uint32_t sb = w_addr + uint32_t(slot) * W_STAGE;
+            const uint64_t ds = d0 + uint64_t((uint32_t(slot) * W_STAGE) >> 4);
+#pragma unroll
             for (int ks = 0; ks < W_ROWS / 16; ++ks) {
-                const uint32_t b_hi = sb + 2u * W_PART + uint32_t(ks) * 512u, b_lo = b_hi + W_PART;
+                const uint64_t b_hi = ds + uint64_t((2u * W_PART + uint32_t(ks) * 512u) >> 4), b_lo = b_hi + uint64_t(W_PART >> 4);
                 for (int half = 0; half < nhalf; ++half) {
-                    const uint32_t a_hi = sb + uint32_t(half) * 8u * W_BLOCK + uint32_t(ks) * 512u, a_lo = a_hi + W_PART;
+                    const uint64_t a_hi = ds + uint64_t((uint32_t(half) * 8u * W_BLOCK + uint32_t(ks) * 512u) >> 4), a_lo = a_hi + uint64_t(W_PART >> 4);
                     const uint32_t d = tmem_base + uint32_t(half * 256);
-                    tc::mma_bf16_ss(d, tc::make_desc_sw32(a_lo, W_BLOCK, 256), tc::make_desc_sw32(b_hi, W_BLOCK, 256), idesc, acc || ks > 0);
-                    tc::mma_bf16_ss(d, tc::make_desc_sw32(a_hi, W_BLOCK, 256), tc::make_desc_sw32(b_lo, W_BLOCK, 256), idesc, true);
-                    tc::mma_bf16_ss(d, tc::make_desc_sw32(a_hi, W_BLOCK, 256), tc::make_desc_sw32(b_hi, W_BLOCK, 256), idesc, true);
+                    tc::mma_bf16_ss(d, a_lo, b_hi, idesc, acc || ks > 0);
+                    tc::mma_bf16_ss(d, a_hi, b_lo, idesc, true);
+                    tc::mma_bf16_ss(d, a_hi, b_hi, idesc, true);
                 }
             }
             acc = true;

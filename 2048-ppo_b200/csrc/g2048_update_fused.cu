@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
         };
         if (producer) refill();
         const uint32_t idesc = tc::make_idesc_bf16_major(128, HP, false, false);
-        const uint32_t a_hi = tc::smem_addr(S.A[0]), a_lo = tc::smem_addr(S.A[1]), b_base = tc::smem_addr(S.B[0]);
+        const uint64_t dA0 = tc::make_desc_sw32(tc::smem_addr(S.A[0]), 16, 256), dA1 = tc::make_desc_sw32(tc::smem_addr(S.A[1]), 16, 256),
+                       dB0 = tc::make_desc_sw32(tc::smem_addr(S.B[0]), 16, 256);
         uint32_t stage = 0, bq = 0;                 // running MMA-stage and weight-block counters (issuer)
         double lacc[4] = {0.0, 0.0, 0.0, 0.0};
         float hb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -454,11 +455,10 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
                     const uint32_t slot = bq % RING;
                     tc::mbar_wait(&S.b_full[slot], (bq / RING) & 1u);
                     tc::fence_after_sync();
-                    const uint32_t bb = b_base + slot * B_SLOT;
-                    const uint64_t bh = tc::make_desc_sw32(bb, 16, 256), bl = tc::make_desc_sw32(bb + part_bytes, 16, 256),
-                                   br = tc::make_desc_sw32(bb + 2u * part_bytes, 16, 256);
-                    const uint64_t ah = tc::make_desc_sw32(a_hi + uint32_t(j) * 4096u, 16, 256),
-                                   al = tc::make_desc_sw32(a_lo + uint32_t(j) * 4096u, 16, 256);
+                    // descriptors = one base per buffer + a byte offset (>> 4) in the address field
+                    const uint64_t bh = dB0 + uint64_t((slot * B_SLOT) >> 4), bl = bh + uint64_t(part_bytes >> 4),
+                                   br = bh + uint64_t((2u * part_bytes) >> 4);
+                    const uint64_t ah = dA0 + uint64_t(uint32_t(j) * (4096u >> 4)), al = dA1 + uint64_t(uint32_t(j) * (4096u >> 4));
                     if (kind == ST_STEM) {
                         tc::mma_bf16_ss(tmem_base, ah, br, idesc, j > 0);
                         tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
