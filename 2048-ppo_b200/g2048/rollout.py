@@ -254,6 +254,45 @@ def play_games_batched(model, num_games: int, max_steps: int | None = None, devi
     return _episode_dicts(bufs, boards, dev)
 
 
+@torch.no_grad()
+def evaluate(model, eval_games: int = 100, max_steps: int | None = None, device=None, *, seed: int = 0) -> dict:
+    """The reference's periodic evaluation (train.py:1840-1875): play `eval_games` seeded games to the end with the
+    sampled policy and report the metrics it logs ("eval/max_score", "eval/avg_score", "eval/median_score",
+    "eval/pct_512|1024|2048").  Game i uses the Philox stream (seed, env id i) where the reference seeds Python's
+    `random` with i.  Everything stays on the device; no episode dictionaries are built."""
+    if device is None or torch.device(device).type != "cuda":
+        raise RuntimeError("evaluate runs on a CUDA device only (no CPU fallback)")
+    dev = env.init(device)
+    policy = pack_policy(model, dev)
+    boards = env.reset(eval_games, device=dev, seed=seed, env0=0, ctr=0)
+    alive = torch.ones(eval_games, dtype=torch.uint8, device=dev)
+    scores = torch.zeros(eval_games, dtype=torch.int64, device=dev)
+    played = 0
+    limit = max_steps if max_steps and max_steps > 0 else None
+    while True:
+        T = _CHUNK if limit is None else min(_CHUNK, limit - played)
+        if T <= 0:
+            break
+        buf = rollout(policy, boards, T, seed=seed, env0=0, ctr0=1 + played, auto_reset=False, alive=alive)
+        scores += (buf.points.long() * ((buf.flags & 0x80) != 0)).sum(0)
+        played += T
+        if not bool(alive.any()):
+            break
+    cells = (boards.unsqueeze(1) >> (4 * torch.arange(16, device=dev))) & 15          # final boards -> exponents
+    max_tile = torch.where(cells.max(1).values > 0, 1 << cells.max(1).values, torch.zeros_like(scores))
+    sc = scores.cpu().tolist()
+    pct = lambda t: float((max_tile >= t).sum()) / eval_games * 100
+    return {"eval/max_score": max(sc), "eval/avg_score": sum(sc) / len(sc), "eval/median_score": sorted(sc)[len(sc) // 2],
+            "eval/pct_512": pct(512), "eval/pct_1024": pct(1024), "eval/pct_2048": pct(2048), "scores": sc}
+
+
+def save_best_checkpoint(path, model, eval_avg_score: float, train_step: int) -> None:
+    """best_model.pt in the reference's format (train.py:1887-1897): loads with the reference's own code."""
+    cfg = model.config.model_dump() if hasattr(model.config, "model_dump") else dict(model.config)
+    torch.save({"model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "config": cfg,
+                "eval_avg_score": eval_avg_score, "train_step": train_step}, path)
+
+
 def smoke(dev) -> None:
     """Tiny fused rollouts on `dev` (fp32 FFMA, bf16 tcgen05, GameURM), checked against the oracle env
     and the torch policy."""

@@ -303,3 +303,24 @@ def test_full_size_rollout_properties(precision):
             fresh = nxt[done]
             tiles = sum(((fresh >> (4 * k)) & 15) != 0 for k in range(16))
             assert bool((tiles == 2).all())
+
+
+def test_evaluate_reports_the_reference_metrics(golden, tmp_path):
+    """rollout.evaluate = the eval block of train.py:1840-1875 without the episode dictionaries: its scores are the
+    total_points play_games_batched reports for the same seeded games, and the checkpoint round-trips."""
+    import torch
+    from g2048 import rollout
+    from test_train_cpu import load_policy
+    m, _ = load_policy(golden)
+    m = m.cuda().eval()
+    ev = rollout.evaluate(m, eval_games=64, device="cuda", seed=3)
+    assert set(ev) >= {"eval/max_score", "eval/avg_score", "eval/median_score", "eval/pct_512", "eval/pct_1024", "eval/pct_2048"}
+    assert ev["eval/max_score"] >= ev["eval/median_score"] > 0 and ev["eval/avg_score"] > 500      # the shipped checkpoint plays
+    assert 0.0 <= ev["eval/pct_2048"] <= ev["eval/pct_1024"] <= ev["eval/pct_512"] <= 100.0
+    again = rollout.evaluate(m, eval_games=64, device="cuda", seed=3)
+    assert again["scores"] == ev["scores"]                                                        # seeded => reproducible
+    path = tmp_path / "best_model.pt"
+    rollout.save_best_checkpoint(path, m, ev["eval/avg_score"], 7)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"model_state_dict", "config", "eval_avg_score", "train_step"} and ck["train_step"] == 7
+    assert all(torch.equal(ck["model_state_dict"][k], v.cpu()) for k, v in m.state_dict().items())
