@@ -79,7 +79,16 @@ constexpr int LUT_SMEM_BYTES = LUT_SMEM_ROWS * 4;
 constexpr int MOVE_LUT_OFFSET = LUT_ROWS;            // in entries
 constexpr int MOVE_SMEM_ROWS = 0xC000;
 constexpr int MOVE_SMEM_BYTES = MOVE_SMEM_ROWS * 4;
-constexpr int LUT_BYTES = 2 * LUT_ROWS * 4;
+constexpr int ROW_TABLES_BYTES = 2 * LUT_ROWS * 4;
+// A third region follows: the dense step tables of the fused step kernel (see "dense step tables" below).
+constexpr int DENSE_M_STRIDE = 145;                                 // 12*12 + 1: spreads cells 2,3 over the banks
+constexpr int DENSE_M_ROWS = 143 * DENSE_M_STRIDE + 144;            // 20 879
+constexpr int DENSE_M_BYTES = ((DENSE_M_ROWS * 8 + 15) / 16) * 16;  // 167 040
+constexpr int DENSE_S_ROWS = 13 * 13 * 13 * 13;                     // 28 561
+constexpr int DENSE_S_BYTES = ((DENSE_S_ROWS * 2 + 15) / 16) * 16;  // 57 136
+constexpr int DENSE_BYTES = DENSE_M_BYTES + DENSE_S_BYTES;          // 224 176 (staged whole)
+constexpr int DENSE_OFFSET_BYTES = ROW_TABLES_BYTES;
+constexpr int LUT_BYTES = ROW_TABLES_BYTES + DENSE_BYTES;
 
 __host__ __device__ inline uint32_t lut_entry_for_row(uint32_t row) {
     int c[4] = {int(row & 15), int((row >> 4) & 15), int((row >> 8) & 15), int((row >> 12) & 15)};
@@ -143,6 +152,64 @@ struct LutGlobal {
     const uint32_t* g;
     __device__ __forceinline__ uint32_t operator()(uint32_t row) const { return __ldg(g + row); }
 };
+
+// ------------------------------------------------------------------ dense step tables
+// The fused step kernel (step + all shaping terms) is bound by the integer ALU pipe, not by HBM, so
+// it trades bit arithmetic for table lookups.  Two tables, staged whole into shared memory (219 KiB):
+//
+//  M (u64, dense index of a row with every cell <= 11: digits c0 + 12 c1 + 145 (c2 + 12 c3)),
+//    read for the 4 lines along the move axis (canonical frame):
+//      lo [15:0]  left-move result      [27:16] merge points / 4      [31:28] largest exponent created
+//      hi [3:0]   ge   [7:4]   le   [14:8]  |smoothness| of the row itself          (before the move)
+//         [18:15] ge   [22:19] le   [30:23] |smoothness| of the result row          (after the move)
+//  S (u16, dense base-13 index of a row with every cell <= 12), read for the 4 lines across the move
+//    axis of the board before the move and of the board after it:
+//      [3:0] ge   [7:4] le   [15:8] |smoothness|
+//
+// Per-line values are ge, le <= 3 and |smoothness| <= 33, so the SUM of four entries never carries
+// from one field into the next: a board's pair counts and smoothness are one add chain on whole
+// entries.  ge / le as in the row table (game.py:714-719), |smoothness| = sum of |a-b| over adjacent
+// cells that are both non-zero (game.py:339-357).
+__host__ __device__ inline uint32_t line_stats(uint32_t row) {
+    int c[4] = {int(row & 15), int((row >> 4) & 15), int((row >> 8) & 15), int((row >> 12) & 15)};
+    uint32_t ge = 0, le = 0, sm = 0;
+    for (int i = 0; i < 3; ++i)
+        if (c[i] && c[i + 1]) {
+            ge += c[i] >= c[i + 1];
+            le += c[i] <= c[i + 1];
+            sm += uint32_t(c[i] > c[i + 1] ? c[i] - c[i + 1] : c[i + 1] - c[i]);
+        }
+    return ge | le << 4 | sm << 8;
+}
+// dense M slot -> 16-bit row (0xFFFFFFFF for the unused slots of the stride padding)
+__host__ __device__ inline uint32_t dense_m_row(uint32_t slot) {
+    uint32_t lo = slot % uint32_t(DENSE_M_STRIDE), hi = slot / uint32_t(DENSE_M_STRIDE);
+    if (lo >= 144u || hi >= 144u) return 0xFFFFFFFFu;
+    return (lo % 12u) | (lo / 12u) << 4 | (hi % 12u) << 8 | (hi / 12u) << 12;
+}
+__host__ __device__ inline uint32_t dense_s_row(uint32_t slot) {
+    return (slot % 13u) | ((slot / 13u) % 13u) << 4 | ((slot / 169u) % 13u) << 8 | (slot / 2197u) << 12;
+}
+__host__ __device__ inline uint64_t dense_m_entry(uint32_t slot) {
+    const uint32_t row = dense_m_row(slot);
+    if (row == 0xFFFFFFFFu) return 0ull;
+    const uint32_t mv = move_entry_for_row(row);              // result | points/4 | created (exact: cells <= 11)
+    const uint32_t hi = line_stats(row) | line_stats(mv & 0xFFFFu) << 15;
+    return uint64_t(mv) | uint64_t(hi) << 32;
+}
+__host__ __device__ inline uint32_t dense_s_entry(uint32_t slot) { return line_stats(dense_s_row(slot)); }
+
+// The two rows of a board half -> their two dense indices, in the two 16-bit lanes of the result.
+// Stage 1 turns every byte lo + 16 hi into lo + BASE hi (no borrow between bytes: the bytes only
+// shrink), stage 2 every 16-bit lane d0 + 256 d1 into d0 + STRIDE d1.
+template <uint32_t BASE, uint32_t STRIDE>
+__device__ __forceinline__ uint32_t dense2(uint32_t x) {
+    const uint32_t t = (x >> 4) & 0x0F0F0F0Fu;
+    const uint32_t d = x - (16u - BASE) * t;
+    const uint32_t h = (d >> 8) & 0x00FF00FFu;
+    return d - (256u - STRIDE) * h;
+}
+
 
 // ------------------------------------------------------------------ board ops
 struct Board {
@@ -470,6 +537,123 @@ __device__ __forceinline__ StepOut env_step(Board b, uint32_t action, uint32_t u
     o.points = valid ? points : 0;
     uint32_t lm = legal_mask(o.board);             // game.py:1006 / 963
     o.flags = lm | (lm == 0u ? FLAG_DONE : 0u) | (valid ? 0u : FLAG_INVALID) | ((valid && ovf) ? FLAG_OVERFLOW : 0u);
+    return o;
+}
+
+// ------------------------------------------------------------------ step on the dense tables
+// Exact non-zero-nibble flags at bit 3 of every nibble, three instructions.
+__device__ __forceinline__ uint32_t nz_flags8(uint32_t x) { return (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
+__device__ __forceinline__ uint32_t z_flags8(uint32_t x) { return ~(((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
+
+// largest nibble of the board: a 16-bit unsigned max is decided by the top nibble of each lane, so
+// four shifted copies put every cell of a row there once (what lies below does not matter).
+__device__ __forceinline__ uint32_t max_nibble(Board b) {
+    uint32_t m0 = __vmaxu2(b.lo, b.hi);
+    uint32_t m1 = __vmaxu2(b.lo << 4, b.hi << 4);
+    uint32_t m2 = __vmaxu2(b.lo << 8, b.hi << 8);
+    uint32_t m3 = __vmaxu2(b.lo << 12, b.hi << 12);
+    uint32_t m = __vmaxu2(__vmaxu2(m0, m1), __vmaxu2(m2, m3));
+    return max(m >> 28, (m >> 12) & 15u);
+}
+
+// corner rules for a board whose largest exponent `mx` is known:
+// mono doubling <=> the FIRST max cell in row-major order is a corner (game.py:755-758),
+// corner bonus sign <=> ANY max cell is a corner (game.py:386-399)
+__device__ __forceinline__ void corner_rules(Board b, uint32_t mx, bool& first_corner, bool& in_corner) {
+    const uint32_t rep = mx * 0x11111111u;
+    const uint32_t ql = z_flags8(b.lo ^ rep), qh = z_flags8(b.hi ^ rep);     // cells equal to the max (bit 3 flags)
+    first_corner = ql ? ((ql & (0u - ql)) & 0x00008008u) != 0u : ((qh & (0u - qh)) & 0x80080000u) != 0u;
+    in_corner = ((ql & 0x00008008u) | (qh & 0x80080000u)) != 0u;
+}
+
+// rev_rows(x) when s4 == 4 and sel == 0x2301, x itself when s4 == 0 and sel == 0x3210: the reversal as straight-line
+// code (random actions would make a branch diverge in every warp)
+__device__ __forceinline__ uint32_t rev_rows_if(uint32_t x, uint32_t s4, uint32_t sel) {
+    const uint32_t y = ((x << s4) & 0xF0F0F0F0u) | ((x >> s4) & 0x0F0F0F0Fu);
+    return __byte_perm(y, 0u, sel);
+}
+
+// shared-space loads with the table base as the instruction's immediate offset
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(addr));
+    return v;
+}
+struct DenseSmem {
+    uint32_t m, s;         // shared-space byte addresses of the two tables
+    __device__ __forceinline__ uint2 M(uint32_t byte_off) const { return lds_u64(m + byte_off); }
+    __device__ __forceinline__ uint32_t S(uint32_t byte_off) const { return lds_u16(s + byte_off); }
+};
+// the four S entries of a board's rows, summed.  The byte offsets (2 x index <= 57 120) fit the 16-bit lanes.
+__device__ __forceinline__ uint32_t s_sum(Board x, const DenseSmem& tab) {
+    const uint32_t a = dense2<13, 169>(x.lo), b = dense2<13, 169>(x.hi);
+    const uint32_t a2 = a + a, b2 = b + b;
+    return tab.S(a2 & 0xFFFFu) + tab.S(a2 >> 16) + tab.S(b2 & 0xFFFFu) + tab.S(b2 >> 16);
+}
+
+// env_step<true> for a board with every cell <= 11 (so every line before the move indexes M / S and
+// every line after it indexes S).  12 table reads: the 4 lines along the move axis (M: move result,
+// points, created tile, and the per-line potentials of the line before AND after the move), the 4
+// lines across it before the move (S) and after it (S).  Same results as env_step, bit for bit.
+__device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t action, uint32_t u0, uint32_t u1, const DenseSmem& tab) {
+    StepOut o;
+    const Board bt = transpose(b);
+    const bool horiz = (action & 2u) != 0u;
+    const uint32_t s4 = (action & 1u) << 2, sel = (action & 1u) ? 0x2301u : 0x3210u;
+    const Board along = horiz ? b : bt, cross = horiz ? bt : b;
+    const Board canon = {rev_rows_if(along.lo, s4, sel), rev_rows_if(along.hi, s4, sel)};
+    const uint32_t ia = dense2<12, DENSE_M_STRIDE>(canon.lo), ib = dense2<12, DENSE_M_STRIDE>(canon.hi);
+    const uint2 m0 = tab.M((ia << 3) & 0x7FFF8u), m1 = tab.M((ia >> 13) & 0x7FFF8u);
+    const uint2 m2 = tab.M((ib << 3) & 0x7FFF8u), m3 = tab.M((ib >> 13) & 0x7FFF8u);
+    const uint32_t cb = s_sum(cross, tab);
+    const Board moved_c = {__byte_perm(m0.x, m1.x, 0x5410), __byte_perm(m2.x, m3.x, 0x5410)};
+    const bool valid = !same(moved_c, canon);                      // game.py:959
+    // merge points and the largest exponent created (move table layout)
+    const uint32_t pt = (__byte_perm(m0.x, m1.x, 0x7632) & 0x0FFF0FFFu) + (__byte_perm(m2.x, m3.x, 0x7632) & 0x0FFF0FFFu);
+    const uint32_t points = ((pt & 0xFFFFu) + (pt >> 16)) << 2;
+    const uint32_t created = max(max(m0.x, m1.x), max(m2.x, m3.x)) >> 28;
+    // back to the real frame; the transpose doubles as the source of the cross lines after the move
+    const Board un = {rev_rows_if(moved_c.lo, s4, sel), rev_rows_if(moved_c.hi, s4, sel)};
+    const Board unt = transpose(un);
+    const Board moved = horiz ? un : unt;
+    const uint32_t ca = s_sum(unt, tab);
+    const uint32_t al = m0.y + m1.y + m2.y + m3.y;                 // along the axis: before [14:0], after [30:15]
+    const uint32_t aa = al >> 15;
+    const uint32_t pairs_b = max(al & 15u, (al >> 4) & 15u) + max(cb & 15u, (cb >> 4) & 15u);
+    const uint32_t pairs_a = max(aa & 15u, (aa >> 4) & 15u) + max(ca & 15u, (ca >> 4) & 15u);
+    const uint32_t smooth_b = ((al >> 8) & 127u) + (cb >> 8);
+    const uint32_t smooth_a = (aa >> 8) + (ca >> 8);
+    const uint32_t mx_b = max_nibble(b), mx_a = max(mx_b, created);  // a merge only ever raises the maximum
+    bool fc_b, ic_b, fc_a, ic_a;
+    corner_rules(b, mx_b, fc_b, ic_b);
+    corner_rules(moved, mx_a, fc_a, ic_a);
+    const uint32_t mono_b = fc_b ? pairs_b * 2u : pairs_b >> 1, mono_a = fc_a ? pairs_a * 2u : pairs_a >> 1;
+    const uint32_t empt_b = 16u - __popc(nz_flags8(b.lo)) - __popc(nz_flags8(b.hi));
+    // spawn (game.py:923-940, as spawn_tile) -- its count of empty cells is emptiness_after
+    const uint32_t zl = z_flags8(moved.lo) >> 3, zh = z_flags8(moved.hi) >> 3;
+    const uint32_t pl = zl * 0x11111111u;
+    const uint32_t nl = pl >> 28, empt_a = nl + __popc(zh);
+    const uint32_t k = __umulhi(u0, empt_a);
+    const bool in_lo = k < nl;
+    const uint32_t z = in_lo ? zl : zh;
+    const uint32_t p = in_lo ? pl : zh * 0x11111111u;
+    const uint32_t t = in_lo ? k + 1u : k + 1u - nl;
+    const uint32_t hit = z_flags8(p ^ (t * 0x11111111u)) & (z << 3);   // the empty nibble whose prefix count is t
+    const uint32_t tile = (hit >> 3) * (u1 >= 3865470567u ? 2u : 1u);   // hit is one flag (none on a full board)
+    const Board spawned = {moved.lo | (in_lo ? tile : 0u), moved.hi | (in_lo ? 0u : tile)};
+    uint32_t lo = mono_b | mono_a << 6 | empt_b << 12 | empt_a << 17 | created << 22 | mx_b << 27 | uint32_t(ic_b) << 31;
+    uint32_t hi = mx_a | uint32_t(ic_a) << 4 | smooth_b << 5 | smooth_a << 14;
+    o.shape_lo = valid ? lo : 0u;
+    o.shape_hi = valid ? hi : 0u;
+    o.board = valid ? spawned : b;
+    o.points = valid ? int(points) : 0;
+    const uint32_t lm = legal_mask(o.board);                       // game.py:1006 / 963
+    o.flags = lm | (lm == 0u ? FLAG_DONE : 0u) | (valid ? 0u : FLAG_INVALID);   // no cell >= 12: no overflow possible
     return o;
 }
 

@@ -42,13 +42,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <uint32_t BYTES = uint32_t(LUT_SMEM_BYTES)>
 __device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, uint64_t* bar) {
     constexpr uint32_t CHUNK = 32768;
-    static_assert(BYTES % CHUNK == 0, "whole chunks");
+    static_assert(BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, BYTES);
 #pragma unroll
         for (uint32_t off = 0; off < BYTES; off += CHUNK)
-            bulk_copy_g2s(reinterpret_cast<uint8_t*>(slut) + off, reinterpret_cast<const uint8_t*>(glut) + off, CHUNK, bar);
+            bulk_copy_g2s(reinterpret_cast<uint8_t*>(slut) + off, reinterpret_cast<const uint8_t*>(glut) + off,
+                          BYTES - off < CHUNK ? BYTES - off : CHUNK, bar);
     }
     __syncthreads();          // barrier init visible to all waiters
     mbar_wait(bar, 0);
@@ -61,6 +62,11 @@ __global__ void build_lut_kernel(uint32_t* lut) {
         lut[row] = lut_entry_for_row(row);
         lut[MOVE_LUT_OFFSET + move_slot(row)] = move_entry_for_row(row);
     }
+    // dense step tables (M: u64 slots, S: u16 slots) behind the two row tables
+    uint8_t* dense = reinterpret_cast<uint8_t*>(lut) + DENSE_OFFSET_BYTES;
+    if (row < uint32_t(DENSE_M_BYTES / 8)) reinterpret_cast<uint64_t*>(dense)[row] = row < uint32_t(DENSE_M_ROWS) ? dense_m_entry(row) : 0ull;
+    if (row < uint32_t(DENSE_S_BYTES / 2))
+        reinterpret_cast<uint16_t*>(dense + DENSE_M_BYTES)[row] = row < uint32_t(DENSE_S_ROWS) ? uint16_t(dense_s_entry(row)) : uint16_t(0);
 }
 
 __global__ void reset_kernel(uint64_t* boards, int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0,
@@ -128,6 +134,49 @@ step_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* in, const 
     const uint32_t a0 = i0 < n ? __ldg(actions + i0) : 0u;
     stage_lut(slut, glut, &bar);
     step_loop<SHAPING, true>(slut, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr, b0, a0);
+}
+
+// Step + every shaping term on the dense tables (M | S staged whole, 219 KiB): persistent, one CTA per SM,
+// one transition per thread and iteration.  Boards with a 4096+ tile take the general path through L2.
+__global__ void __launch_bounds__(STEP_THREADS, 1)
+step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict__ in, const uint8_t* __restrict__ actions,
+                  uint64_t* __restrict__ out, int32_t* __restrict__ points, uint8_t* __restrict__ flags,
+                  uint64_t* __restrict__ shaping, int64_t n, const uint32_t* __restrict__ replay, const PhiloxKeys seed,
+                  uint64_t env0, uint64_t ctr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint64_t next_board = i < n ? __ldg(in + i) : 0ull;                   // issued before the table staging wait
+    uint32_t next_action = i < n ? __ldg(actions + i) : 0u;
+    stage_lut<uint32_t(DENSE_BYTES)>(reinterpret_cast<uint32_t*>(smem_raw),
+                                     reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
+    const DenseSmem tab{smem_u32(smem_raw), smem_u32(smem_raw) + uint32_t(DENSE_M_BYTES)};
+    for (; i < n; i += stride) {
+        const Board b = make_board(next_board);
+        const uint32_t a = next_action & 3u;
+        if (i + stride < n) {                         // next transition's inputs in flight while this one is computed
+            next_board = __ldg(in + i + stride);
+            next_action = __ldg(actions + i + stride);
+        }
+        uint32_t u0, u1;
+        if (replay) {
+            const uint2 r = __ldg(reinterpret_cast<const uint2*>(replay) + i);
+            u0 = r.x;
+            u1 = r.y;
+        } else {
+            const U4 d = env_draws(seed, env0 + uint64_t(i), ctr);
+            u0 = d.x;
+            u1 = d.y;
+        }
+        StepOut o;
+        if (!has_big_tile(b)) o = env_step_dense(b, a, u0, u1, tab);
+        else o = env_step<true>(b, a, u0, u1, LutGlobal{glut});           // rare: a 4096+ tile on the board
+        out[i] = pack_board(o.board);
+        points[i] = o.points;
+        flags[i] = uint8_t(o.flags);
+        shaping[i] = uint64_t(o.shape_lo) | uint64_t(o.shape_hi) << 32;
+    }
 }
 
 template <bool SHAPING>
@@ -461,7 +510,12 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
     G2048_REQUIRE(d_lut && boards_in && actions && boards_out && points && flags, "g2048_step: NULL pointer argument");
     const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
     cudaStream_t st = cudaStream_t(stream);
-    if (n >= STAGED_MIN_UNITS) {
+    if (n >= STAGED_MIN_UNITS && shaping) {
+        G2048_CHECK_CUDA(ensure_smem(step_kernel_dense, DENSE_BYTES));
+        step_kernel_dense<<<num_sms(), STEP_THREADS, DENSE_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,
+                                                                       shaping, n, replay, philox_round_keys(seed), env0, ctr);
+        G2048_CHECK_LAUNCH("step_kernel_dense");
+    } else if (n >= STAGED_MIN_UNITS) {
         auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;
         G2048_CHECK_CUDA(ensure_smem(kern, LUT_SMEM_BYTES));
         kern<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,

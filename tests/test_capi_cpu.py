@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 8
     for n in names:
         assert hasattr(lib, n), f"libg2048.so does not export {n}"
-    assert lib.g2048_lut_bytes() == 2 * 65536 * 4
+    assert lib.g2048_lut_bytes() == 2 * 65536 * 4 + 167040 + 57136   # row tables + dense step tables (M | S)
     assert b"sm_100a" in lib.g2048_version()
 
 

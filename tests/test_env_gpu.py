@@ -150,6 +150,67 @@ def test_step_all_rows_exhaustive(env):
         check_step(env, boards, actions, draws)
 
 
+def test_dense_step_tables_match_oracle(env):
+    """The dense tables of the fused step kernel (M: u64 per row with cells <= 11, S: u16 per row with cells
+    <= 12) against the oracle's row table and a direct count of the per-line potentials."""
+    raw = env.lut(0).cpu().numpy()
+    m = raw[2 * 65536 * 4:2 * 65536 * 4 + 167040].view(np.uint64)
+    s16 = raw[2 * 65536 * 4 + 167040:].view(np.uint16)
+    out4, score, mt = O.row_table()
+
+    def stats(rows):
+        c = np.stack([(rows >> (4 * k)) & 15 for k in range(4)], axis=1).astype(np.int64)
+        both = (c[:, :-1] > 0) & (c[:, 1:] > 0)
+        ge = (both & (c[:, :-1] >= c[:, 1:])).sum(1)
+        le = (both & (c[:, :-1] <= c[:, 1:])).sum(1)
+        sm = (both * np.abs(c[:, :-1] - c[:, 1:])).sum(1)
+        return ge | le << 4 | sm << 8
+
+    d = np.arange(12)
+    c0, c1, c2, c3 = np.meshgrid(d, d, d, d, indexing="ij")
+    rows = (c0 | c1 << 4 | c2 << 8 | c3 << 12).reshape(-1)
+    slot = (c0 + 12 * c1 + 145 * (c2 + 12 * c3)).reshape(-1)
+    e = m[slot]
+    lo, hi = (e & np.uint64(0xFFFFFFFF)).astype(np.int64), (e >> np.uint64(32)).astype(np.int64)
+    res = (out4[rows].astype(np.int64) << (4 * np.arange(4))).sum(1)
+    np.testing.assert_array_equal(lo & 0xFFFF, res)
+    np.testing.assert_array_equal(((lo >> 16) & 0xFFF) * 4, score[rows])
+    np.testing.assert_array_equal(lo >> 28, mt[rows])
+    np.testing.assert_array_equal(hi & 0x7FFF, stats(rows))
+    np.testing.assert_array_equal(hi >> 15, stats(res))
+    used = np.zeros(m.size, bool)
+    used[slot] = True
+    assert not m[~used].any()
+    d = np.arange(13)
+    c0, c1, c2, c3 = np.meshgrid(d, d, d, d, indexing="ij")
+    rows = (c0 | c1 << 4 | c2 << 8 | c3 << 12).reshape(-1)
+    slot = (c0 + 13 * c1 + 169 * c2 + 2197 * c3).reshape(-1)
+    np.testing.assert_array_equal(s16[slot].astype(np.int64), stats(rows))
+
+
+def test_step_all_small_rows_through_the_dense_kernel(env):
+    """Every row with exponents <= 11 tiled into the 4 rows / 4 columns of a board, padded with random boards
+    past the staging threshold so that the dense-table kernel (not the direct one) sees all of them."""
+    vals = np.arange(12, dtype=np.uint64)
+    rows = (vals[:, None, None, None] | vals[None, :, None, None] << np.uint64(4) |
+            vals[None, None, :, None] << np.uint64(8) | vals[None, None, None, :] << np.uint64(12)).reshape(-1)
+    horiz = rows | rows << np.uint64(16) | rows << np.uint64(32) | rows << np.uint64(48)
+    c = [(rows >> np.uint64(4 * k)) & np.uint64(15) for k in range(4)]
+    col = lambda v: v | v << np.uint64(4) | v << np.uint64(8) | v << np.uint64(12)
+    vert = col(c[0]) | col(c[1]) << np.uint64(16) | col(c[2]) << np.uint64(32) | col(c[3]) << np.uint64(48)
+    mixed = rows | np.roll(rows, 1) << np.uint64(16) | np.roll(rows, 7) << np.uint64(32) | np.roll(rows, 1234) << np.uint64(48)
+    base = np.concatenate([horiz, vert, mixed, random_boards(1 << 16, 77, hi=14)])
+    boards = np.concatenate([base] * 4)
+    actions = np.repeat(np.arange(4, dtype=np.uint8), base.size)
+    assert boards.size >= 1 << 17
+    rng = np.random.default_rng(5)
+    draws = rng.integers(0, 2**32, (boards.size, 2), dtype=np.uint64).astype(np.uint32)
+    draws[::7, 1] = 3865470567 - (np.arange(draws[::7].shape[0]) % 2)         # both sides of the 4-tile threshold
+    draws[::11, 0] = np.uint32(0xFFFFFFFF)
+    draws[::13, 0] = 0
+    check_step(env, boards, actions, draws)
+
+
 def test_philox_path_matches_oracle(env):
     n = 1 << 17
     boards = random_boards(n, 11)
