@@ -160,8 +160,8 @@ struct LutGlobal {
 //  M (u64, dense index of a row with every cell <= 11: digits c0 + 12 c1 + 145 (c2 + 12 c3)),
 //    read for the 4 lines along the move axis (canonical frame):
 //      lo [15:0]  left-move result      [27:16] merge points / 4      [31:28] largest exponent created
-//      hi [3:0]   ge   [7:4]   le   [14:8]  |smoothness| of the row itself          (before the move)
-//         [18:15] ge   [22:19] le   [30:23] |smoothness| of the result row          (after the move)
+//      hi [3:0]   ge   [7:4]   le   [15:8]  |smoothness| of the row itself          (before the move)
+//         [19:16] ge   [23:20] le   [31:24] |smoothness| of the result row          (after the move)
 //  S (u16, dense base-13 index of a row with every cell <= 12), read for the 4 lines across the move
 //    axis of the board before the move and of the board after it:
 //      [3:0] ge   [7:4] le   [15:8] |smoothness|
@@ -194,7 +194,7 @@ __host__ __device__ inline uint64_t dense_m_entry(uint32_t slot) {
     const uint32_t row = dense_m_row(slot);
     if (row == 0xFFFFFFFFu) return 0ull;
     const uint32_t mv = move_entry_for_row(row);              // result | points/4 | created (exact: cells <= 11)
-    const uint32_t hi = line_stats(row) | line_stats(mv & 0xFFFFu) << 15;
+    const uint32_t hi = line_stats(row) | line_stats(mv & 0xFFFFu) << 16;
     return uint64_t(mv) | uint64_t(hi) << 32;
 }
 __host__ __device__ inline uint32_t dense_s_entry(uint32_t slot) { return line_stats(dense_s_row(slot)); }
@@ -298,21 +298,24 @@ __device__ __forceinline__ void move_stats(Lines l, int& points, int& max_tile) 
 // bit d set <=> direction d (0=UP 1=DOWN 2=LEFT 3=RIGHT) changes the board, i.e.
 // can-slide or can-merge (game.py:116-119).  Slide toward a side <=> some empty cell
 // has a tile as its immediate neighbour on the far side; merge <=> equal adjacent tiles.
+__device__ __forceinline__ uint32_t nz_flags8(uint32_t x) { return (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
+__device__ __forceinline__ uint32_t z_flags8(uint32_t x) { return ~(((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
 __device__ __forceinline__ uint32_t legal_mask(Board b) {
-    uint32_t nzl = nz_flags32(b.lo), nzh = nz_flags32(b.hi);
-    uint32_t el = nzl ^ 0x11111111u, eh = nzh ^ 0x11111111u;
+    // flags live at bit 3 of every nibble (exact non-zero test in three instructions)
+    uint32_t nzl = nz_flags8(b.lo), nzh = nz_flags8(b.hi);
+    uint32_t el = nzl ^ 0x88888888u, eh = nzh ^ 0x88888888u;
     // horizontal neighbours (c, c+1), c = 0..2
-    uint32_t dl = b.lo ^ shr<4>(b.lo), dh = b.hi ^ shr<4>(b.hi);
-    uint32_t mh = ((z_flags32(dl) & nzl) | (z_flags32(dh) & nzh)) & 0x01110111u;
+    uint32_t dl = b.lo ^ (b.lo >> 4), dh = b.hi ^ (b.hi >> 4);
+    uint32_t mh = ((z_flags8(dl) & nzl) | (z_flags8(dh) & nzh)) & 0x08880888u;
     // vertical neighbours (r, r+1), r = 0..2
     uint32_t lo16 = __funnelshift_r(b.lo, b.hi, 16);
-    uint32_t vl = b.lo ^ lo16, vh = b.hi ^ shr<16>(b.hi);
-    uint32_t mv = (z_flags32(vl) & nzl) | (z_flags32(vh) & nzh & 0x00001111u);
-    uint32_t left = ((el & shr<4>(nzl)) | (eh & shr<4>(nzh))) & 0x01110111u;
-    uint32_t right = ((el & shl<4>(nzl)) | (eh & shl<4>(nzh))) & 0x11101110u;
+    uint32_t vl = b.lo ^ lo16, vh = b.hi ^ (b.hi >> 16);
+    uint32_t mv = (z_flags8(vl) & nzl) | (z_flags8(vh) & nzh & 0x00008888u);
+    uint32_t left = ((el & (nzl >> 4)) | (eh & (nzh >> 4))) & 0x08880888u;
+    uint32_t right = ((el & (nzl << 4)) | (eh & (nzh << 4))) & 0x88808880u;
     uint32_t nz16 = __funnelshift_r(nzl, nzh, 16);
-    uint32_t up = (el & nz16) | (eh & shr<16>(nzh));
-    uint32_t down = (eh & nz16) | (el & shl<16>(nzl));
+    uint32_t up = (el & nz16) | (eh & (nzh >> 16));
+    uint32_t down = (eh & nz16) | (el & (nzl << 16));
     uint32_t m = 0;
     if (up | mv) m |= 1u;
     if (down | mv) m |= 2u;
@@ -541,9 +544,6 @@ __device__ __forceinline__ StepOut env_step(Board b, uint32_t action, uint32_t u
 }
 
 // ------------------------------------------------------------------ step on the dense tables
-// Exact non-zero-nibble flags at bit 3 of every nibble, three instructions.
-__device__ __forceinline__ uint32_t nz_flags8(uint32_t x) { return (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
-__device__ __forceinline__ uint32_t z_flags8(uint32_t x) { return ~(((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u; }
 
 // largest nibble of the board: a 16-bit unsigned max is decided by the top nibble of each lane, so
 // four shifted copies put every cell of a row there once (what lies below does not matter).
@@ -596,11 +596,11 @@ __device__ __forceinline__ uint32_t s_sum(Board x, const DenseSmem& tab) {
     return tab.S(a2 & 0xFFFFu) + tab.S(a2 >> 16) + tab.S(b2 & 0xFFFFu) + tab.S(b2 >> 16);
 }
 
-// env_step<true> for a board with every cell <= 11 (so every line before the move indexes M / S and
+// env_step<true> for a board with every cell <= 11, i.e. mx_b = max_nibble(b) <= 11 (so every line before the move indexes M / S and
 // every line after it indexes S).  12 table reads: the 4 lines along the move axis (M: move result,
 // points, created tile, and the per-line potentials of the line before AND after the move), the 4
 // lines across it before the move (S) and after it (S).  Same results as env_step, bit for bit.
-__device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t action, uint32_t u0, uint32_t u1, const DenseSmem& tab) {
+__device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t mx_b, uint32_t action, uint32_t u0, uint32_t u1, const DenseSmem& tab) {
     StepOut o;
     const Board bt = transpose(b);
     const bool horiz = (action & 2u) != 0u;
@@ -622,17 +622,19 @@ __device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t action, uint
     const Board unt = transpose(un);
     const Board moved = horiz ? un : unt;
     const uint32_t ca = s_sum(unt, tab);
-    const uint32_t al = m0.y + m1.y + m2.y + m3.y;                 // along the axis: before [14:0], after [30:15]
-    const uint32_t aa = al >> 15;
-    const uint32_t pairs_b = max(al & 15u, (al >> 4) & 15u) + max(cb & 15u, (cb >> 4) & 15u);
-    const uint32_t pairs_a = max(aa & 15u, (aa >> 4) & 15u) + max(ca & 15u, (ca >> 4) & 15u);
-    const uint32_t smooth_b = ((al >> 8) & 127u) + (cb >> 8);
-    const uint32_t smooth_a = (aa >> 8) + (ca >> 8);
-    const uint32_t mx_b = max_nibble(b), mx_a = max(mx_b, created);  // a merge only ever raises the maximum
+    // potentials of both boards at once: 16-bit lane 0 = before the move, lane 1 = after it
+    const uint32_t al = m0.y + m1.y + m2.y + m3.y;                 // lines along the move axis
+    const uint32_t cr = ca * 65536u + cb;                          // lines across it
+    const uint32_t pairs = __vmaxu2(al & 0x000F000Fu, (al >> 4) & 0x000F000Fu) +
+                           __vmaxu2(cr & 0x000F000Fu, (cr >> 4) & 0x000F000Fu);     // SURVEY A7, <= 24 per lane
+    const uint32_t smooth = ((al >> 8) & 0x00FF00FFu) + ((cr >> 8) & 0x00FF00FFu);    // <= 264 per lane
+    const uint32_t mx_a = max(mx_b, created);                      // a merge only ever raises the maximum
     bool fc_b, ic_b, fc_a, ic_a;
     corner_rules(b, mx_b, fc_b, ic_b);
     corner_rules(moved, mx_a, fc_a, ic_a);
-    const uint32_t mono_b = fc_b ? pairs_b * 2u : pairs_b >> 1, mono_a = fc_a ? pairs_a * 2u : pairs_a >> 1;
+    const uint32_t dbl = pairs + pairs, hlf = (pairs >> 1) & 0x000F000Fu;            // game.py:755-758
+    const uint32_t mono_b = (fc_b ? dbl : hlf) & 0x3Fu, mono_a = (fc_a ? dbl : hlf) >> 16;
+    const uint32_t smooth_b = smooth & 0xFFFFu, smooth_a = smooth >> 16;
     const uint32_t empt_b = 16u - __popc(nz_flags8(b.lo)) - __popc(nz_flags8(b.hi));
     // spawn (game.py:923-940, as spawn_tile) -- its count of empty cells is emptiness_after
     const uint32_t zl = z_flags8(moved.lo) >> 3, zh = z_flags8(moved.hi) >> 3;

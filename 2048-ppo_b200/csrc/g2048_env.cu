@@ -145,19 +145,22 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
                   uint64_t env0, uint64_t ctr) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ uint64_t bar;
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    uint64_t next_board = i < n ? __ldg(in + i) : 0ull;                   // issued before the table staging wait
-    uint32_t next_action = i < n ? __ldg(actions + i) : 0u;
+    // 32-bit indices (the host splits launches at 2^30 transitions): one IMAD.WIDE per address instead of
+    // 64-bit add chains on the integer pipe this kernel is bound by
+    const uint32_t stride = gridDim.x * blockDim.x, n32 = uint32_t(n);
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t next_board = i < n32 ? __ldg(in + i) : 0ull;                 // issued before the table staging wait
+    uint32_t next_action = i < n32 ? __ldg(actions + i) : 0u;
     stage_lut<uint32_t(DENSE_BYTES)>(reinterpret_cast<uint32_t*>(smem_raw),
                                      reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
     const DenseSmem tab{smem_u32(smem_raw), smem_u32(smem_raw) + uint32_t(DENSE_M_BYTES)};
-    for (; i < n; i += stride) {
+    for (; i < n32; i += stride) {
         const Board b = make_board(next_board);
         const uint32_t a = next_action & 3u;
-        if (i + stride < n) {                         // next transition's inputs in flight while this one is computed
-            next_board = __ldg(in + i + stride);
-            next_action = __ldg(actions + i + stride);
+        const uint32_t nx = i + stride;
+        if (nx < n32) {                               // next transition's inputs in flight while this one is computed
+            next_board = __ldg(in + nx);
+            next_action = __ldg(actions + nx);
         }
         uint32_t u0, u1;
         if (replay) {
@@ -170,7 +173,8 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
             u1 = d.y;
         }
         StepOut o;
-        if (!has_big_tile(b)) o = env_step_dense(b, a, u0, u1, tab);
+        const uint32_t mx = max_nibble(b);
+        if (mx <= 11u) o = env_step_dense(b, mx, a, u0, u1, tab);
         else o = env_step<true>(b, a, u0, u1, LutGlobal{glut});           // rare: a 4096+ tile on the board
         out[i] = pack_board(o.board);
         points[i] = o.points;
@@ -512,8 +516,13 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
     cudaStream_t st = cudaStream_t(stream);
     if (n >= STAGED_MIN_UNITS && shaping) {
         G2048_CHECK_CUDA(ensure_smem(step_kernel_dense, DENSE_BYTES));
-        step_kernel_dense<<<num_sms(), STEP_THREADS, DENSE_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,
-                                                                       shaping, n, replay, philox_round_keys(seed), env0, ctr);
+        constexpr int64_t SPLIT = int64_t(1) << 30;               // the kernel indexes with 32 bits
+        for (int64_t o = 0; o < n; o += SPLIT) {
+            const int64_t m = n - o < SPLIT ? n - o : SPLIT;
+            step_kernel_dense<<<num_sms(), STEP_THREADS, DENSE_BYTES, st>>>(
+                lut, boards_in + o, actions + o, boards_out + o, points + o, flags + o, shaping + o, m,
+                replay ? replay + 2 * o : nullptr, philox_round_keys(seed), env0 + uint64_t(o), ctr);
+        }
         G2048_CHECK_LAUNCH("step_kernel_dense");
     } else if (n >= STAGED_MIN_UNITS) {
         auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;

@@ -176,8 +176,8 @@ def test_dense_step_tables_match_oracle(env):
     np.testing.assert_array_equal(lo & 0xFFFF, res)
     np.testing.assert_array_equal(((lo >> 16) & 0xFFF) * 4, score[rows])
     np.testing.assert_array_equal(lo >> 28, mt[rows])
-    np.testing.assert_array_equal(hi & 0x7FFF, stats(rows))
-    np.testing.assert_array_equal(hi >> 15, stats(res))
+    np.testing.assert_array_equal(hi & 0xFFFF, stats(rows))
+    np.testing.assert_array_equal(hi >> 16, stats(res))
     used = np.zeros(m.size, bool)
     used[slot] = True
     assert not m[~used].any()

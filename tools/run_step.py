@@ -1,0 +1,23 @@
+"""One C2-sized g2048_step launch sequence (for ncu): 2^22 transitions with shaping, Philox draws."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "2048-ppo_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from g2048 import env  # noqa: E402
+
+dev = torch.device("cuda:0")
+env.lut(dev)
+g = torch.Generator(device=dev).manual_seed(2048)
+n = 1 << 22
+e = torch.randint(1, 12, (n, 16), generator=g, device=dev, dtype=torch.int64)
+e[torch.rand((n, 16), generator=g, device=dev) < 0.30] = 0
+boards = (e << (torch.arange(16, device=dev) * 4)).sum(1)
+acts = torch.randint(0, 4, (n,), generator=g, device=dev, dtype=torch.uint8)
+for k in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
+    r = env.step(boards, acts, seed=1, ctr=k)
+torch.cuda.synchronize()
+print("ok", int(r["points"].sum()))
