@@ -38,9 +38,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// Stage the first BYTES of a table into shared memory (224 / 192 KiB, 32 KiB bulk copies).
-template <uint32_t BYTES = uint32_t(LUT_SMEM_BYTES)>
-__device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, uint64_t* bar) {
+// Stage the first BYTES of a table into shared memory (<= 32 KiB bulk copies on one mbarrier): issue, then wait.
+template <uint32_t BYTES>
+__device__ __forceinline__ void stage_lut_issue(uint32_t* slut, const uint32_t* glut, uint64_t* bar) {
     constexpr uint32_t CHUNK = 32768;
     static_assert(BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
     if (threadIdx.x == 0) {
@@ -51,9 +51,24 @@ __device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, 
             bulk_copy_g2s(reinterpret_cast<uint8_t*>(slut) + off, reinterpret_cast<const uint8_t*>(glut) + off,
                           BYTES - off < CHUNK ? BYTES - off : CHUNK, bar);
     }
+}
+__device__ __forceinline__ void stage_lut_wait(uint64_t* bar) {
     __syncthreads();          // barrier init visible to all waiters
     mbar_wait(bar, 0);
 }
+template <uint32_t BYTES = uint32_t(LUT_SMEM_BYTES)>
+__device__ __forceinline__ void stage_lut(uint32_t* slut, const uint32_t* glut, uint64_t* bar) {
+    stage_lut_issue<BYTES>(slut, glut, bar);
+    stage_lut_wait(bar);
+}
+
+// Programmatic dependent launch: the persistent table kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a CTA may start (and stage its table, which no
+// kernel in flight writes: g2048_build_lut returns only once the table is complete) while the previous
+// kernel of the stream is still draining.  pdl_wait() returns when that kernel has completed and its writes
+// are visible; nothing the caller owns is read or written before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------ kernels
 __global__ void build_lut_kernel(uint32_t* lut) {
@@ -149,10 +164,13 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
     // 64-bit add chains on the integer pipe this kernel is bound by
     const uint32_t stride = gridDim.x * blockDim.x, n32 = uint32_t(n);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t next_board = i < n32 ? __ldg(in + i) : 0ull;                 // issued before the table staging wait
+    pdl_launch_dependents();
+    stage_lut_issue<uint32_t(DENSE_BYTES)>(reinterpret_cast<uint32_t*>(smem_raw),
+                                           reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
+    pdl_wait();
+    uint64_t next_board = i < n32 ? __ldg(in + i) : 0ull;                 // in flight during the table staging wait
     uint32_t next_action = i < n32 ? __ldg(actions + i) : 0u;
-    stage_lut<uint32_t(DENSE_BYTES)>(reinterpret_cast<uint32_t*>(smem_raw),
-                                     reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
+    stage_lut_wait(&bar);
     const DenseSmem tab{smem_u32(smem_raw), smem_u32(smem_raw) + uint32_t(DENSE_M_BYTES)};
     for (; i < n32; i += stride) {
         const Board b = make_board(next_board);
@@ -259,8 +277,11 @@ expand4_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* boards,
     __shared__ uint64_t bar;
     uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
     const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint64_t first = i0 < n ? __ldg(boards + i0) : 0ull;            // issued before the table staging wait
-    stage_lut<uint32_t(MOVE_SMEM_BYTES)>(slut, glut + MOVE_LUT_OFFSET, &bar);
+    pdl_launch_dependents();
+    stage_lut_issue<uint32_t(MOVE_SMEM_BYTES)>(slut, glut + MOVE_LUT_OFFSET, &bar);
+    pdl_wait();
+    const uint64_t first = i0 < n ? __ldg(boards + i0) : 0ull;            // in flight during the table staging wait
+    stage_lut_wait(&bar);
     expand4_loop<true>(slut, glut, boards, succ, points, legal, max_tile, n, first);
 }
 
@@ -481,6 +502,22 @@ augment_kernel(const uint64_t* __restrict__ before, const uint64_t* __restrict__
 // below this many units the 224 KiB table staging (per CTA) costs more than it saves
 constexpr int64_t STAGED_MIN_UNITS = 1 << 17;
 
+// kernel<<<grid, block, smem, stream>>>(args...) with cudaLaunchAttributeProgrammaticStreamSerialization
+template <class... P, class... A>
+cudaError_t launch_pdl(void (*kernel)(P...), int grid, int block, int smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(unsigned(block));
+    cfg.dynamicSmemBytes = size_t(smem);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, P(args)...);
+}
+
 }  // namespace g2048
 
 using namespace g2048;
@@ -493,6 +530,12 @@ int g2048_build_lut(void* d_lut, void* stream) {
     G2048_REQUIRE(d_lut != nullptr, "g2048_build_lut: d_lut is NULL");
     build_lut_kernel<<<LUT_ROWS / 256, 256, 0, cudaStream_t(stream)>>>(static_cast<uint32_t*>(d_lut));
     G2048_CHECK_LAUNCH("build_lut_kernel");
+    // One-time initialisation, the only entry point that blocks: kernels launched with programmatic stream
+    // serialisation stage the table before they wait for their predecessor, so it must be complete on return.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    G2048_CHECK_CUDA(cudaStreamIsCapturing(cudaStream_t(stream), &cap));
+    G2048_REQUIRE(cap == cudaStreamCaptureStatusNone, "g2048_build_lut: build the table outside stream capture");
+    G2048_CHECK_CUDA(cudaStreamSynchronize(cudaStream_t(stream)));
     return G2048_OK;
 }
 
@@ -519,11 +562,11 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
         constexpr int64_t SPLIT = int64_t(1) << 30;               // the kernel indexes with 32 bits
         for (int64_t o = 0; o < n; o += SPLIT) {
             const int64_t m = n - o < SPLIT ? n - o : SPLIT;
-            step_kernel_dense<<<num_sms(), STEP_THREADS, DENSE_BYTES, st>>>(
-                lut, boards_in + o, actions + o, boards_out + o, points + o, flags + o, shaping + o, m,
-                replay ? replay + 2 * o : nullptr, philox_round_keys(seed), env0 + uint64_t(o), ctr);
+            G2048_CHECK_CUDA(launch_pdl(step_kernel_dense, num_sms(), STEP_THREADS, DENSE_BYTES, st, lut, boards_in + o, actions + o,
+                                        boards_out + o, points + o, flags + o, shaping + o, m,
+                                        replay ? replay + 2 * o : static_cast<const uint32_t*>(nullptr),
+                                        philox_round_keys(seed), env0 + uint64_t(o), ctr));
         }
-        G2048_CHECK_LAUNCH("step_kernel_dense");
     } else if (n >= STAGED_MIN_UNITS) {
         auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;
         G2048_CHECK_CUDA(ensure_smem(kern, LUT_SMEM_BYTES));
@@ -548,9 +591,8 @@ int g2048_expand4(const void* d_lut, const uint64_t* boards, uint64_t* succ, int
     cudaStream_t st = cudaStream_t(stream);
     if (n >= STAGED_MIN_UNITS) {
         G2048_CHECK_CUDA(ensure_smem(expand4_kernel_staged, MOVE_SMEM_BYTES));
-        expand4_kernel_staged<<<num_sms(), STEP_THREADS, MOVE_SMEM_BYTES, st>>>(lut, boards, succ, points, legal,
-                                                                               max_tile, n);
-        G2048_CHECK_LAUNCH("expand4_kernel_staged");
+        G2048_CHECK_CUDA(launch_pdl(expand4_kernel_staged, num_sms(), STEP_THREADS, MOVE_SMEM_BYTES, st, lut, boards, succ, points,
+                                    legal, max_tile, n));
     } else {
         expand4_kernel_direct<<<unsigned((n + 255) / 256), 256, 0, st>>>(lut, boards, succ, points, legal, max_tile, n);
         G2048_CHECK_LAUNCH("expand4_kernel_direct");

@@ -35,10 +35,10 @@ N_BOARDS = 1 << 20
 MOVES = 4
 N_TRANS = N_BOARDS * MOVES
 BYTES_PER_TRANSITION = 30      # 8 board in + 1 action + 8 board out + 4 points + 1 flags + 8 shaping
-# dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel_staged<true> launch on this workload, from the
-# committed `ncu --set full` capture (profiles/r01_env_kernels_ncu.txt: 38.0 MB read + 33.7 MB written; the rest of
+# dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel_dense launch on this workload, from the
+# committed `ncu --set full` capture (profiles/r01_step_dense_ncu.txt: 38.0 MB read + 32.5 MB written; the rest of
 # the 88 MB of outputs is still dirty in the 126 MB L2 when the kernel ends)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 71.7e6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 70.5e6
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -489,7 +489,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "algorithmic_bytes_per_launch": BYTES_PER_TRANSITION * N_TRANS,
-                         "peak_source": which, "kernel": "step_kernel_staged<true>",
+                         "peak_source": which, "kernel": "step_kernel_dense",
                          "bytes_per_unit": BYTES_PER_TRANSITION, "units_per_launch": N_TRANS},
         }
         line["expand4"] = expand

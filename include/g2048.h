@@ -64,10 +64,14 @@ const char* g2048_version(void);
 /* Checks that `device` is a compute-capability-10.x GPU and makes it current. */
 int g2048_init(int device);
 
-/* Row tables: 2 x 65536 x u32 (g2048_lut_bytes() = 524288 bytes), built on the device: the general
- * table (move result, merge codes, per-line potentials) and the move table of the 4-move expansion
- * (move result, merge points, created tile).  Replace game.py:224-257
- * (_merge_and_shift_left/right_with_score) for every row. */
+/* Tables (g2048_lut_bytes() = 748464 bytes), built on the device: the general row table (move result,
+ * merge codes, per-line potentials) and the move table of the 4-move expansion (move result, merge points,
+ * created tile), 65536 x u32 each, followed by the dense step tables of the fused step kernel (M: u64 per
+ * row with cells <= 11, S: u16 per row with cells <= 12; layout in csrc/g2048_device.cuh).  Replace
+ * game.py:224-257 (_merge_and_shift_left/right_with_score) and the per-line parts of game.py:339-357,
+ * 683-800 for every row.  g2048_build_lut is one-time initialisation and the only entry point that blocks:
+ * it returns once the table is complete (the persistent kernels are launched with programmatic stream
+ * serialisation and stage the table before they wait for their predecessor in the stream). */
 int64_t g2048_lut_bytes(void);
 int g2048_build_lut(void* d_lut, void* stream);
 

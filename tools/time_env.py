@@ -45,6 +45,22 @@ for logn in (18, 20, 22, 24):
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / reps
-        print(f"{name:13s} n=2^{logn} ring={ring:2d}: {us:9.2f} us/launch  {n / us * 1e6:.3e} units/s  {n * bytes_per / us / 1e3:8.1f} GB/s")
+        # the same launches replayed from one CUDA graph (no host launch cost in the timed region)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            fn(0)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for k in range(reps):
+                fn(k)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        gus = e0.elapsed_time(e1) * 1e3 / reps
+        print(f"{name:13s} n=2^{logn} ring={ring:2d}: {us:9.2f} us/launch eager, {gus:9.2f} us/launch graph  {n / gus * 1e6:.3e} units/s  {n * bytes_per / gus / 1e3:8.1f} GB/s")
     del ins, outs, acts, souts
     torch.cuda.empty_cache()
