@@ -218,13 +218,18 @@ constexpr uint32_t W_PART = MAXB * W_BLOCK;       // one operand part (13 blocks
 constexpr uint32_t W_STAGE = 4 * W_PART;          // dY hi | dY lo | X hi | X lo
 constexpr int W_FLUSH = 256;                      // stages between accumulator flushes (8192 samples)
 constexpr int W_UNITS = 2 * MAXB * (W_ROWS / 8);  // (matrix, block, 8-row group) load units per stage = 104
+// Two groups of 8 loader warps take alternate stages: the loads of stage q+1 are in flight while stage q is split
+// and stored (one group alone exposes the HBM latency once per stage: measured 51-64 % of the HBM peak).
+constexpr int W_GROUPS = 2;
+constexpr int W_EPI_WARP0 = 8 * W_GROUPS, W_ISSUER_WARP = W_EPI_WARP0 + 4;
+constexpr int W_THREADS = (W_ISSUER_WARP + 1) * 32;      // 672 -> at most 96 registers per thread
 
 struct WgradBars {
     uint64_t full[W_STAGES], empty[W_STAGES], d_full, d_empty;
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(W_THREADS, 1)
 x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ partial, int64_t M, int N,
                 int K, int dy_hp, int x_hp) {
     extern __shared__ uint8_t smem_raw[];
@@ -236,7 +241,7 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
     const int64_t s_begin = stages * blockIdx.x / gridDim.x, s_end = stages * (blockIdx.x + 1) / gridDim.x;
     const int my_stages = int(s_end - s_begin);
 
-    if (warp == ISSUER_WARP) tc::tmem_alloc(&S.tmem_base, 512);
+    if (warp == W_ISSUER_WARP) tc::tmem_alloc(&S.tmem_base, 512);
     if (tid == 0) {
         for (int i = 0; i < W_STAGES; ++i) {
             tc::mbar_init(&S.full[i], NUM_LOADERS);
@@ -247,22 +252,23 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
         tc::mbar_fence_init();
     }
     // blocks past the real feature count are read by the second M = 128 half: keep them finite
-    for (uint32_t i = tid * 16; i < W_STAGES * W_STAGE; i += NUM_THREADS * 16) *reinterpret_cast<uint4*>(sW + i) = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid * 16; i < W_STAGES * W_STAGE; i += W_THREADS * 16) *reinterpret_cast<uint4*>(sW + i) = make_uint4(0, 0, 0, 0);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = S.tmem_base;
 
-    if (warp < EPI_WARP0) {
-        // ---------------- loaders
+    if (warp < W_EPI_WARP0) {
+        // ---------------- loaders: group (warp / 8) takes the stages q = group, group + W_GROUPS, ...
         constexpr int PER_WARP = W_UNITS / 8;     // 13
-        for (int q = 0; q < my_stages; ++q) {
+        const int wg = warp & 7;
+        for (int q = warp >> 3; q < my_stages; q += W_GROUPS) {
             const int64_t sample0 = (s_begin + q) * W_ROWS;
             float4 v[PER_WARP];
 #pragma unroll
             for (int i = 0; i < PER_WARP; ++i) {
-                const int u = warp + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
+                const int u = wg + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
                 const int row = rg * 8 + (lane >> 2), f = lane & 3, col = b * 16 + f * 4;
                 const int ld = mat ? K : N, hp = mat ? x_hp : dy_hp;
                 const float* src = mat ? X : dY;
@@ -280,7 +286,7 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
             uint8_t* dst = sW + uint32_t(slot) * W_STAGE;
 #pragma unroll
             for (int i = 0; i < PER_WARP; ++i) {
-                const int u = warp + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
+                const int u = wg + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
                 if (b >= (mat ? KPB : NPB)) continue;
                 const int row = rg * 8 + (lane >> 2), f = lane & 3;
                 uint2 hi, lo;
@@ -292,9 +298,9 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
             tc::fence_async_smem();
             tc::mbar_arrive(&S.full[slot]);
         }
-    } else if (warp < ISSUER_WARP) {
+    } else if (warp < W_ISSUER_WARP) {
         // ---------------- epilogue: add the accumulators into this CTA's fp32 partial
-        const int ew = warp - EPI_WARP0, row = ew * 32 + lane;
+        const int ew = warp - W_EPI_WARP0, row = ew * 32 + lane;
         const uint32_t tlane = tmem_base + (uint32_t(ew * 32) << 16);
         const int nflush = (my_stages + W_FLUSH - 1) / W_FLUSH;
         float* mine = partial + size_t(blockIdx.x) * MAXF * MAXF;
@@ -364,7 +370,7 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == ISSUER_WARP) tc::tmem_dealloc(tmem_base, 512);
+    if (warp == W_ISSUER_WARP) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // fixed-order sum of the per-CTA partials
@@ -445,7 +451,7 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
     G2048_CHECK_CUDA(ensure_smem(x3_wgrad_kernel, smem));
     const int64_t stages = (M + W_ROWS - 1) / W_ROWS;
     const int grid = int(stages < num_sms() ? stages : num_sms());
-    x3_wgrad_kernel<<<grid, NUM_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
+    x3_wgrad_kernel<<<grid, W_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
     G2048_CHECK_LAUNCH("x3_wgrad_kernel");
     x3_wgrad_reduce_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), dW, N, K, grid);
     G2048_CHECK_LAUNCH("x3_wgrad_reduce_kernel");

@@ -73,7 +73,7 @@ def init(device: torch.device | int | None = None) -> torch.device:
 
 
 def lut(device=None) -> torch.Tensor:
-    """The 256 KiB row table of `device`, built on first use by g2048_build_lut."""
+    """The table buffer of `device` (row tables + dense step tables, g2048_lut_bytes() bytes), built on first use."""
     dev = init(device)
     if dev.index not in _LUTS:
         with torch.cuda.device(dev):
