@@ -188,6 +188,18 @@ class GameURM(nn.Module):  # game.py:1355-1458
     def directions(self):
         return list(DIRECTIONS)
 
+    def get_param_groups(self, value_lr: float, other_lr: float) -> list[dict]:
+        """Same grouping as GameMLP.get_param_groups (game.py:1093-1127), which the reference's optimiser set-up
+        (train.py:1587-1597) needs and its GameURM lacks (its CLI refuses --model-type urm, train.py:1523-1532):
+        matrices -> Muon, everything else (LayerNorm, biases, init_hidden [1,16,h], depthwise conv [c,1,k]) -> AdamW,
+        the value head on its own learning rate."""
+        v1, v2, o1, o2 = [], [], [], []
+        for name, p in self.named_parameters():
+            value = name.startswith("value_head")
+            (v2 if value else o2).append(p) if p.ndim == 2 else (v1 if value else o1).append(p)
+        return [{"params": o2, "lr": other_lr}, {"params": o1, "lr": other_lr},
+                {"params": v2, "lr": value_lr}, {"params": v1, "lr": value_lr}]
+
     def forward(self, inputs: torch.Tensor):
         if inputs.ndim == 1:
             inputs = inputs.unsqueeze(0)

@@ -14,11 +14,16 @@ from dataclasses import dataclass, field
 import torch
 
 from . import dp, env, fused, ppo, rollout, update
-from .policy import GameMLP, MLPConfig
+from .policy import GameMLP, GameURM, GameURMConfig, MLPConfig
 
 
 @dataclass
 class TrainConfig:
+    model_type: str = "mlp"        # "mlp" = GameMLP (the reference's only trainable model) or "urm" = GameURM: rollout on the
+                                   # fused URM kernel, update through torch autograd on the policy mirror (truncated loops under
+                                   # no_grad as in game.py:1400-1413) with the fused PPO-loss kernel -- SURVEY 8(f) N4, host half
+    urm: GameURMConfig = field(default_factory=lambda: GameURMConfig(dropout=0.0))
+    urm_chunk: int = 1 << 15       # samples per autograd chunk of the URM update (~0.4 MB of saved activations per sample)
     hidden_dim: int = 196
     num_layers: int = 2
     envs: int = 65536              # global env count (sharded over ranks)
@@ -82,7 +87,7 @@ class MultiOptimizer:  # train.py:1232-1281
         return [o.param_groups[0]["lr"] for o in self.optimizers]
 
 
-def make_optimizer(model: GameMLP, cfg: TrainConfig) -> MultiOptimizer:
+def make_optimizer(model, cfg: TrainConfig) -> MultiOptimizer:
     o2, o1, v2, v1 = model.get_param_groups(cfg.critic_lr, cfg.lr)
     adamw = torch.optim.AdamW([o1, v1], betas=(0.9, 0.999), weight_decay=cfg.weight_decay)
     muon = torch.optim.Muon([o2, v2], adjust_lr_fn="match_rms_adamw", weight_decay=cfg.weight_decay)
@@ -105,8 +110,15 @@ class Trainer:
         self.rank, self.world = dp.world()
         self.lo, self.hi = dp.shard_range(cfg.envs, self.rank, self.world)
         torch.manual_seed(cfg.seed)   # identical initial weights on every rank
-        self.model = model if model is not None else GameMLP(
-            MLPConfig(hidden_dim=cfg.hidden_dim, num_layers=cfg.num_layers, dropout=cfg.dropout))
+        if cfg.model_type not in ("mlp", "urm"):
+            raise ValueError(f"model_type must be 'mlp' or 'urm', got {cfg.model_type!r}")
+        if model is not None:
+            self.model = model
+        elif cfg.model_type == "urm":
+            self.model = GameURM(cfg.urm)
+        else:
+            self.model = GameMLP(MLPConfig(hidden_dim=cfg.hidden_dim, num_layers=cfg.num_layers, dropout=cfg.dropout))
+        self.is_mlp = isinstance(self.model, GameMLP) or hasattr(self.model, "backbone")
         self.model.to(self.device)
         if cfg.zero_heads and model is None:
             with torch.no_grad():
@@ -172,17 +184,21 @@ class Trainer:
                 n_mb_global = n_global if c.minibatches == 1 else (m1 - m0) * self.world
                 self.opt.zero_grad()
                 tot = torch.zeros(4, dtype=torch.float64, device=self.device)
-                use_fused = c.update_matmul == "fused" and update.supported(self.model)
+                use_fused = self.is_mlp and c.update_matmul == "fused" and update.supported(self.model)
                 packed = update.pack(self.model) if use_fused else None
-                for c0 in range(m0, m1, c.chunk):
-                    sl = slice(c0, min(m1, c0 + c.chunk)) if order is None else order[c0:min(m1, c0 + c.chunk)]
+                chunk = c.chunk if self.is_mlp else c.urm_chunk
+                for c0 in range(m0, m1, chunk):
+                    sl = slice(c0, min(m1, c0 + chunk)) if order is None else order[c0:min(m1, c0 + chunk)]
                     if use_fused:
                         tot += update.loss_and_grads(self.model, boards[sl], actions[sl], legal[sl], logp[sl], a[sl], g[sl],
                                                      flags=flags[sl], clip_eps=c.clip_eps, critic_strength=c.critic_strength,
                                                      entropy_strength=c.entropy_strength, n_total=n_mb_global, packed=packed)
                         continue
-                    logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
-                                                  matmul="x3" if c.update_matmul in ("x3", "fused") else "cublas")
+                    if self.is_mlp:
+                        logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
+                                                      matmul="x3" if c.update_matmul in ("x3", "fused") else "cublas")
+                    else:
+                        logits, v = self.model(env.encode(boards[sl]))
                     loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],
                                                clip_eps=c.clip_eps, critic_strength=c.critic_strength,
                                                entropy_strength=c.entropy_strength, n_total=n_mb_global)

@@ -114,3 +114,42 @@ def test_urm_rollout_env_path_bit_exact(B, T, layers):
     # (outlier bound), while the bulk agrees to ~1e-3 (mean bound)
     assert float((got[fin] - emu[fin]).abs().max()) < 8e-2 and float((buf.value.reshape(-1) - ev).abs().max()) < 8e-2
     assert float((got[fin] - emu[fin]).abs().mean()) < 1e-2 and float((buf.value.reshape(-1) - ev).abs().mean()) < 1e-2
+
+
+def test_trainer_urm_train_steps_match_autograd_on_the_same_batch():
+    """SURVEY 8(f) N4, host half: TrainConfig(model_type="urm") rolls out on the fused URM kernel and updates
+    through torch autograd on the GameURM mirror (first loop under no_grad, game.py:1400-1413) with the fused
+    PPO-loss kernel.  One update is replayed by hand on the recorded batch with the plain-torch loss restatement
+    (tests/helpers.py) and must give the same clipped gradient; the weights must move and the loss stay finite."""
+    from g2048 import env, trainer as tr
+    from helpers import ref_ppo_loss_torch
+    dev = torch.device("cuda:0")
+    cfg = tr.TrainConfig(model_type="urm", envs=256, horizon=8, zero_heads=False, urm_chunk=512, warmup_steps=0)
+    t = tr.Trainer(cfg, dev)
+    assert not t.is_mlp and sum(p.numel() for p in t.model.parameters()) == 81237
+    buf = t.collect()
+    adv = t.advantages(buf)
+    n = buf.flags.numel()
+    # by hand: whole batch, plain torch
+    ref = type(t.model)(cfg.urm).to(dev)
+    ref.load_state_dict(t.model.state_dict())
+    ref.train()
+    logits, v = ref(env.encode(buf.boards.reshape(n)))
+    valid = (buf.flags.reshape(n) & 0x80) != 0
+    loss, _ = ref_ppo_loss_torch(logits[valid], v[valid], buf.logp.reshape(n, 4)[valid], buf.actions.reshape(n)[valid],
+                                 buf.legal.reshape(n)[valid], adv["adv"].reshape(n)[valid], adv["g_norm"].reshape(n)[valid],
+                                 clip_eps=cfg.clip_eps, critic_strength=cfg.critic_strength, entropy_strength=cfg.entropy_strength)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    before = [p.detach().clone() for p in t.model.parameters()]
+    stats = t.update(buf, adv)                      # 4 chunks of 512 samples, gradient accumulated
+    assert abs(stats["loss"] - float(loss.detach())) <= 1e-4 * max(1.0, abs(float(loss.detach())))
+    for (name, p), q in zip(t.model.named_parameters(), ref.parameters()):
+        if q.grad is None:                          # init_hidden only feeds the truncated (no_grad) loop
+            assert name == "init_hidden" and (p.grad is None or not p.grad.any())
+            continue
+        assert p.grad is not None, name
+        torch.testing.assert_close(p.grad, q.grad, rtol=2e-3, atol=2e-5, msg=name)
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(before, t.model.parameters()))
+    s2 = t.train_step()
+    assert all(np.isfinite(s2[k]) for k in ("loss", "policy_loss", "value_loss", "entropy", "grad_norm"))
