@@ -129,7 +129,7 @@ class HostStepper:
     directions and the kernel overlap.  Same results as step(); this is the host-buffer entry point
     that bench.py's `e2e` figure measures."""
 
-    def __init__(self, n: int, *, device=None, chunk: int = 1 << 19, streams: int = 3, shaping: bool = True):
+    def __init__(self, n: int, *, device=None, chunk: int = 1 << 20, streams: int = 2, shaping: bool = True):
         self.n, self.chunk, self.shaping = n, min(chunk, max(n, 1)), shaping
         self.dev = init(device)
         self.table = lut(self.dev)
