@@ -452,6 +452,9 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
     from g2048 import env
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     hb, ha = c2_transitions(4242 + rank)
+    old_affinity = env.bind_host_thread_to_gpu(dev)      # pinned buffers next to the GPU (restored below)
+    print(f"[bench] rank {rank}: host thread bound to {len(os.sched_getaffinity(0))} of {os.cpu_count()} cpus for the e2e leg"
+          f" ({'NVML affinity' if old_affinity else 'unbound'})", file=sys.stderr)
     h_boards, h_actions = torch.from_numpy(hb).pin_memory(), torch.from_numpy(ha).pin_memory()
     h_out = dict(boards=torch.empty(N_TRANS, dtype=torch.int64).pin_memory(),
                  points=torch.empty(N_TRANS, dtype=torch.int32).pin_memory(),
@@ -478,6 +481,8 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = world * N_TRANS * e2e_steps / (e2e_ms * 1e-3)
+    if old_affinity:
+        os.sched_setaffinity(0, old_affinity)            # the cpu_baseline leg uses every core
     return e2e_value, e2e_ms, e2e_steps
 
 
