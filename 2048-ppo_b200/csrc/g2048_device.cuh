@@ -579,6 +579,11 @@ __device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint32_t v;
     asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(addr));
@@ -587,6 +592,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 struct DenseSmem {
     uint32_t m, s;         // shared-space byte addresses of the two tables
     __device__ __forceinline__ uint2 M(uint32_t byte_off) const { return lds_u64(m + byte_off); }
+    __device__ __forceinline__ uint32_t Mlo(uint32_t byte_off) const { return lds_u32(m + byte_off); }
     __device__ __forceinline__ uint32_t S(uint32_t byte_off) const { return lds_u16(s + byte_off); }
 };
 // the four S entries of a board's rows, summed.  The byte offsets (2 x index <= 57 120) fit the 16-bit lanes.
@@ -600,6 +606,8 @@ __device__ __forceinline__ uint32_t s_sum(Board x, const DenseSmem& tab) {
 // every line after it indexes S).  12 table reads: the 4 lines along the move axis (M: move result,
 // points, created tile, and the per-line potentials of the line before AND after the move), the 4
 // lines across it before the move (S) and after it (S).  Same results as env_step, bit for bit.
+// SHAPING = false (the caller passed no shaping array): only the 4 M reads, no potentials.
+template <bool SHAPING>
 __device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t mx_b, uint32_t action, uint32_t u0, uint32_t u1, const DenseSmem& tab) {
     StepOut o;
     const Board bt = transpose(b);
@@ -608,9 +616,16 @@ __device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t mx_b, uint32
     const Board along = horiz ? b : bt, cross = horiz ? bt : b;
     const Board canon = {rev_rows_if(along.lo, s4, sel), rev_rows_if(along.hi, s4, sel)};
     const uint32_t ia = dense2<12, DENSE_M_STRIDE>(canon.lo), ib = dense2<12, DENSE_M_STRIDE>(canon.hi);
-    const uint2 m0 = tab.M((ia << 3) & 0x7FFF8u), m1 = tab.M((ia >> 13) & 0x7FFF8u);
-    const uint2 m2 = tab.M((ib << 3) & 0x7FFF8u), m3 = tab.M((ib >> 13) & 0x7FFF8u);
-    const uint32_t cb = s_sum(cross, tab);
+    uint2 m0, m1, m2, m3;
+    if constexpr (SHAPING) {
+        m0 = tab.M((ia << 3) & 0x7FFF8u), m1 = tab.M((ia >> 13) & 0x7FFF8u);
+        m2 = tab.M((ib << 3) & 0x7FFF8u), m3 = tab.M((ib >> 13) & 0x7FFF8u);
+    } else {
+        m0 = make_uint2(tab.Mlo((ia << 3) & 0x7FFF8u), 0u), m1 = make_uint2(tab.Mlo((ia >> 13) & 0x7FFF8u), 0u);
+        m2 = make_uint2(tab.Mlo((ib << 3) & 0x7FFF8u), 0u), m3 = make_uint2(tab.Mlo((ib >> 13) & 0x7FFF8u), 0u);
+    }
+    uint32_t cb = 0u;
+    if constexpr (SHAPING) cb = s_sum(cross, tab);
     const Board moved_c = {__byte_perm(m0.x, m1.x, 0x5410), __byte_perm(m2.x, m3.x, 0x5410)};
     const bool valid = !same(moved_c, canon);                      // game.py:959
     // merge points and the largest exponent created (move table layout)
@@ -621,21 +636,26 @@ __device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t mx_b, uint32
     const Board un = {rev_rows_if(moved_c.lo, s4, sel), rev_rows_if(moved_c.hi, s4, sel)};
     const Board unt = transpose(un);
     const Board moved = horiz ? un : unt;
-    const uint32_t ca = s_sum(unt, tab);
-    // potentials of both boards at once: 16-bit lane 0 = before the move, lane 1 = after it
-    const uint32_t al = m0.y + m1.y + m2.y + m3.y;                 // lines along the move axis
-    const uint32_t cr = ca * 65536u + cb;                          // lines across it
-    const uint32_t pairs = __vmaxu2(al & 0x000F000Fu, (al >> 4) & 0x000F000Fu) +
-                           __vmaxu2(cr & 0x000F000Fu, (cr >> 4) & 0x000F000Fu);     // SURVEY A7, <= 24 per lane
-    const uint32_t smooth = ((al >> 8) & 0x00FF00FFu) + ((cr >> 8) & 0x00FF00FFu);    // <= 264 per lane
-    const uint32_t mx_a = max(mx_b, created);                      // a merge only ever raises the maximum
-    bool fc_b, ic_b, fc_a, ic_a;
-    corner_rules(b, mx_b, fc_b, ic_b);
-    corner_rules(moved, mx_a, fc_a, ic_a);
-    const uint32_t dbl = pairs + pairs, hlf = (pairs >> 1) & 0x000F000Fu;            // game.py:755-758
-    const uint32_t mono_b = (fc_b ? dbl : hlf) & 0x3Fu, mono_a = (fc_a ? dbl : hlf) >> 16;
-    const uint32_t smooth_b = smooth & 0xFFFFu, smooth_a = smooth >> 16;
-    const uint32_t empt_b = 16u - __popc(nz_flags8(b.lo)) - __popc(nz_flags8(b.hi));
+    uint32_t shape_lo = 0u, shape_hi = 0u;
+    if constexpr (SHAPING) {
+        const uint32_t ca = s_sum(unt, tab);
+        // potentials of both boards at once: 16-bit lane 0 = before the move, lane 1 = after it
+        const uint32_t al = m0.y + m1.y + m2.y + m3.y;                 // lines along the move axis
+        const uint32_t cr = ca * 65536u + cb;                          // lines across it
+        const uint32_t pairs = __vmaxu2(al & 0x000F000Fu, (al >> 4) & 0x000F000Fu) +
+                               __vmaxu2(cr & 0x000F000Fu, (cr >> 4) & 0x000F000Fu);     // SURVEY A7, <= 24 per lane
+        const uint32_t smooth = ((al >> 8) & 0x00FF00FFu) + ((cr >> 8) & 0x00FF00FFu);    // <= 264 per lane
+        const uint32_t mx_a = max(mx_b, created);                      // a merge only ever raises the maximum
+        bool fc_b, ic_b, fc_a, ic_a;
+        corner_rules(b, mx_b, fc_b, ic_b);
+        corner_rules(moved, mx_a, fc_a, ic_a);
+        const uint32_t dbl = pairs + pairs, hlf = (pairs >> 1) & 0x000F000Fu;            // game.py:755-758
+        const uint32_t mono_b = (fc_b ? dbl : hlf) & 0x3Fu, mono_a = (fc_a ? dbl : hlf) >> 16;
+        const uint32_t smooth_b = smooth & 0xFFFFu, smooth_a = smooth >> 16;
+        const uint32_t empt_b = 16u - __popc(nz_flags8(b.lo)) - __popc(nz_flags8(b.hi));
+        shape_lo = mono_b | mono_a << 6 | empt_b << 12 | created << 22 | mx_b << 27 | uint32_t(ic_b) << 31;   // + empt_a below
+        shape_hi = mx_a | uint32_t(ic_a) << 4 | smooth_b << 5 | smooth_a << 14;
+    }
     // spawn (game.py:923-940, as spawn_tile) -- its count of empty cells is emptiness_after
     const uint32_t zl = z_flags8(moved.lo) >> 3, zh = z_flags8(moved.hi) >> 3;
     const uint32_t pl = zl * 0x11111111u;
@@ -648,10 +668,8 @@ __device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t mx_b, uint32
     const uint32_t hit = z_flags8(p ^ (t * 0x11111111u)) & (z << 3);   // the empty nibble whose prefix count is t
     const uint32_t tile = (hit >> 3) * (u1 >= 3865470567u ? 2u : 1u);   // hit is one flag (none on a full board)
     const Board spawned = {moved.lo | (in_lo ? tile : 0u), moved.hi | (in_lo ? 0u : tile)};
-    uint32_t lo = mono_b | mono_a << 6 | empt_b << 12 | empt_a << 17 | created << 22 | mx_b << 27 | uint32_t(ic_b) << 31;
-    uint32_t hi = mx_a | uint32_t(ic_a) << 4 | smooth_b << 5 | smooth_a << 14;
-    o.shape_lo = valid ? lo : 0u;
-    o.shape_hi = valid ? hi : 0u;
+    o.shape_lo = (SHAPING && valid) ? (shape_lo | empt_a << 17) : 0u;
+    o.shape_hi = (SHAPING && valid) ? shape_hi : 0u;
     o.board = valid ? spawned : b;
     o.points = valid ? int(points) : 0;
     const uint32_t lm = legal_mask(o.board);                       // game.py:1006 / 963

@@ -136,23 +136,9 @@ __device__ __forceinline__ void step_loop(const uint32_t* slut, const uint32_t* 
     }
 }
 
+// Step (+ every shaping term when SHAPING) on the dense tables (M | S staged whole, 219 KiB; M alone without shaping):
+// persistent, one CTA per SM, one transition per thread and iteration.  Boards with a 4096+ tile take the general path through L2.
 template <bool SHAPING>
-__global__ void __launch_bounds__(STEP_THREADS, 1)
-step_kernel_staged(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
-                   int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
-                   const PhiloxKeys seed, uint64_t env0, uint64_t ctr) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ uint64_t bar;
-    uint32_t* slut = reinterpret_cast<uint32_t*>(smem_raw);
-    const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint64_t b0 = i0 < n ? __ldg(in + i0) : 0ull;                   // issued before the table staging wait
-    const uint32_t a0 = i0 < n ? __ldg(actions + i0) : 0u;
-    stage_lut(slut, glut, &bar);
-    step_loop<SHAPING, true>(slut, glut, in, actions, out, points, flags, shaping, n, replay, seed, env0, ctr, b0, a0);
-}
-
-// Step + every shaping term on the dense tables (M | S staged whole, 219 KiB): persistent, one CTA per SM,
-// one transition per thread and iteration.  Boards with a 4096+ tile take the general path through L2.
 __global__ void __launch_bounds__(STEP_THREADS, 1)
 step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict__ in, const uint8_t* __restrict__ actions,
                   uint64_t* __restrict__ out, int32_t* __restrict__ points, uint8_t* __restrict__ flags,
@@ -165,8 +151,8 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
     const uint32_t stride = gridDim.x * blockDim.x, n32 = uint32_t(n);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     pdl_launch_dependents();
-    stage_lut_issue<uint32_t(DENSE_BYTES)>(reinterpret_cast<uint32_t*>(smem_raw),
-                                           reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
+    stage_lut_issue<uint32_t(SHAPING ? DENSE_BYTES : DENSE_M_BYTES)>(      // S is only read for the potentials
+        reinterpret_cast<uint32_t*>(smem_raw), reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
     pdl_wait();
     uint64_t next_board = i < n32 ? __ldg(in + i) : 0ull;                 // in flight during the table staging wait
     uint32_t next_action = i < n32 ? __ldg(actions + i) : 0u;
@@ -192,12 +178,12 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
         }
         StepOut o;
         const uint32_t mx = max_nibble(b);
-        if (mx <= 11u) o = env_step_dense(b, mx, a, u0, u1, tab);
-        else o = env_step<true>(b, a, u0, u1, LutGlobal{glut});           // rare: a 4096+ tile on the board
+        if (mx <= 11u) o = env_step_dense<SHAPING>(b, mx, a, u0, u1, tab);
+        else o = env_step<SHAPING>(b, a, u0, u1, LutGlobal{glut});        // rare: a 4096+ tile on the board
         out[i] = pack_board(o.board);
         points[i] = o.points;
         flags[i] = uint8_t(o.flags);
-        shaping[i] = uint64_t(o.shape_lo) | uint64_t(o.shape_hi) << 32;
+        if (SHAPING) shaping[i] = uint64_t(o.shape_lo) | uint64_t(o.shape_hi) << 32;
     }
 }
 
@@ -557,22 +543,17 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
     G2048_REQUIRE(d_lut && boards_in && actions && boards_out && points && flags, "g2048_step: NULL pointer argument");
     const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
     cudaStream_t st = cudaStream_t(stream);
-    if (n >= STAGED_MIN_UNITS && shaping) {
-        G2048_CHECK_CUDA(ensure_smem(step_kernel_dense, DENSE_BYTES));
+    if (n >= STAGED_MIN_UNITS) {
+        auto kern = shaping ? step_kernel_dense<true> : step_kernel_dense<false>;
+        G2048_CHECK_CUDA(ensure_smem(kern, DENSE_BYTES));
         constexpr int64_t SPLIT = int64_t(1) << 30;               // the kernel indexes with 32 bits
         for (int64_t o = 0; o < n; o += SPLIT) {
             const int64_t m = n - o < SPLIT ? n - o : SPLIT;
-            G2048_CHECK_CUDA(launch_pdl(step_kernel_dense, num_sms(), STEP_THREADS, DENSE_BYTES, st, lut, boards_in + o, actions + o,
-                                        boards_out + o, points + o, flags + o, shaping + o, m,
+            G2048_CHECK_CUDA(launch_pdl(kern, num_sms(), STEP_THREADS, DENSE_BYTES, st, lut, boards_in + o, actions + o,
+                                        boards_out + o, points + o, flags + o, shaping ? shaping + o : static_cast<uint64_t*>(nullptr), m,
                                         replay ? replay + 2 * o : static_cast<const uint32_t*>(nullptr),
                                         philox_round_keys(seed), env0 + uint64_t(o), ctr));
         }
-    } else if (n >= STAGED_MIN_UNITS) {
-        auto kern = shaping ? step_kernel_staged<true> : step_kernel_staged<false>;
-        G2048_CHECK_CUDA(ensure_smem(kern, LUT_SMEM_BYTES));
-        kern<<<num_sms(), STEP_THREADS, LUT_SMEM_BYTES, st>>>(lut, boards_in, actions, boards_out, points, flags,
-                                                              shaping, n, replay, philox_round_keys(seed), env0, ctr);
-        G2048_CHECK_LAUNCH("step_kernel_staged");
     } else {
         auto kern = shaping ? step_kernel_direct<true> : step_kernel_direct<false>;
         kern<<<unsigned((n + 255) / 256), 256, 0, st>>>(lut, boards_in, actions, boards_out, points, flags, shaping, n,

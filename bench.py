@@ -360,6 +360,19 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * N_TRANS * args.steps / (ms * 1e-3)
 
+    # ---- the same step without the shaping record (shaping == NULL: 22 B / transition)
+    ns_out = [dict(boards=s["out"]["boards"], points=s["out"]["points"], flags=s["out"]["flags"]) for s in sets]
+    ns_graph = capture(lambda k: env.step(sets[k % RING]["boards"], sets[k % RING]["actions"], seed=2048, env0=env0, ctr=1 + k,
+                                          shaping=False, out=ns_out[k % RING]), args.steps)
+    barrier()
+    ev0.record()
+    ns_graph.replay()
+    ev1.record()
+    barrier()
+    ns_ms = ev0.elapsed_time(ev1) / args.steps
+    no_shaping = {"ms_per_launch": ns_ms, "bytes_per_transition": 22, "env_steps_per_sec": world * N_TRANS / (ns_ms * 1e-3),
+                  "achieved_gbs": 22 * N_TRANS / (ns_ms * 1e-3) / 1e9, "kernel": "step_kernel_dense<false>"}
+
     # ---- C2 in its 4-move expansion form (g2048_expand4: all four pre-spawn successors per board)
     ex_sets = [dict(succ=torch.empty((N_BOARDS, 4), dtype=torch.int64, device=dev),
                     points=torch.empty((N_BOARDS, 4), dtype=torch.int32, device=dev),
@@ -391,7 +404,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     ex2_ms = ev0.elapsed_time(ev1) / ex_steps
-    expand = {"ms_per_launch": ex_ms, "boards_per_launch": N_BOARDS, "ms_per_launch_on_post_step_boards": ex2_ms,
+    expand = {"no_shaping_step": no_shaping, "ms_per_launch": ex_ms, "boards_per_launch": N_BOARDS, "ms_per_launch_on_post_step_boards": ex2_ms,
               "transitions_per_sec": world * N_BOARDS * 4 / (ex_ms * 1e-3),
               "bytes_per_board": 57, "achieved_gbs": 57 * N_BOARDS / (ex_ms * 1e-3) / 1e9,
               "l2": "12 distinct input / output sets (57 MiB each) used round-robin"}
@@ -490,6 +503,8 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
     if True:
         peak, which = peaks()
         expand["frac_of_hbm_peak"] = expand["achieved_gbs"] / peak
+        no_shaping = expand.pop("no_shaping_step")
+        no_shaping["frac_of_hbm_peak"] = no_shaping["achieved_gbs"] / peak
         expand["large_batch"]["frac_of_hbm_peak"] = expand["large_batch"]["achieved_gbs"] / peak
         achieved = BYTES_PER_TRANSITION * N_TRANS / (ms_per_step * 1e-3) / 1e9
         line = {
@@ -508,6 +523,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
                          "peak_source": which, "kernel": "step_kernel_dense",
                          "bytes_per_unit": BYTES_PER_TRANSITION, "units_per_launch": N_TRANS},
         }
+        line["step_without_shaping"] = no_shaping
         line["expand4"] = expand
         if ro is not None:
             line["rollout"] = ro
