@@ -337,6 +337,7 @@ def run_ours(args):
         with torch.cuda.graph(graph):
             for k in range(count):
                 fn(k)
+        graph.replay()     # untimed: the first launch of a graph also uploads it to the device (~2 % of a 200-node replay)
         return graph
 
     for w in range(max(args.warmup, 3)):
@@ -513,7 +514,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step (move+merge points+shaping+Philox spawn+legal/done), one g2048_step launch",
                        "boards": N_BOARDS, "moves": MOVES, "l2": f"ring of {RING} distinct 120 MiB buffer sets (> 126 MB L2) used round-robin",
-                       "spawn": "philox4x32-10", "launch": "the K timed launches are replayed from one CUDA graph"},
+                       "spawn": "philox4x32-10", "launch": "the K timed launches are one replay of a CUDA graph (after one untimed replay that uploads it)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": (e2e_ms / e2e_steps) if e2e_steps else None},
