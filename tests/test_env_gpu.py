@@ -390,3 +390,38 @@ def test_facade_info_dict_is_complete(env):
                          "monotonicity_before", "monotonicity_after", "emptiness_before", "emptiness_after",
                          "topological_delta", "topological_anchor"}
     assert info["topological_anchor"] == (3, 3) and info["monotonicity_before"] == 30
+
+
+def test_dense_step_chain_back_to_back_and_in_place(env):
+    """Six consecutive g2048_step launches of the persistent dense kernel, each consuming the boards the previous
+    one wrote, issued back to back without a host sync (programmatic dependent launch: a launch stages its table
+    while its predecessor drains and must not read the boards before that one completed), out-of-place through
+    two buffers and in place.  Every step against the oracle."""
+    n = (1 << 17) + 5
+    boards = random_boards(n, 21)
+    rng = np.random.default_rng(21)
+    acts = [rng.integers(0, 4, n).astype(np.uint8) for _ in range(6)]
+    want = [boards]
+    for t, a in enumerate(acts):
+        want.append(O.step_batch(want[-1], a, seed=77, env0=3, ctr=10 + t)[0])
+    d_acts = [torch.from_numpy(a).cuda() for a in acts]
+    mk = lambda: dict(boards=torch.empty(n, dtype=torch.int64, device="cuda"), points=torch.empty(n, dtype=torch.int32, device="cuda"),
+                      flags=torch.empty(n, dtype=torch.uint8, device="cuda"), shaping=torch.empty(n, dtype=torch.int64, device="cuda"))
+    bufs = [mk(), mk()]
+    cur = dev_boards(boards)
+    snaps = []
+    torch.cuda.synchronize()
+    for t in range(6):
+        out = bufs[t % 2]
+        env.step(cur, d_acts[t], seed=77, env0=3, ctr=10 + t, out=out)
+        snaps.append(out["boards"].clone())         # stream-ordered copy between the launches
+        cur = out["boards"]
+    torch.cuda.synchronize()
+    for t in range(6):
+        np.testing.assert_array_equal(host_u64(snaps[t]), want[t + 1], err_msg=f"step {t}")
+    # in place: boards_out == boards_in
+    inplace = mk()
+    inplace["boards"].copy_(dev_boards(boards))
+    for t in range(6):
+        env.step(inplace["boards"], d_acts[t], seed=77, env0=3, ctr=10 + t, out=inplace)
+    np.testing.assert_array_equal(host_u64(inplace["boards"]), want[6])
