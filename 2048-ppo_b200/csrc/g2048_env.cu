@@ -245,9 +245,10 @@ __device__ __forceinline__ void expand4_loop(const uint32_t* slut, const uint32_
 #pragma unroll
         for (int d = 0; d < 4; ++d) lm |= same(s[d], b) ? 0u : (1u << d);
         // 4 successors = 32 contiguous bytes per board, 16 bytes of points
-        uint4* so = reinterpret_cast<uint4*>(succ + 4 * i);
-        so[0] = make_uint4(s[0].lo, s[0].hi, s[1].lo, s[1].hi);
-        so[1] = make_uint4(s[2].lo, s[2].hi, s[3].lo, s[3].hi);
+        // one 256-bit store: the warp writes its 1 KiB of successors with full sectors in one instruction
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(succ + 4 * i), "r"(s[0].lo), "r"(s[0].hi), "r"(s[1].lo),
+                     "r"(s[1].hi), "r"(s[2].lo), "r"(s[2].hi), "r"(s[3].lo), "r"(s[3].hi)
+                     : "memory");
         *reinterpret_cast<int4*>(points + 4 * i) = make_int4(p[0], p[1], p[2], p[3]);
         legal[i] = uint8_t(lm);
         if (max_tile)
