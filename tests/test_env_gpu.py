@@ -425,3 +425,33 @@ def test_dense_step_chain_back_to_back_and_in_place(env):
     for t in range(6):
         env.step(inplace["boards"], d_acts[t], seed=77, env0=3, ctr=10 + t, out=inplace)
     np.testing.assert_array_equal(host_u64(inplace["boards"]), want[6])
+
+
+def test_c2_full_size_step_matches_oracle_and_the_direct_kernel(env):
+    """BASELINE config C2 at its full size (2^20 boards x 4 moves = 4 194 304 transitions, Philox draws): the
+    persistent dense-table kernel against the oracle on every output, and against the direct kernel (row table
+    through L2, bit-parallel potentials: an independent implementation) run over the same transitions in chunks
+    below the staging threshold."""
+    nb = 1 << 20
+    b = random_boards(nb, 2048)
+    boards = np.tile(b, 4)
+    actions = np.repeat(np.arange(4, dtype=np.uint8), nb)
+    d_b, d_a = dev_boards(boards), torch.from_numpy(actions).cuda()
+    r = env.step(d_b, d_a, seed=2048, env0=0, ctr=1)
+    want_b, want = O.step_batch(boards, actions, seed=2048, env0=0, ctr=1)
+    assert want["overflow"].sum() == 0
+    np.testing.assert_array_equal(host_u64(r["boards"]), want_b)
+    np.testing.assert_array_equal(r["points"].cpu().numpy(), want["points"])
+    fl = r["flags"].cpu().numpy()
+    np.testing.assert_array_equal(fl & 0x0F, want["legal_after"])
+    np.testing.assert_array_equal((fl >> 4) & 1, want["done"])
+    np.testing.assert_array_equal((fl >> 5) & 1, want["invalid"])
+    sh = env.decode_shaping(r["shaping"].cpu().numpy())
+    for k in SH_KEYS:
+        np.testing.assert_array_equal(sh[k], want[k], err_msg=k)
+    chunk = 1 << 16
+    for lo in range(0, boards.size, chunk):
+        q = env.step(d_b[lo:lo + chunk], d_a[lo:lo + chunk], seed=2048, env0=lo, ctr=1)
+        for k in ("boards", "points", "flags", "shaping"):
+            assert torch.equal(q[k], r[k][lo:lo + chunk]), (k, lo)
+    assert int(r["points"].sum()) == int(want["points"].sum())
