@@ -28,6 +28,14 @@ constexpr int TC_SPLIT = 4;              // threads per env row (column quarters
 constexpr int TC_ENV_THREADS = 128 * TC_SPLIT;   // 16 warps: warp w owns lane quarter (w & 3) and column quarter (w >> 2)
 constexpr int TC_THREADS = TC_ENV_THREADS;   // env thread 0 doubles as the MMA issuer / weight producer
 constexpr uint32_t TC_X_COL = 256;      // TMEM column of the residual stream
+constexpr int TC_MAX_LAYERS = 6;        // LayerNorm parameter slots in shared memory (the fp32 kernel takes up to 8 blocks)
+
+// Per-env exchange between the four threads of a row during the policy / env-step tail of a step.
+struct TcXch {
+    uint64_t board;      // the board the step starts from (written by part 0 at the start of the step)
+    uint64_t moved;      // part 0 -> part 2: board after the move, before the spawn; then part 2 -> part 0: its potentials
+    uint32_t pb[2];      // part 1 -> part 0: potentials of `board`
+};
 
 template <int HP>
 struct TcSmem {
@@ -38,11 +46,12 @@ struct TcSmem {
     alignas(16) float b0[HP];
     alignas(16) float stem_g[HP];
     alignas(16) float stem_b[HP];
-    alignas(16) float ln_g[8][HP];
-    alignas(16) float ln_b[8][HP];
+    alignas(16) float ln_g[TC_MAX_LAYERS][HP];
+    alignas(16) float ln_b[TC_MAX_LAYERS][HP];
     alignas(16) float headw[5 * HP + 8];
     float red[2][TC_SPLIT][128];                    // [sum | sq][column part][row]
     float headp[TC_SPLIT - 1][128][5];             // partial head dots of parts 1..TC_SPLIT-1
+    TcXch xch[128];
     uint64_t a_ready, mma_done, b_full, stem_full;
     uint32_t tmem_base;
 };
@@ -172,6 +181,123 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
     }
 }
 
+// ------------------------------------------------------------------ policy / env-step tail, split over a row's threads
+// policy_env_step (g2048_rollout.cuh) is ~1 000 dependent instructions with three rounds of L2 table reads; run by
+// the owner thread alone it kept 12 of the 16 warps idle for a quarter of the kernel (ncu source view).  Here the
+// potentials of the current board (part 1) and of the moved board (part 2) run on the row's other threads while
+// part 0 samples, moves, spawns and computes the legal mask.  Same records, bit for bit.
+__device__ __forceinline__ uint2 pack_potentials(const Potentials& q) {
+    return make_uint2(uint32_t(q.mono) | uint32_t(q.empt) << 6 | uint32_t(q.max_exp) << 11 | uint32_t(q.in_corner) << 15,
+                      uint32_t(q.smooth_abs));
+}
+__device__ __forceinline__ uint2 board_potentials(Board b, const LutGlobal& lut) {
+    return pack_potentials(potentials(b, lookup_rows(b, lut), lookup_rows(transpose(b), lut)));
+}
+struct TailState {
+    float lp[4], e[4], mx, se, ent, value;
+    uint32_t a, u0, u1, lm;
+    Board moved;
+    int points, max_tile;
+    bool valid, ovf;
+    uint32_t flags;
+};
+// part 0, first third: masked log-softmax, sample, move (train.py:266-294 up to the move of game.py:952-1003)
+__device__ __forceinline__ void tail_sample_and_move(const RolloutParams& p, const LutGlobal& lut, int64_t ri, int64_t env, uint64_t ctr,
+                                                     uint32_t lm, const float (&o)[5], Board board, TailState& ts) {
+    // exp / log / divide as the hardware approximations (ex2 / lg2 / rcp, ~1e-6 relative): this kernel's logits
+    // already carry bf16 GEMM error (~1e-2); the fp32 kernel keeps expf / logf.  Only what the sample needs
+    // comes before the move; log-probs and entropy are finished in tail_spawn, off the critical path.
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if ((lm >> j) & 1u) mx = fmaxf(mx, o[j]);
+    float e[4], se = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        e[j] = ((lm >> j) & 1u) ? __expf(o[j] - mx) : 0.f;
+        se += e[j];
+        ts.lp[j] = o[j];
+        ts.e[j] = e[j];
+    }
+    ts.mx = mx;
+    ts.se = se;
+    const U4 d = env_draws(p.seed, p.env0 + uint64_t(env), ctr);
+    uint32_t a;
+    if (p.forced_actions) {
+        a = p.forced_actions[ri] & 3u;
+    } else {
+        const float thr = float(d.z >> 8) * (1.0f / 16777216.0f) * se;
+        float cum = 0.f;
+        a = 31u - uint32_t(__clz(int(lm)));
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cum += e[j];
+            if (!found && ((lm >> j) & 1u) && thr < cum) {
+                a = uint32_t(j);
+                found = true;
+            }
+        }
+    }
+    ts.a = a;
+    ts.u0 = d.x;
+    ts.u1 = d.y;
+    ts.lm = lm;
+    ts.value = o[4];
+    const Board bt = transpose(board);
+    const Board canon = to_canonical(board, bt, a);
+    const Lines mv = lookup_rows(canon, lut);
+    const Board moved_c = result_of(mv);
+    ts.valid = !same(moved_c, canon);
+    merge_stats(mv, ts.points, ts.max_tile, ts.ovf);
+    ts.moved = from_canonical(moved_c, a);
+}
+// part 0, second third: spawn, legal mask, flags (game.py:1005-1006)
+__device__ __forceinline__ Board tail_spawn(Board board, TailState& ts) {
+    // masked log-softmax and entropy (train.py:271-274, 290-291, 326) from the exponentials of tail_sample_and_move
+    const float lse = ts.mx + __logf(ts.se), inv = __fdividef(1.0f, ts.se);
+    ts.ent = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool legal = (ts.lm >> j) & 1u;
+        const float pj = ts.e[j] * inv;
+        ts.lp[j] = legal ? ts.lp[j] - lse : -INFINITY;
+        if (pj > 0.f) ts.ent -= pj * __logf(pj);
+    }
+    const Board spawned = spawn_tile(ts.moved, ts.u0, ts.u1);
+    const Board next = ts.valid ? spawned : board;
+    const uint32_t lm = legal_mask(next);
+    ts.flags = lm | (lm == 0u ? FLAG_DONE : 0u) | (ts.valid ? 0u : FLAG_INVALID) | ((ts.valid && ts.ovf) ? FLAG_OVERFLOW : 0u);
+    return next;
+}
+// part 0, last third: shaping record from the two potential words, the [t, env] record
+__device__ __forceinline__ void tail_record(const RolloutParams& p, int64_t ri, Board board, const TailState& ts, uint2 pb, uint2 pa) {
+    uint32_t lo = (pb.x & 63u) | (pa.x & 63u) << 6 | ((pb.x >> 6) & 31u) << 12 | ((pa.x >> 6) & 31u) << 17 | uint32_t(ts.max_tile) << 22 |
+                  ((pb.x >> 11) & 15u) << 27 | ((pb.x >> 15) & 1u) << 31;
+    uint32_t hi = ((pa.x >> 11) & 15u) | ((pa.x >> 15) & 1u) << 4 | pb.y << 5 | pa.y << 14;
+    if (!ts.valid) lo = hi = 0u;
+    p.rec_boards[ri] = pack_board(board);
+    p.rec_actions[ri] = uint8_t(ts.a);
+    p.rec_legal[ri] = uint8_t(ts.lm);
+    reinterpret_cast<float4*>(p.rec_logp)[ri] = make_float4(ts.lp[0], ts.lp[1], ts.lp[2], ts.lp[3]);
+    p.rec_value[ri] = ts.value;
+    p.rec_points[ri] = ts.valid ? ts.points : 0;
+    p.rec_shaping[ri] = uint64_t(lo) | uint64_t(hi) << 32;
+    p.rec_flags[ri] = uint8_t(ts.flags | 0x80u);
+    if (p.rec_entropy) p.rec_entropy[ri] = ts.ent;
+}
+__device__ __forceinline__ void tail_record_idle(const RolloutParams& p, int64_t ri, Board board) {
+    p.rec_flags[ri] = 0;
+    p.rec_boards[ri] = pack_board(board);
+    p.rec_actions[ri] = 0;
+    p.rec_legal[ri] = 0;
+    p.rec_value[ri] = 0.f;
+    p.rec_points[ri] = 0;
+    p.rec_shaping[ri] = 0;
+    reinterpret_cast<float4*>(p.rec_logp)[ri] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.rec_entropy) p.rec_entropy[ri] = 0.f;
+}
+
 // MMA issue + weight streaming, run by env thread 0 between its a_ready arrive and its mma_done wait.
 template <int HP>
 struct Issuer {
@@ -284,6 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_mlp_tc_kernel(RolloutPa
             uint32_t lm = 0;
             if (owner) lm = begin_step(p, env, ctr, board, alive);
             if (half == 0) {
+                S.xch[row].board = pack_board(board);            // read by part 1 in the tail of this step
                 // model input: 16 exponents as bf16 (exact) = units 0,1 of block 0; row/col features
                 // are folded into the stem bias b0
                 uint32_t w[8];
@@ -318,7 +445,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) rollout_mlp_tc_kernel(RolloutPa
                     epilogue<HP, false, false>(S, tmem_lane, row, half, h, nullptr, S.ln_g[s - 1], S.ln_b[s - 1], o);
                 }
             }
-            if (owner) policy_env_step(p, lut, t, env, ctr, lm, o, board, alive);
+            // ---- policy + env-step tail over the row's threads (see tail_* above); the barriers are taken by all 512
+            const int64_t ri = int64_t(t) * p.B + env;
+            TailState ts;
+            const bool act = owner && alive;
+            if (half == 1) {
+                const uint2 pb = board_potentials(make_board(S.xch[row].board), lut);
+                S.xch[row].pb[0] = pb.x;
+                S.xch[row].pb[1] = pb.y;
+            }
+            if (act) {
+                tail_sample_and_move(p, lut, ri, env, ctr, lm, o, board, ts);
+                S.xch[row].moved = pack_board(ts.moved);
+            }
+            env_sync();
+            if (half == 2) {
+                const uint2 pa = board_potentials(make_board(S.xch[row].moved), lut);
+                S.xch[row].moved = uint64_t(pa.x) | uint64_t(pa.y) << 32;
+            }
+            Board next = board;
+            if (act) next = tail_spawn(board, ts);
+            env_sync();
+            if (act) {
+                const uint64_t paw = S.xch[row].moved;
+                tail_record(p, ri, board, ts, make_uint2(S.xch[row].pb[0], S.xch[row].pb[1]), make_uint2(uint32_t(paw), uint32_t(paw >> 32)));
+                board = next;
+                if (ts.flags & FLAG_DONE) {
+                    if (p.auto_reset) board = reset_board(env_draws(p.seed ^ RESET_KEY_TWEAK, p.env0 + uint64_t(env), ctr));
+                    else alive = false;
+                }
+            } else if (owner) {
+                tail_record_idle(p, ri, board);
+            }
         }
         if (owner) {
             p.boards[env] = pack_board(board);
@@ -343,6 +501,9 @@ static int launch_tc(const RolloutParams& p, cudaStream_t st) {
 }
 
 int launch_rollout_tc(const RolloutParams& p, int HP, cudaStream_t st) {
+    if (p.layers > TC_MAX_LAYERS)
+        return fail(G2048_ESHAPE, "g2048_rollout_mlp: the tensor-core kernel takes at most %d residual blocks (got %d); use the fp32 kernel",
+                    TC_MAX_LAYERS, p.layers);
     switch (HP) {
         case 64: return launch_tc<64>(p, st);
         case 128: return launch_tc<128>(p, st);

@@ -43,6 +43,7 @@ _lib.register("g2048_urm_pack", [C.c_int32] + [C.c_void_p] * 16)
 _lib.register("g2048_rollout_urm", [C.POINTER(_RolloutStruct), C.c_int32, C.c_void_p])
 
 
+TC_MAX_LAYERS = 6      # residual blocks the tensor-core kernel keeps LayerNorm parameters for (fp32 kernel: 8)
 TC_MIN_ENVS = 16384   # "auto": envs per GPU from which the rollout GEMMs run on the tensor cores
 
 
@@ -160,7 +161,7 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
                            _dp(policy.weights), _dp(env.lut(dev)), _dp(boards), _dp(alive), _dp(forced_actions),
                            _dp(buf.boards), _dp(buf.actions), _dp(buf.legal), _dp(buf.logp), _dp(buf.value),
                            _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy),
-                           int(precision == "bf16" or (precision == "auto" and B >= TC_MIN_ENVS)), 0)
+                           int(precision == "bf16" or (precision == "auto" and B >= TC_MIN_ENVS and policy.layers <= TC_MAX_LAYERS)), 0)
         if policy.kind == "urm":
             _lib.call("g2048_rollout_urm", C.byref(s), policy.loops, _stream())
         else:
