@@ -324,3 +324,26 @@ def test_evaluate_reports_the_reference_metrics(golden, tmp_path):
     ck = torch.load(path, weights_only=False)
     assert set(ck) == {"model_state_dict", "config", "eval_avg_score", "train_step"} and ck["train_step"] == 7
     assert all(torch.equal(ck["model_state_dict"][k], v.cpu()) for k, v in m.state_dict().items())
+
+
+def test_tensor_core_rollout_forced_actions_and_idle_envs():
+    """Without auto-reset games end and their envs go idle (zero records); with forced actions the env path of
+    the tensor-core kernel (whose per-env tail is split over the four threads of a row) must write the same
+    integer records as the fp32 kernel, idle rows included."""
+    from g2048 import env, rollout
+    model = random_model(64, 1, seed=5)
+    pol = rollout.pack_policy(model)
+    B, T, seed = 200, 320, 11
+    start = env.reset(B, device=0, seed=seed, env0=3, ctr=0)
+    ones = lambda: torch.ones(B, dtype=torch.uint8, device="cuda")
+    a1, a2 = ones(), ones()
+    ref = rollout.rollout(pol, start.clone(), T, seed=seed, env0=3, ctr0=1, auto_reset=False, alive=a1, precision="fp32")
+    tcb = rollout.rollout(pol, start.clone(), T, seed=seed, env0=3, ctr0=1, auto_reset=False, alive=a2, precision="bf16",
+                          forced_actions=ref.actions.clone())
+    assert int(a1.sum()) < B, "the horizon should outlive some games"
+    assert torch.equal(a1, a2)
+    assert bool((ref.flags[-1] == 0).any()) and bool((ref.flags[0] & 0x80).all())
+    for name in ("boards", "actions", "legal", "points", "shaping", "flags"):
+        assert torch.equal(getattr(ref, name), getattr(tcb, name)), name
+    idle = ref.flags == 0
+    assert bool((tcb.value[idle] == 0).all()) and bool((tcb.logp[idle] == 0).all())
