@@ -120,7 +120,9 @@ __global__ void pack_kernel(PackSrc s, int L, float* __restrict__ out) {
     }
 }
 
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// x * sigmoid(x) with the hardware ex2 / rcp approximations (~1e-6 relative): the surrounding GEMM operands are bf16 (~4e-3), and
+// the IEEE divide + expf were a fifth of this kernel's instructions (ncu source view: 240 SiLUs per token and block)
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ void sync128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // write 8 consecutive K-elements [k0, k0+8) of this thread's A row (k0 % 8 == 0) as bf16
@@ -312,10 +314,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_urm_kernel(RolloutParams p
                             float den = 0.f;
 #pragma unroll
                             for (int j = 0; j < SEQ; ++j) {
-                                sc[j] = expf(sc[j] - mx);
+                                sc[j] = __expf(sc[j] - mx);
                                 den += sc[j];
                             }
-                            const float inv = 1.0f / den;
+                            const float inv = __fdividef(1.0f, den);
                             float o[HD];
 #pragma unroll
                             for (int d = 0; d < HD; ++d) o[d] = 0.f;
