@@ -272,7 +272,7 @@ def rollout_section(args, dev, world, rank, barrier):
                               "kernel": "rollout_mlp_kernel<208>"},
         "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
         "train_step_ms": step_ms,
-        "update": "update_mlp_kernel (one tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-bf16 x3 GEMMs) + x3_wgrad_kernel weight gradients, Muon+AdamW",
+        "update": "update_mlp_kernel (one tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-bf16 GEMMs: x6 forward, x3 backward) + x3_wgrad_kernel weight gradients, Muon+AdamW",
         "x3_autograd_update_variant": {"train_step_ms": x3_ms, "rollout_update_steps_per_sec": world * n_local / (x3_ms * 1e-3)},
         "cublas_fp32_update_variant": {"train_step_ms": fp32_ms, "rollout_update_steps_per_sec": world * n_local / (fp32_ms * 1e-3)},
         "cublas_tf32_update_variant": {"train_step_ms": tf32_ms, "rollout_update_steps_per_sec": world * n_local / (tf32_ms * 1e-3)},
