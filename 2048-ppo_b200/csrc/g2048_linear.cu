@@ -229,6 +229,8 @@ struct WgradBars {
     uint32_t tmem_base;
 };
 
+// DY_IMG / X_IMG: that operand is a bf16 hi|lo image (dy_hp / x_hp = its padded width) instead of row-major fp32
+template <bool DY_IMG, bool X_IMG>
 __global__ void __launch_bounds__(W_THREADS, 1)
 x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ partial, int64_t M, int N,
                 int K, int dy_hp, int x_hp) {
@@ -261,8 +263,12 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
 
     if (warp < W_EPI_WARP0) {
         // ---------------- loaders: group (warp / 8) takes the stages q = group, group + W_GROUPS, ...
+        // A matrix with hp > 0 is a bf16 hi|lo operand image written by update_mlp_kernel (store_image): its two
+        // parts of a stage are bulk-copied straight into the ring (no registers, no conversion); hp == 0 is
+        // row-major fp32, loaded, split and stored by the loader threads.
         constexpr int PER_WARP = W_UNITS / 8;     // 13
         const int wg = warp & 7;
+        const bool elected = wg == 0 && lane == 0;
         for (int q = warp >> 3; q < my_stages; q += W_GROUPS) {
             const int64_t sample0 = (s_begin + q) * W_ROWS;
             float4 v[PER_WARP];
@@ -270,24 +276,32 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
             for (int i = 0; i < PER_WARP; ++i) {
                 const int u = wg + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
                 const int row = rg * 8 + (lane >> 2), f = lane & 3, col = b * 16 + f * 4;
-                const int ld = mat ? K : N, hp = mat ? x_hp : dy_hp;
+                const int ld = mat ? K : N;
+                const bool img = mat ? X_IMG : DY_IMG;
                 const float* src = mat ? X : dY;
                 const int64_t s = sample0 + row;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (s < M && col < ld) {
-                    // hp > 0: the update kernel's tiled layout [tile][col / 8][row][8] with hp padded columns
-                    const float* a = hp ? src + (((s >> 7) * (hp >> 3) + (col >> 3)) * 128 + (s & 127)) * 8 + (col & 7)
-                                        : src + s * ld + col;
-                    v[i] = __ldg(reinterpret_cast<const float4*>(a));
-                }
+                if (!img && s < M && col < ld) v[i] = __ldg(reinterpret_cast<const float4*>(src + s * ld + col));
             }
             const int slot = q % W_STAGES;
             tc::mbar_wait(&S.empty[slot], (uint32_t(q / W_STAGES) & 1u) ^ 1u);
             uint8_t* dst = sW + uint32_t(slot) * W_STAGE;
+            if (elected) {
+#pragma unroll
+                for (int mat = 0; mat < 2; ++mat) {
+                    const int hp = mat ? x_hp : dy_hp;
+                    if (!(mat ? X_IMG : DY_IMG)) continue;
+                    const uint32_t part = uint32_t(hp >> 4) * W_BLOCK;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(mat ? X : dY) + size_t(s_begin + q) * 2u * part;
+                    tc::mbar_add_tx(&S.full[slot], 2u * part);          // this thread's own arrival follows below
+                    tc::bulk_g2s(dst + uint32_t(mat) * 2u * W_PART, src, part, &S.full[slot]);
+                    tc::bulk_g2s(dst + uint32_t(mat) * 2u * W_PART + W_PART, src + part, part, &S.full[slot]);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < PER_WARP; ++i) {
                 const int u = wg + 8 * i, mat = u / (W_UNITS / 2), rem = u % (W_UNITS / 2), rg = rem & 3, b = rem >> 2;
-                if (b >= (mat ? KPB : NPB)) continue;
+                if ((mat ? X_IMG : DY_IMG) || b >= (mat ? KPB : NPB)) continue;
                 const int row = rg * 8 + (lane >> 2), f = lane & 3;
                 uint2 hi, lo;
                 split4(v[i], hi, lo);
@@ -448,10 +462,12 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
     G2048_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "g2048_x3_wgrad: pointers must be 16-byte aligned");
     const int smem = int(W_STAGES * W_STAGE + sizeof(WgradBars) + 1024);
-    G2048_CHECK_CUDA(ensure_smem(x3_wgrad_kernel, smem));
     const int64_t stages = (M + W_ROWS - 1) / W_ROWS;
     const int grid = int(stages < num_sms() ? stages : num_sms());
-    x3_wgrad_kernel<<<grid, W_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
+    auto kern = dy_hp ? (x_hp ? x3_wgrad_kernel<true, true> : x3_wgrad_kernel<true, false>)
+                      : (x_hp ? x3_wgrad_kernel<false, true> : x3_wgrad_kernel<false, false>);
+    G2048_CHECK_CUDA(ensure_smem(kern, smem));
+    kern<<<grid, W_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
     G2048_CHECK_LAUNCH("x3_wgrad_kernel");
     x3_wgrad_reduce_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), dW, N, K, grid);
     G2048_CHECK_LAUNCH("x3_wgrad_reduce_kernel");

@@ -60,7 +60,7 @@ struct Params {
     float clip_eps, c_v, beta_ent, inv_n;
     const float* pf;              // fp32 section of the pack
     const uint8_t* img;           // weight k-blocks in consumption order
-    float* h_out;                 // [L+1][ntiles][HP/8][128][8]  (tiled, see st256)
+    float* h_out;                 // [L+1][ntiles] bf16 hi|lo operand images of 128 samples x HP (see store_image), 4 B / value
     float* dz_out;                // same layout
     float* dhead;                 // [n][8]: d loss / d (logits, V), 3 zero pads
     float* logits;                // [n][4] or NULL
@@ -112,8 +112,8 @@ __device__ __forceinline__ void red_add(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-// 8 consecutive columns (col % 8 == 0) of row `row` -> bf16 hi/lo operand bytes
-__device__ __forceinline__ void store_operand(Smem& S, int row, int col, const float* x) {
+// 8 consecutive fp32 values -> their bf16 hi / lo terms (x = hi + lo to 16 mantissa bits), packed 8 x bf16 = 16 bytes each
+__device__ __forceinline__ void split8(const float* x, uint4& hi4, uint4& lo4) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -123,9 +123,39 @@ __device__ __forceinline__ void store_operand(Smem& S, int row, int col, const f
         hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
         lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
     }
+    hi4 = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    lo4 = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// 8 consecutive columns (col % 8 == 0) of row `row` -> bf16 hi/lo operand bytes
+__device__ __forceinline__ void store_operand(Smem& S, int row, int col, const uint4& hi4, const uint4& lo4) {
     const uint32_t off = uint32_t(col >> 4) * 4096u + uint32_t(row) * 32u + uint32_t(((((col >> 3) & 1) ^ (row >> 2)) & 1) << 4);
-    *reinterpret_cast<uint4*>(S.A[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(S.A[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(S.A[0] + off) = hi4;
+    *reinterpret_cast<uint4*>(S.A[1] + off) = lo4;
+}
+__device__ __forceinline__ void store_operand(Smem& S, int row, int col, const float* x) {
+    uint4 hi4, lo4;
+    split8(x, hi4, lo4);
+    store_operand(S, row, col, hi4, lo4);
+}
+// The same two terms to HBM as the operand image x3_wgrad_kernel bulk-copies into its ring: per stage of 32 samples
+// [hi | lo][16-feature block][sample 0..31][32 B, the two 16-byte halves swapped on (sample >> 2) & 1] -- exactly the
+// bytes of a ring stage (g2048_linear.cu), so the weight-gradient kernel neither converts nor touches registers.
+// Same 4 bytes per value as fp32.  `tile_img` = image of this 128-sample tile.
+__device__ __forceinline__ void store_image(uint8_t* tile_img, int HP, int row, int col, const uint4& hi4, const uint4& lo4) {
+    const uint32_t part = uint32_t(HP >> 4) * 1024u, r = uint32_t(row & 31);
+    const uint32_t off = uint32_t(row >> 5) * 2u * part + uint32_t(col >> 4) * 1024u + r * 32u +
+                         uint32_t(((((col >> 3) & 1) ^ (r >> 2)) & 1) << 4);
+    *reinterpret_cast<uint4*>(tile_img + off) = hi4;
+    *reinterpret_cast<uint4*>(tile_img + off + part) = lo4;
+}
+// rows past the sample count are zero in the image: the weight-gradient kernel sums whole 32-sample stages
+__device__ __forceinline__ void store_image(uint8_t* tile_img, int HP, int row, int col, const uint4& hi4, const uint4& lo4, bool valid) {
+    if (valid) {
+        store_image(tile_img, HP, row, col, hi4, lo4);
+    } else {                                   // only in the last tile of a launch
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        store_image(tile_img, HP, row, col, zero, zero);
+    }
 }
 
 // third split term r = x - hi - lo of 8 consecutive columns -> the lo operand buffer (second MMA phase)
@@ -235,7 +265,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
         S.stats[l][1][c.row] = rstd;
     }
     // tiled addresses of (this row, column group 0); + 1024 floats per column group
-    float* hrow = p.h_out + ((size_t(l) * p.ntiles + c.tile) * (HP / 8) * 128 + c.row) * 8;
+    uint8_t* himg = reinterpret_cast<uint8_t*>(p.h_out) + (size_t(l) * p.ntiles + c.tile) * size_t(HP) * 512;   // 128 samples x HP x 4 B
     float* zrow = last ? nullptr : p.zscratch + ((size_t(blockIdx.x) * L + l) * (HP / 8) * 128 + c.row) * 8;
 #pragma unroll
     for (int q = 0; q < 5; ++q) o[q] = 0.f;
@@ -253,8 +283,10 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
             x[j] = STEM ? r : x[j] + r;
         }
         tc::tmem_st8(c.tX + uint32_t(8 * g), x);
-        store_operand(S, c.row, col, x);
-        if (c.valid && p.backward) st256(hrow + size_t(col) * 128, x);
+        uint4 hi4, lo4;
+        split8(x, hi4, lo4);
+        store_operand(S, c.row, col, hi4, lo4);
+        if (p.backward) store_image(himg, HP, c.row, col, hi4, lo4, c.valid);
         if (zrow && p.backward) st256(zrow + size_t(col) * 128, z);
         if (last) {
 #pragma unroll
@@ -346,7 +378,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
     tc::tmem_st_wait();
     const float m1 = exchange(S, 0, c.part, c.row, s1) * inv_h;
     const float m2 = exchange(S, 1, c.part, c.row, s2) * inv_h;
-    float* dzrow = p.dz_out + ((size_t(l) * p.ntiles + c.tile) * (HP / 8) * 128 + c.row) * 8;
+    uint8_t* dzimg = reinterpret_cast<uint8_t*>(p.dz_out) + (size_t(l) * p.ntiles + c.tile) * size_t(HP) * 512;
 #pragma unroll 1
     for (int g = 0; g < c.ng; ++g) {
         const int col = c.c0 + 8 * g;
@@ -358,8 +390,10 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
             const float t = (y > 0.f ? dh[j] : 0.f) * gam[8 * g + j];
             dz[j] = (col + j < h) ? rstd * (t - m1 - xh[j] * m2) : 0.f;
         }
-        if (c.valid) st256(dzrow + size_t(col) * 128, dz);
-        if (l > 0) store_operand(S, c.row, col, dz);
+        uint4 hi4, lo4;
+        split8(dz, hi4, lo4);
+        store_image(dzimg, HP, c.row, col, hi4, lo4, c.valid);
+        if (l > 0) store_operand(S, c.row, col, hi4, lo4);
     }
 }
 

@@ -83,8 +83,9 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 
 def wgrad_tiled(dy: torch.Tensor, x: torch.Tensor, m: int, n: int, k: int, dy_hp: int = 0, x_hp: int = 0) -> torch.Tensor:
-    """dy^T x over m samples where either operand may be in the fused update kernel's tiled layout
-    (`*_hp` = its padded column count, 0 = row-major [m, features])."""
+    """dy^T x over m samples where either operand may be a bf16 hi|lo operand image written by the fused update kernel
+    (`*_hp` = its padded column count; the kernel bulk-copies it straight into its operand ring), 0 = row-major fp32
+    [m, features] (loaded, split and stored by the loader warps)."""
     dev = init(dy.device)
     with torch.cuda.device(dev):
         if dev.index not in _WS:

@@ -119,7 +119,7 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
     assert old_logp.numel() == stride * n
     with torch.cuda.device(dev):
         hp, per_layer = (h + 15) // 16 * 16, (n + 127) // 128 * 128 * ((h + 15) // 16 * 16)
-        h_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)    # tiled, see untile()
+        h_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)    # bf16 hi|lo operand images (4 B / value), see untile()
         dz_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)
         dhead = torch.empty((n, 8), dtype=torch.float32, device=dev)
         ln_grad = torch.empty((L + 1, 2, h), dtype=torch.float32, device=dev)
@@ -161,7 +161,13 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
 
 
 def untile(t: torch.Tensor, n: int, h: int) -> torch.Tensor:
-    """[n, h] view-copy of a tensor in the kernel's tiled layout [tile][column group of 8][row 0..127][8]."""
+    """[n, h] fp32 copy of a tensor the fused kernel wrote as a bf16 hi|lo operand image: per tile of 128 samples
+    4 stages of 32 samples, each [hi | lo][16-feature block][sample][32 B with the 16-byte halves swapped on
+    (sample >> 2) & 1] (csrc/g2048_update_fused.cu store_image).  Returns hi + lo (16 mantissa bits of the value)."""
     hp = (h + 15) // 16 * 16
     tiles = (n + 127) // 128
-    return t.view(tiles, hp // 8, 128, 8).permute(0, 2, 1, 3).reshape(tiles * 128, hp)[:n, :h].contiguous()
+    x = t.contiguous().view(torch.uint8)[: tiles * 128 * hp * 4].view(torch.bfloat16).view(tiles, 4, 2, hp // 16, 32, 2, 8)
+    swap = ((torch.arange(32, device=t.device) >> 2) & 1).view(1, 1, 1, 1, 32, 1, 1).bool()
+    x = torch.where(swap, x.flip(-2), x)
+    v = x[:, :, 0].float() + x[:, :, 1].float()                      # [tiles, 4, blocks, 32, 2, 8]
+    return v.permute(0, 1, 3, 2, 4, 5).reshape(tiles * 128, hp)[:n, :h].contiguous()

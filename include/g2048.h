@@ -248,9 +248,10 @@ int g2048_x3_gemm(const float* A, const void* image, float* C, int64_t M, int32_
 int64_t g2048_x3_wgrad_workspace_bytes(void);
 int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                    void* stream);
-/* same, with either operand in the tiled layout g2048_update_mlp_fwd_bwd writes (h_out / dz_out):
- * [tile of 128 samples][column group of 8][sample in tile][8 floats], `*_hp` = padded column count of that
- * operand (hidden rounded up to 16), 0 = plain row-major. */
+/* same, with either operand as the bf16 hi|lo operand image g2048_update_mlp_fwd_bwd writes (h_out / dz_out, 4 bytes
+ * per value like fp32): per stage of 32 samples [hi | lo][16-feature block][sample 0..31][32 B, the two 16-byte halves
+ * swapped on (sample >> 2) & 1], rows past the sample count zero -- the bytes of the kernel's operand ring, which it
+ * fills by bulk copies.  `*_hp` = padded column count of that operand (hidden rounded up to 16), 0 = row-major fp32. */
 int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                          int32_t dy_hp, int32_t x_hp, void* stream);
 
@@ -260,8 +261,8 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
  * forward (game.py:1145-1220) from packed boards, the PPO-clip + critic + entropy terms (train.py:497-554)
  * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-bf16: three terms per
  * operand in the forward (fp32-grade pre-activations, ~1e-6), two in the backward (~1e-5).
- * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], fp32 in the
- * tiled layout of g2048_x3_wgrad_tiled (ceil(n/128) * 128 * HP floats per l, HP = hidden rounded up to 16),
+ * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], as the bf16 hi|lo
+ * operand images of g2048_x3_wgrad_tiled (ceil(n/128) * 128 * HP * 4 bytes per l, HP = hidden rounded up to 16),
  * plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0), row-major; then (g2048_x3_wgrad_tiled)
  *     d stem.0.weight        = wgrad(dz_out[0], g2048_encode(boards))        [hidden, 48]
  *     d backbone.l.mlp.0.w   = wgrad(dz_out[l+1], h_out[l])                  [hidden, hidden]
@@ -296,7 +297,7 @@ typedef struct G2048UpdateMlp {
     float inv_n;                   /* 1 / (global sample count of the minibatch): the loss is a mean (train.py:554) */
     const void* packed;            /* g2048_update_mlp_pack output */
     void* workspace;               /* g2048_update_mlp_workspace_bytes bytes */
-    float* h_out;                  /* [layers+1][ceil(n/128)*128*HP] tiled */
+    float* h_out;                  /* [layers+1][ceil(n/128)*128*HP*4 bytes] operand images */
     float* dz_out;                 /* same */
     float* dhead;                  /* [n][8] */
     float* logits;                 /* [n][4] or NULL */
