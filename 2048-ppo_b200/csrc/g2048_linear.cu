@@ -268,7 +268,6 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
         // row-major fp32, loaded, split and stored by the loader threads.
         constexpr int PER_WARP = W_UNITS / 8;     // 13
         const int wg = warp & 7;
-        const bool elected = wg == 0 && lane == 0;
         for (int q = warp >> 3; q < my_stages; q += W_GROUPS) {
             const int64_t sample0 = (s_begin + q) * W_ROWS;
             float4 v[PER_WARP];
@@ -286,16 +285,23 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
             const int slot = q % W_STAGES;
             tc::mbar_wait(&S.empty[slot], (uint32_t(q / W_STAGES) & 1u) ^ 1u);
             uint8_t* dst = sW + uint32_t(slot) * W_STAGE;
-            if (elected) {
+            if (wg == 0) {
+                // image operands: per 128-sample tile [hi | lo][16-feature block][sample 0..127][32 B] (the update kernel's
+                // operand tile, copy_out_tile); a stage takes the 1 KiB slice of its 32 samples from every block.  One
+                // copy per lane: lanes 0..12 the hi blocks, 13..25 the lo blocks.
+                const int64_t gstage = s_begin + q;
 #pragma unroll
                 for (int mat = 0; mat < 2; ++mat) {
-                    const int hp = mat ? x_hp : dy_hp;
                     if (!(mat ? X_IMG : DY_IMG)) continue;
-                    const uint32_t part = uint32_t(hp >> 4) * W_BLOCK;
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(mat ? X : dY) + size_t(s_begin + q) * 2u * part;
-                    tc::mbar_add_tx(&S.full[slot], 2u * part);          // this thread's own arrival follows below
-                    tc::bulk_g2s(dst + uint32_t(mat) * 2u * W_PART, src, part, &S.full[slot]);
-                    tc::bulk_g2s(dst + uint32_t(mat) * 2u * W_PART + W_PART, src + part, part, &S.full[slot]);
+                    const int kb = (mat ? x_hp : dy_hp) >> 4;
+                    if (lane == 0) tc::mbar_add_tx(&S.full[slot], uint32_t(2 * kb) * W_BLOCK);   // this warp's arrivals follow below
+                    if (lane < 2 * kb) {
+                        const int part = lane >= kb, b = lane - part * kb;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(mat ? X : dY) +
+                                             (size_t(gstage >> 2) * size_t(2 * kb) + size_t(part * kb + b)) * 4096u + size_t(gstage & 3) * 1024u;
+                        tc::bulk_g2s(dst + uint32_t(mat) * 2u * W_PART + uint32_t(part) * W_PART + uint32_t(b) * W_BLOCK, src, W_BLOCK,
+                                     &S.full[slot]);
+                    }
                 }
             }
 #pragma unroll

@@ -137,25 +137,16 @@ __device__ __forceinline__ void store_operand(Smem& S, int row, int col, const f
     split8(x, hi4, lo4);
     store_operand(S, row, col, hi4, lo4);
 }
-// The same two terms to HBM as the operand image x3_wgrad_kernel bulk-copies into its ring: per stage of 32 samples
-// [hi | lo][16-feature block][sample 0..31][32 B, the two 16-byte halves swapped on (sample >> 2) & 1] -- exactly the
-// bytes of a ring stage (g2048_linear.cu), so the weight-gradient kernel neither converts nor touches registers.
-// Same 4 bytes per value as fp32.  `tile_img` = image of this 128-sample tile.
-__device__ __forceinline__ void store_image(uint8_t* tile_img, int HP, int row, int col, const uint4& hi4, const uint4& lo4) {
-    const uint32_t part = uint32_t(HP >> 4) * 1024u, r = uint32_t(row & 31);
-    const uint32_t off = uint32_t(row >> 5) * 2u * part + uint32_t(col >> 4) * 1024u + r * 32u +
-                         uint32_t(((((col >> 3) & 1) ^ (r >> 2)) & 1) << 4);
-    *reinterpret_cast<uint4*>(tile_img + off) = hi4;
-    *reinterpret_cast<uint4*>(tile_img + off + part) = lo4;
-}
-// rows past the sample count are zero in the image: the weight-gradient kernel sums whole 32-sample stages
-__device__ __forceinline__ void store_image(uint8_t* tile_img, int HP, int row, int col, const uint4& hi4, const uint4& lo4, bool valid) {
-    if (valid) {
-        store_image(tile_img, HP, row, col, hi4, lo4);
-    } else {                                   // only in the last tile of a launch
-        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-        store_image(tile_img, HP, row, col, zero, zero);
-    }
+// The operand tile in shared memory ([hi | lo][16-feature block][sample 0..127][32 B], 13 x 4 KiB per part) doubles as
+// the tensor's image in HBM: x3_wgrad_kernel bulk-copies the 32-sample slices of its blocks straight into its ring, so
+// the weight-gradient pass neither converts nor touches registers, and this kernel writes h_l / dz_l with two bulk
+// copies per tile (full lines) instead of per-thread stores.  Rows past the sample count are zeroed on the way in
+// (the weight gradient sums whole stages).  Same 4 bytes per value as fp32.
+__device__ __forceinline__ void copy_out_tile(Smem& S, uint8_t* tile_img, int HP) {
+    const uint32_t part = uint32_t(HP >> 4) * 4096u;
+    tc::bulk_s2g(tile_img, S.A[0], part);
+    tc::bulk_s2g(tile_img + part, S.A[1], part);
+    tc::bulk_commit();
 }
 
 // third split term r = x - hi - lo of 8 consecutive columns -> the lo operand buffer (second MMA phase)
@@ -265,7 +256,6 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
         S.stats[l][1][c.row] = rstd;
     }
     // tiled addresses of (this row, column group 0); + 1024 floats per column group
-    uint8_t* himg = reinterpret_cast<uint8_t*>(p.h_out) + (size_t(l) * p.ntiles + c.tile) * size_t(HP) * 512;   // 128 samples x HP x 4 B
     float* zrow = last ? nullptr : p.zscratch + ((size_t(blockIdx.x) * L + l) * (HP / 8) * 128 + c.row) * 8;
 #pragma unroll
     for (int q = 0; q < 5; ++q) o[q] = 0.f;
@@ -285,8 +275,8 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
         tc::tmem_st8(c.tX + uint32_t(8 * g), x);
         uint4 hi4, lo4;
         split8(x, hi4, lo4);
+        if (!c.valid) hi4 = lo4 = make_uint4(0u, 0u, 0u, 0u);      // only in the last tile of a launch
         store_operand(S, c.row, col, hi4, lo4);
-        if (p.backward) store_image(himg, HP, c.row, col, hi4, lo4, c.valid);
         if (zrow && p.backward) st256(zrow + size_t(col) * 128, z);
         if (last) {
 #pragma unroll
@@ -297,6 +287,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
     }
     tc::tmem_st_wait();
     if (last) {
+        tc::fence_async_smem();      // the operand tile (h_L) is bulk-copied out after the next barrier
         // partial head dots of parts 1..3 -> part 0 (through the dhead buffer, free at this point)
         if (c.part != 0) {
 #pragma unroll
@@ -376,9 +367,9 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
         colsum4x2(scr, c.lane, gx + 4, gg + 4, lnp + col + 4, lnp + HP + col + 4);
     }
     tc::tmem_st_wait();
+    if (first && threadIdx.x == 0) tc::bulk_wait_read0();   // h_L has left the operand buffers (copy issued before pass A) before pass B writes dz_L there
     const float m1 = exchange(S, 0, c.part, c.row, s1) * inv_h;
     const float m2 = exchange(S, 1, c.part, c.row, s2) * inv_h;
-    uint8_t* dzimg = reinterpret_cast<uint8_t*>(p.dz_out) + (size_t(l) * p.ntiles + c.tile) * size_t(HP) * 512;
 #pragma unroll 1
     for (int g = 0; g < c.ng; ++g) {
         const int col = c.c0 + 8 * g;
@@ -392,8 +383,8 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
         }
         uint4 hi4, lo4;
         split8(dz, hi4, lo4);
-        store_image(dzimg, HP, c.row, col, hi4, lo4, c.valid);
-        if (l > 0) store_operand(S, c.row, col, hi4, lo4);
+        if (!c.valid) hi4 = lo4 = make_uint4(0u, 0u, 0u, 0u);
+        store_operand(S, c.row, col, hi4, lo4);                    // next MMA operand (l > 0) and the image of dz_l
     }
 }
 
@@ -484,13 +475,15 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
         //   ST_FWD2: the lo buffer now holds r             D += r*hi + hi*r
         //   ST_BWD : A = (hi, lo), 2-part weight blocks    D  = lo*hi + hi*lo + hi*hi
         enum { ST_STEM, ST_FWD1, ST_FWD2, ST_BWD };
-        auto run_stage = [&](int kblocks, int kind) {
+        // `img`: where the operand tile of this stage goes as a tensor image (h_{l-1} / dz_l), or nullptr
+        auto run_stage = [&](int kblocks, int kind, uint8_t* img) {
             tc::fence_async_smem();
             tc::fence_before_sync();
             tc::mbar_arrive(&S.a_ready);
             if (issuer) {
                 tc::mbar_wait(&S.a_ready, stage & 1u);
                 tc::fence_after_sync();
+                if (img) copy_out_tile(S, img, HP);
                 for (int j = 0; j < kblocks; ++j, ++bq) {
                     const uint32_t slot = bq % RING;
                     tc::mbar_wait(&S.b_full[slot], (bq / RING) & 1u);
@@ -518,6 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
                     }
                     tc::mma_commit(&S.b_empty[slot]);
                 }
+                if (img) tc::bulk_wait_read0();      // mma_done (below) releases the operand buffers to the row threads
                 tc::mma_commit(&S.mma_done);
             }
             if (producer) {
@@ -544,8 +538,13 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             c.valid = c.grow < p.n;
             // model input: the 16 exponents are exact in bf16 (k-block 0, hi part; row / column features
             // are folded into b0)
+            const uint64_t b_in = (c.part == 0 && c.valid) ? p.boards[c.grow] : 0ull;   // in flight during the wait below
+            if (p.backward && t > 0) {                 // the previous tile's dz_0 has left the operand buffers
+                if (issuer) tc::bulk_wait_read0();
+                row_sync();
+            }
             if (c.part == 0) {
-                const uint64_t b = c.valid ? p.boards[c.grow] : 0ull;
+                const uint64_t b = b_in;
                 float e[8];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -555,14 +554,18 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
                 }
             }
             float o[5];
-            run_stage(1, ST_STEM);
+            auto image = [&](float* base, int l) -> uint8_t* {      // image of tensor l of this tile: 128 samples x HP x 4 B
+                return p.backward ? reinterpret_cast<uint8_t*>(base) + (size_t(l) * p.ntiles + c.tile) * size_t(HP) * 512 : nullptr;
+            };
+            run_stage(1, ST_STEM, nullptr);
             fwd_epilogue<true>(S, p, c, 0, o);
             for (int l = 1; l <= L; ++l) {
-                run_stage(KB, ST_FWD1);
+                run_stage(KB, ST_FWD1, image(p.h_out, l - 1));     // the operand tile is h_{l-1}
                 write_residual_terms();
-                run_stage(KB, ST_FWD2);
+                run_stage(KB, ST_FWD2, nullptr);
                 fwd_epilogue<false>(S, p, c, l, o);
             }
+            if (issuer && p.backward) copy_out_tile(S, image(p.h_out, L), HP);   // h_L: ordered by the barriers of the last epilogue
             // ---- heads -> loss terms and their gradients (one thread per row)
             if (c.part == 0) {
                 float gl[4] = {0.f, 0.f, 0.f, 0.f}, dv = 0.f;
@@ -598,10 +601,15 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             // ---- backward-data
             bwd_epilogue(S, p, c, L, true);
             for (int l = L; l >= 1; --l) {
-                run_stage(KB, ST_BWD);                 // D = dz_l W_l
+                run_stage(KB, ST_BWD, image(p.dz_out, l));          // D = dz_l W_l; the operand tile is dz_l
                 bwd_epilogue(S, p, c, l - 1, false);
             }
+            // dz_0 has no MMA after it: copy it out between two barriers before the next tile's input overwrites block 0
+            tc::fence_async_smem();
+            row_sync();
+            if (issuer) copy_out_tile(S, image(p.dz_out, 0), HP);   // waited for at the top of the next tile
         }
+        if (issuer) tc::bulk_wait0();                  // every image is complete in HBM before the kernel ends
         // ---- per-CTA loss sums and head-bias gradients, fixed order
         if (p.backward) {
             row_sync();

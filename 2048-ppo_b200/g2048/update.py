@@ -162,12 +162,12 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
 
 def untile(t: torch.Tensor, n: int, h: int) -> torch.Tensor:
     """[n, h] fp32 copy of a tensor the fused kernel wrote as a bf16 hi|lo operand image: per tile of 128 samples
-    4 stages of 32 samples, each [hi | lo][16-feature block][sample][32 B with the 16-byte halves swapped on
-    (sample >> 2) & 1] (csrc/g2048_update_fused.cu store_image).  Returns hi + lo (16 mantissa bits of the value)."""
+    [hi | lo][16-feature block][sample 0..127][32 B with the 16-byte halves swapped on (sample >> 2) & 1]
+    (csrc/g2048_update_fused.cu copy_out_tile).  Returns hi + lo (16 mantissa bits of the value)."""
     hp = (h + 15) // 16 * 16
     tiles = (n + 127) // 128
-    x = t.contiguous().view(torch.uint8)[: tiles * 128 * hp * 4].view(torch.bfloat16).view(tiles, 4, 2, hp // 16, 32, 2, 8)
-    swap = ((torch.arange(32, device=t.device) >> 2) & 1).view(1, 1, 1, 1, 32, 1, 1).bool()
+    x = t.contiguous().view(torch.uint8)[: tiles * 128 * hp * 4].view(torch.bfloat16).view(tiles, 2, hp // 16, 128, 2, 8)
+    swap = ((torch.arange(128, device=t.device) >> 2) & 1).view(1, 1, 1, 128, 1, 1).bool()
     x = torch.where(swap, x.flip(-2), x)
-    v = x[:, :, 0].float() + x[:, :, 1].float()                      # [tiles, 4, blocks, 32, 2, 8]
-    return v.permute(0, 1, 3, 2, 4, 5).reshape(tiles * 128, hp)[:n, :h].contiguous()
+    v = x[:, 0].float() + x[:, 1].float()                            # [tiles, blocks, 128, 2, 8]
+    return v.permute(0, 2, 1, 3, 4).reshape(tiles * 128, hp)[:n, :h].contiguous()

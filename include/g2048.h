@@ -249,9 +249,9 @@ int64_t g2048_x3_wgrad_workspace_bytes(void);
 int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                    void* stream);
 /* same, with either operand as the bf16 hi|lo operand image g2048_update_mlp_fwd_bwd writes (h_out / dz_out, 4 bytes
- * per value like fp32): per stage of 32 samples [hi | lo][16-feature block][sample 0..31][32 B, the two 16-byte halves
- * swapped on (sample >> 2) & 1], rows past the sample count zero -- the bytes of the kernel's operand ring, which it
- * fills by bulk copies.  `*_hp` = padded column count of that operand (hidden rounded up to 16), 0 = row-major fp32. */
+ * per value like fp32): per tile of 128 samples [hi | lo][16-feature block][sample 0..127][32 B, the two 16-byte halves
+ * swapped on (sample >> 2) & 1], rows past the sample count zero -- the update kernel's own MMA operand tile, copied out
+ * by two bulk copies; the weight-gradient kernel bulk-copies the 32-sample slices of its blocks into its operand ring.  `*_hp` = padded column count of that operand (hidden rounded up to 16), 0 = row-major fp32. */
 int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                          int32_t dy_hp, int32_t x_hp, void* stream);
 

@@ -90,18 +90,18 @@ def test_linear_rejects_unsupported_inputs():
 
 
 def operand_image(x: torch.Tensor, hp: int) -> torch.Tensor:
-    """[m, f] fp32 -> the bf16 hi|lo operand image the fused update kernel writes (store_image) and x3_wgrad_kernel
-    bulk-copies: per stage of 32 samples [hi | lo][16-feature block][sample][32 B, halves swapped on (sample >> 2) & 1]."""
+    """[m, f] fp32 -> the bf16 hi|lo operand image the fused update kernel writes (copy_out_tile) and x3_wgrad_kernel
+    bulk-copies: per tile of 128 samples [hi | lo][16-feature block][sample][32 B, halves swapped on (sample >> 2) & 1]."""
     m, f = x.shape
-    stages = (m + 127) // 128 * 4
-    xp = torch.zeros((stages * 32, hp), dtype=torch.float32, device=x.device)
+    tiles = (m + 127) // 128
+    xp = torch.zeros((tiles * 128, hp), dtype=torch.float32, device=x.device)
     xp[:m, :f] = x
     hi = xp.bfloat16()
     lo = (xp - hi.float()).bfloat16()
-    parts = torch.stack([hi, lo], 0).view(2, stages, 32, hp // 16, 2, 8)          # [part, stage, row, block, half, 8]
-    swap = ((torch.arange(32, device=x.device) >> 2) & 1).view(1, 1, 32, 1, 1, 1).bool()
+    parts = torch.stack([hi, lo], 0).view(2, tiles, 128, hp // 16, 2, 8)          # [part, tile, row, block, half, 8]
+    swap = ((torch.arange(128, device=x.device) >> 2) & 1).view(1, 1, 128, 1, 1, 1).bool()
     parts = torch.where(swap, parts.flip(-2), parts)
-    img = parts.permute(1, 0, 3, 2, 4, 5).contiguous()                            # [stage, part, block, row, half, 8]
+    img = parts.permute(1, 0, 3, 2, 4, 5).contiguous()                            # [tile, part, block, row, half, 8]
     return img.view(torch.uint8).view(-1).view(torch.float32)
 
 
