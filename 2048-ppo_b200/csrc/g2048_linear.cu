@@ -229,8 +229,10 @@ struct WgradBars {
     uint32_t tmem_base;
 };
 
-// DY_IMG / X_IMG: that operand is a bf16 hi|lo image (dy_hp / x_hp = its padded width) instead of row-major fp32
-template <bool DY_IMG, bool X_IMG>
+// DY_IMG / X_IMG: that operand is a bf16 hi|lo image (dy_hp / x_hp = its padded width) instead of row-major fp32.
+// X_BOARDS: X is the model input of packed boards (uint64 per sample, K = 48): the features [exponent, row/3, col/3] per
+// cell (game.py:92-101) are formed in the loader's registers instead of being materialised by g2048_encode.
+template <bool DY_IMG, bool X_IMG, bool X_BOARDS = false>
 __global__ void __launch_bounds__(W_THREADS, 1)
 x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ partial, int64_t M, int N,
                 int K, int dy_hp, int x_hp) {
@@ -280,7 +282,23 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
                 const float* src = mat ? X : dY;
                 const int64_t s = sample0 + row;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!img && s < M && col < ld) v[i] = __ldg(reinterpret_cast<const float4*>(src + s * ld + col));
+                if (X_BOARDS && mat == 1) {
+                    if (s < M && col < 48) {
+                        const uint64_t board = __ldg(reinterpret_cast<const uint64_t*>(X) + s);
+                        float e[4];
+                        const uint32_t lo32 = uint32_t(board), hi32 = uint32_t(board >> 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t idx = uint32_t(col + j), cell = (idx * 43691u) >> 17, kind = idx - 3u * cell;   // idx / 3, idx < 48
+                            const uint32_t half = cell & 8u ? hi32 : lo32;
+                            const uint32_t pos = kind == 1u ? (cell >> 2) : (cell & 3u);
+                            // float(pos) / 3.0f as in g2048_encode, from constants
+                            const float pf = pos == 0u ? 0.0f : pos == 1u ? (1.0f / 3.0f) : pos == 2u ? (2.0f / 3.0f) : 1.0f;
+                            e[j] = kind == 0u ? float((half >> (4u * (cell & 7u))) & 15u) : pf;
+                        }
+                        v[i] = make_float4(e[0], e[1], e[2], e[3]);
+                    }
+                } else if (!img && s < M && col < ld) v[i] = __ldg(reinterpret_cast<const float4*>(src + s * ld + col));
             }
             const int slot = q % W_STAGES;
             tc::mbar_wait(&S.empty[slot], (uint32_t(q / W_STAGES) & 1u) ^ 1u);
@@ -455,7 +473,8 @@ int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, 
 int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                          int32_t dy_hp, int32_t x_hp, void* stream) {
     G2048_REQUIRE(M >= 0, "g2048_x3_wgrad: M < 0");
-    G2048_REQUIRE((dy_hp == 0 || (dy_hp % 16 == 0 && dy_hp >= N && dy_hp <= MAXF)) && (x_hp == 0 || (x_hp % 16 == 0 && x_hp >= K && x_hp <= MAXF)),
+    G2048_REQUIRE(x_hp >= 0 || K == 48, "g2048_x3_wgrad: x_hp < 0 (X = packed boards) needs K == 48");
+    G2048_REQUIRE((dy_hp == 0 || (dy_hp % 16 == 0 && dy_hp >= N && dy_hp <= MAXF)) && (x_hp <= 0 || (x_hp % 16 == 0 && x_hp >= K && x_hp <= MAXF)),
                   "g2048_x3_wgrad: tiled operands need a padded width that is a multiple of 16 in [features, 208]");
     G2048_REQUIRE(dW != nullptr, "g2048_x3_wgrad: dW is NULL");
     if (!feat_ok(N) || !feat_ok(K)) return fail(G2048_ESHAPE, "g2048_x3_wgrad: N=%d, K=%d must be multiples of 4 in [4,208]", N, K);
@@ -465,13 +484,14 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
         return G2048_OK;
     }
     G2048_REQUIRE(dY && X && workspace, "g2048_x3_wgrad: NULL pointer argument");
-    G2048_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+    G2048_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & (x_hp < 0 ? 7 : 15)) == 0 &&
                       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "g2048_x3_wgrad: pointers must be 16-byte aligned");
     const int smem = int(W_STAGES * W_STAGE + sizeof(WgradBars) + 1024);
     const int64_t stages = (M + W_ROWS - 1) / W_ROWS;
     const int grid = int(stages < num_sms() ? stages : num_sms());
-    auto kern = dy_hp ? (x_hp ? x3_wgrad_kernel<true, true> : x3_wgrad_kernel<true, false>)
-                      : (x_hp ? x3_wgrad_kernel<false, true> : x3_wgrad_kernel<false, false>);
+    auto kern = x_hp < 0 ? (dy_hp ? x3_wgrad_kernel<true, false, true> : x3_wgrad_kernel<false, false, true>)
+                : dy_hp  ? (x_hp ? x3_wgrad_kernel<true, true> : x3_wgrad_kernel<true, false>)
+                         : (x_hp ? x3_wgrad_kernel<false, true> : x3_wgrad_kernel<false, false>);
     G2048_CHECK_CUDA(ensure_smem(kern, smem));
     kern<<<grid, W_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
     G2048_CHECK_LAUNCH("x3_wgrad_kernel");

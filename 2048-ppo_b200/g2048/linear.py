@@ -85,7 +85,8 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 def wgrad_tiled(dy: torch.Tensor, x: torch.Tensor, m: int, n: int, k: int, dy_hp: int = 0, x_hp: int = 0) -> torch.Tensor:
     """dy^T x over m samples where either operand may be a bf16 hi|lo operand image written by the fused update kernel
     (`*_hp` = its padded column count; the kernel bulk-copies it straight into its operand ring), 0 = row-major fp32
-    [m, features] (loaded, split and stored by the loader warps)."""
+    [m, features] (loaded, split and stored by the loader warps); x_hp = -1: `x` is int64 packed boards [m] and k == 48 --
+    the model input [exponent, row/3, col/3] per cell is formed in the loader (no g2048_encode pass)."""
     dev = init(dy.device)
     with torch.cuda.device(dev):
         if dev.index not in _WS:

@@ -142,7 +142,7 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
         _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
         if n > 0:
             # weight gradients: reductions over samples on the tensor cores
-            _acc(model.stem[0].weight, linear.wgrad_tiled(dz_out[0], env.encode(boards), n, h, 48, dy_hp=hp))
+            _acc(model.stem[0].weight, linear.wgrad_tiled(dz_out[0], boards, n, h, 48, dy_hp=hp, x_hp=-1))   # X = the packed boards
             for l, blk in enumerate(model.backbone):
                 _acc(blk.mlp[0].weight, linear.wgrad_tiled(dz_out[l + 1], h_out[l], n, h, h, dy_hp=hp, x_hp=hp))
             dwh = linear.wgrad_tiled(dhead, h_out[L], n, 8, h, x_hp=hp)

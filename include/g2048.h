@@ -251,7 +251,9 @@ int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, 
 /* same, with either operand as the bf16 hi|lo operand image g2048_update_mlp_fwd_bwd writes (h_out / dz_out, 4 bytes
  * per value like fp32): per tile of 128 samples [hi | lo][16-feature block][sample 0..127][32 B, the two 16-byte halves
  * swapped on (sample >> 2) & 1], rows past the sample count zero -- the update kernel's own MMA operand tile, copied out
- * by two bulk copies; the weight-gradient kernel bulk-copies the 32-sample slices of its blocks into its operand ring.  `*_hp` = padded column count of that operand (hidden rounded up to 16), 0 = row-major fp32. */
+ * by two bulk copies; the weight-gradient kernel bulk-copies the 32-sample slices of its blocks into its operand ring.
+ * x_hp = -1: X is the array of packed boards (uint64 per sample) and K == 48: the model input of game.py:92-101 is formed
+ * in the kernel (the stem's weight gradient without a g2048_encode pass).  `*_hp` = padded column count of that operand (hidden rounded up to 16), 0 = row-major fp32. */
 int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                          int32_t dy_hp, int32_t x_hp, void* stream);
 

@@ -124,3 +124,19 @@ def test_wgrad_with_operand_images(m, n, k, dy_img, x_img):
     want = dy.double().T @ x.double()
     bound = 2e-5 * (dy.double().abs().T @ x.double().abs()) + 1e-9
     assert bool(((got.double() - want).abs() <= bound).all())
+
+
+@pytest.mark.parametrize("m,dy_img", [(1000, True), (70001, True), (4097, False)])
+def test_stem_wgrad_from_packed_boards(m, dy_img):
+    """x_hp = -1: X is the packed boards; the kernel forms the 48 model inputs itself (game.py:92-101) and must give
+    exactly what it gives on g2048_encode's output."""
+    from g2048 import env, linear
+    g = torch.Generator(device="cuda").manual_seed(m)
+    e = torch.randint(0, 16, (m, 16), generator=g, device="cuda", dtype=torch.int64)
+    boards = (e << (torch.arange(16, device="cuda") * 4)).sum(1)
+    dy = torch.randn((m, 196), generator=g, device="cuda") * 0.1
+    a = operand_image(dy, 208) if dy_img else dy
+    hp = 208 if dy_img else 0
+    want = linear.wgrad_tiled(a, env.encode(boards), m, 196, 48, dy_hp=hp)
+    got = linear.wgrad_tiled(a, boards, m, 196, 48, dy_hp=hp, x_hp=-1)
+    assert torch.equal(got, want)
