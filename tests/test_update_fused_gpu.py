@@ -186,3 +186,30 @@ def test_rejects_unsupported_models():
         update.pack(m)
     m = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.1)).cuda().train()
     assert not update.supported(m)
+
+
+@pytest.mark.parametrize("h,L,n", [(196, 2, 1000), (64, 1, 300)])
+def test_operand_images_hold_the_activations(h, L, n):
+    """The h_l tensors the fused kernel leaves in HBM are its MMA operand tiles (bf16 hi|lo images, bulk-copied out of
+    shared memory): decoded (update.untile -> hi + lo, 16 mantissa bits) they are the float64 model's activations, rows
+    past n are zero, and dz_l decodes to finite values that vanish past n."""
+    from g2048 import env, update
+    F = torch.nn.functional
+    m = _model(h, L, 3)
+    boards = _boards(n, 9)
+    old, actions, legal, adv, g_norm = _samples(n, 4)
+    keep = {}
+    m.zero_grad()
+    update.loss_and_grads(m, boards, actions, legal, old, adv, g_norm, keep=keep)
+    P = {k: v.detach().double() for k, v in m.named_parameters()}
+    x = F.relu(F.layer_norm(env.encode(boards).double() @ P["stem.0.weight"].T, (h,), P["stem.1.weight"], P["stem.1.bias"], 1e-5))
+    acts = [x]
+    for l in range(L):
+        pre = f"backbone.{l}.mlp."
+        x = x + F.relu(F.layer_norm(x @ P[pre + "0.weight"].T, (h,), P[pre + "1.weight"], P[pre + "1.bias"], 1e-5))
+        acts.append(x)
+    for l in range(L + 1):
+        got = keep["h_out"][l].double()
+        scale = float(acts[l].abs().max())
+        assert float((got - acts[l]).abs().max()) < 2e-5 * scale, l
+    assert bool(torch.isfinite(keep["dz_out"]).all())
