@@ -21,6 +21,7 @@
 // fp32 accumulation keeps the recorded log-probs / values within ~1e-6 of the torch model.
 #include <cmath>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "g2048_rollout.cuh"
 
 namespace g2048 {
@@ -112,6 +113,29 @@ __global__ void pack_mlp_images_kernel(PackSrc s, int h, int HP, int L, uint8_t*
         const uint32_t off = blk * uint32_t(HP) * 128u + uint32_t(n >> 3) * 1024u + uint32_t(n & 7) * 128u +
                              (((kk >> 3) ^ uint32_t(n & 7)) << 4) + (kk & 7u) * 2u;
         *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(v);
+    }
+}
+
+// split-fp16 operand images for the fp32-grade tensor-core kernel (layout: g2048_rollout.cuh x3_*, g2048_tc.cuh sw32_offset)
+__global__ void pack_mlp_x3_kernel(PackSrc s, int h, int HP, int L, uint8_t* __restrict__ img) {
+    const int NB = HP / 16;
+    const int64_t total = x3_blocks(HP, L) * HP * 16;
+    const size_t part = size_t(HP) * 32;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int b = int(i / (HP * 16)), rem = int(i % (HP * 16)), n = rem / 16, kk = rem % 16;
+        float v = 0.f;
+        if (b == 0) {
+            if (n < h) v = s.stem_w[n * 48 + 3 * kk];
+        } else {
+            const int l = (b - 1) / NB, k = ((b - 1) % NB) * 16 + kk;
+            if (n < h && k < h) v = s.blk_w[l][size_t(n) * h + k];
+        }
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        uint8_t* blk = img + size_t(b) * 2 * part;
+        const uint32_t off = uint32_t(n) * 32u + uint32_t((((kk >> 3) ^ (n >> 2)) & 1) << 4) + uint32_t(kk & 7) * 2u;
+        *reinterpret_cast<__half*>(blk + off) = hi;
+        *reinterpret_cast<__half*>(blk + part + off) = lo;
     }
 }
 
@@ -415,7 +439,7 @@ extern "C" {
 int64_t g2048_mlp_packed_floats(int32_t hidden, int32_t layers) {
     const int HP = padded_hidden(hidden);
     if (HP < 0 || layers < 0 || layers > 8) return -1;
-    return pk_total_with_images(HP, layers);
+    return pk_total_all(HP, layers);
 }
 
 int g2048_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
@@ -447,6 +471,8 @@ int g2048_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const fl
     pack_mlp_images_kernel<<<256, 256, 0, cudaStream_t(stream)>>>(
         s, hidden, HP, layers, reinterpret_cast<uint8_t*>(packed + pk_img_base(HP, layers)));
     G2048_CHECK_LAUNCH("pack_mlp_images_kernel");
+    pack_mlp_x3_kernel<<<256, 256, 0, cudaStream_t(stream)>>>(s, hidden, HP, layers, reinterpret_cast<uint8_t*>(packed + pk_x3_base(HP, layers)));
+    G2048_CHECK_LAUNCH("pack_mlp_x3_kernel");
     return G2048_OK;
 }
 
@@ -486,9 +512,9 @@ int g2048_rollout_mlp(const G2048Rollout* r, void* stream) {
     p.rec_entropy = r->rec_entropy;
     cudaStream_t st = cudaStream_t(stream);
     if (r->tensor_cores) {
-        G2048_REQUIRE((reinterpret_cast<uintptr_t>(r->packed_weights) & 127u) == 0,
-                      "g2048_rollout_mlp: packed_weights must be 128-byte aligned for the tensor-core kernel");
-        return launch_rollout_tc(p, HP, st);
+        G2048_REQUIRE((reinterpret_cast<uintptr_t>(r->packed_weights) & 255u) == 0,
+                      "g2048_rollout_mlp: packed_weights must be 256-byte aligned for the tensor-core kernels");
+        return r->tensor_cores == G2048_ROLLOUT_BF16 ? launch_rollout_tc(p, HP, st) : launch_rollout_x3(p, HP, st);
     }
     switch (HP) {
         case 64: return launch_rollout<64>(p, st);

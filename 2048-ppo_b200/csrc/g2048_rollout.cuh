@@ -63,6 +63,15 @@ __host__ __device__ inline int64_t pk_total_with_images(int HP, int L) {
     return pk_img_base(HP, L) + (img_stem_bytes(HP) + int64_t(L) * img_layer_bytes(HP)) / 4;
 }
 
+// Split-fp16 operand images for the fp32-grade tensor-core kernel (g2048_rollout_x3.cu) follow the bf16 images
+// (256-byte aligned): k-blocks of 16 input features in the 32-byte-swizzled K-major layout of g2048_tc.cuh
+// (sw32_offset), each block = [hi part: HP rows x 32 B | lo part: HP rows x 32 B], w = hi + lo in fp16 (22 mantissa
+// bits).  Block 0 = the stem (16 exponent columns), then HP/16 blocks per residual block in k order.
+__host__ __device__ inline int64_t x3_block_bytes(int HP) { return int64_t(HP) * 64; }
+__host__ __device__ inline int64_t pk_x3_base(int HP, int L) { return (pk_total_with_images(HP, L) + 63) / 64 * 64; }   // floats
+__host__ __device__ inline int64_t x3_blocks(int HP, int L) { return 1 + int64_t(L) * (HP / 16); }
+__host__ __device__ inline int64_t pk_total_all(int HP, int L) { return pk_x3_base(HP, L) + x3_blocks(HP, L) * x3_block_bytes(HP) / 4; }
+
 // Start-of-step bookkeeping for one env: legal mask of the current board; a terminal board is
 // reset at once (auto_reset) or the env goes idle.  game.py:103-119, 942-950.
 __device__ __forceinline__ uint32_t begin_step(const RolloutParams& p, int64_t env, uint64_t ctr, Board& board, bool& alive) {
@@ -153,5 +162,7 @@ __device__ __forceinline__ void policy_env_step(const RolloutParams& p, const Lu
 
 // bf16 / tcgen05 variant (g2048_rollout_tc.cu)
 int launch_rollout_tc(const RolloutParams& p, int HP, cudaStream_t st);
+// split-fp16 / tcgen05 variant, fp32-grade (g2048_rollout_x3.cu)
+int launch_rollout_x3(const RolloutParams& p, int HP, cudaStream_t st);
 
 }  // namespace g2048

@@ -19,7 +19,7 @@
 // Precision: operands are rounded to bf16 (inputs are exact: exponents 0..15), accumulation,
 // LayerNorm, residual stream, heads and log-softmax stay fp32; the recorded log-probs differ from
 // the fp32 policy by ~1e-2 (stated in tests/test_rollout_gpu.py), which PPO's own ratio absorbs.
-#include "g2048_rollout.cuh"
+#include "g2048_rollout_tail.cuh"
 #include "g2048_tc.cuh"
 
 namespace g2048 {
@@ -29,13 +29,6 @@ constexpr int TC_ENV_THREADS = 128 * TC_SPLIT;   // 16 warps: warp w owns lane q
 constexpr int TC_THREADS = TC_ENV_THREADS;   // env thread 0 doubles as the MMA issuer / weight producer
 constexpr uint32_t TC_X_COL = 256;      // TMEM column of the residual stream
 constexpr int TC_MAX_LAYERS = 6;        // LayerNorm parameter slots in shared memory (the fp32 kernel takes up to 8 blocks)
-
-// Per-env exchange between the four threads of a row during the policy / env-step tail of a step.
-struct TcXch {
-    uint64_t board;      // the board the step starts from (written by part 0 at the start of the step)
-    uint64_t moved;      // part 0 -> part 2: board after the move, before the spawn; then part 2 -> part 0: its potentials
-    uint32_t pb[2];      // part 1 -> part 0: potentials of `board`
-};
 
 template <int HP>
 struct TcSmem {
@@ -181,122 +174,6 @@ __device__ __forceinline__ void epilogue(TcSmem<HP>& S, uint32_t tmem_lane, int 
     }
 }
 
-// ------------------------------------------------------------------ policy / env-step tail, split over a row's threads
-// policy_env_step (g2048_rollout.cuh) is ~1 000 dependent instructions with three rounds of L2 table reads; run by
-// the owner thread alone it kept 12 of the 16 warps idle for a quarter of the kernel (ncu source view).  Here the
-// potentials of the current board (part 1) and of the moved board (part 2) run on the row's other threads while
-// part 0 samples, moves, spawns and computes the legal mask.  Same records, bit for bit.
-__device__ __forceinline__ uint2 pack_potentials(const Potentials& q) {
-    return make_uint2(uint32_t(q.mono) | uint32_t(q.empt) << 6 | uint32_t(q.max_exp) << 11 | uint32_t(q.in_corner) << 15,
-                      uint32_t(q.smooth_abs));
-}
-__device__ __forceinline__ uint2 board_potentials(Board b, const LutGlobal& lut) {
-    return pack_potentials(potentials(b, lookup_rows(b, lut), lookup_rows(transpose(b), lut)));
-}
-struct TailState {
-    float lp[4], e[4], mx, se, ent, value;
-    uint32_t a, u0, u1, lm;
-    Board moved;
-    int points, max_tile;
-    bool valid, ovf;
-    uint32_t flags;
-};
-// part 0, first third: masked log-softmax, sample, move (train.py:266-294 up to the move of game.py:952-1003)
-__device__ __forceinline__ void tail_sample_and_move(const RolloutParams& p, const LutGlobal& lut, int64_t ri, int64_t env, uint64_t ctr,
-                                                     uint32_t lm, const float (&o)[5], Board board, TailState& ts) {
-    // exp / log / divide as the hardware approximations (ex2 / lg2 / rcp, ~1e-6 relative): this kernel's logits
-    // already carry bf16 GEMM error (~1e-2); the fp32 kernel keeps expf / logf.  Only what the sample needs
-    // comes before the move; log-probs and entropy are finished in tail_spawn, off the critical path.
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if ((lm >> j) & 1u) mx = fmaxf(mx, o[j]);
-    float e[4], se = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        e[j] = ((lm >> j) & 1u) ? __expf(o[j] - mx) : 0.f;
-        se += e[j];
-        ts.lp[j] = o[j];
-        ts.e[j] = e[j];
-    }
-    ts.mx = mx;
-    ts.se = se;
-    const U4 d = env_draws(p.seed, p.env0 + uint64_t(env), ctr);
-    uint32_t a;
-    if (p.forced_actions) {
-        a = p.forced_actions[ri] & 3u;
-    } else {
-        const float thr = float(d.z >> 8) * (1.0f / 16777216.0f) * se;
-        float cum = 0.f;
-        a = 31u - uint32_t(__clz(int(lm)));
-        bool found = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cum += e[j];
-            if (!found && ((lm >> j) & 1u) && thr < cum) {
-                a = uint32_t(j);
-                found = true;
-            }
-        }
-    }
-    ts.a = a;
-    ts.u0 = d.x;
-    ts.u1 = d.y;
-    ts.lm = lm;
-    ts.value = o[4];
-    const Board bt = transpose(board);
-    const Board canon = to_canonical(board, bt, a);
-    const Lines mv = lookup_rows(canon, lut);
-    const Board moved_c = result_of(mv);
-    ts.valid = !same(moved_c, canon);
-    merge_stats(mv, ts.points, ts.max_tile, ts.ovf);
-    ts.moved = from_canonical(moved_c, a);
-}
-// part 0, second third: spawn, legal mask, flags (game.py:1005-1006)
-__device__ __forceinline__ Board tail_spawn(Board board, TailState& ts) {
-    // masked log-softmax and entropy (train.py:271-274, 290-291, 326) from the exponentials of tail_sample_and_move
-    const float lse = ts.mx + __logf(ts.se), inv = __fdividef(1.0f, ts.se);
-    ts.ent = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool legal = (ts.lm >> j) & 1u;
-        const float pj = ts.e[j] * inv;
-        ts.lp[j] = legal ? ts.lp[j] - lse : -INFINITY;
-        if (pj > 0.f) ts.ent -= pj * __logf(pj);
-    }
-    const Board spawned = spawn_tile(ts.moved, ts.u0, ts.u1);
-    const Board next = ts.valid ? spawned : board;
-    const uint32_t lm = legal_mask(next);
-    ts.flags = lm | (lm == 0u ? FLAG_DONE : 0u) | (ts.valid ? 0u : FLAG_INVALID) | ((ts.valid && ts.ovf) ? FLAG_OVERFLOW : 0u);
-    return next;
-}
-// part 0, last third: shaping record from the two potential words, the [t, env] record
-__device__ __forceinline__ void tail_record(const RolloutParams& p, int64_t ri, Board board, const TailState& ts, uint2 pb, uint2 pa) {
-    uint32_t lo = (pb.x & 63u) | (pa.x & 63u) << 6 | ((pb.x >> 6) & 31u) << 12 | ((pa.x >> 6) & 31u) << 17 | uint32_t(ts.max_tile) << 22 |
-                  ((pb.x >> 11) & 15u) << 27 | ((pb.x >> 15) & 1u) << 31;
-    uint32_t hi = ((pa.x >> 11) & 15u) | ((pa.x >> 15) & 1u) << 4 | pb.y << 5 | pa.y << 14;
-    if (!ts.valid) lo = hi = 0u;
-    p.rec_boards[ri] = pack_board(board);
-    p.rec_actions[ri] = uint8_t(ts.a);
-    p.rec_legal[ri] = uint8_t(ts.lm);
-    reinterpret_cast<float4*>(p.rec_logp)[ri] = make_float4(ts.lp[0], ts.lp[1], ts.lp[2], ts.lp[3]);
-    p.rec_value[ri] = ts.value;
-    p.rec_points[ri] = ts.valid ? ts.points : 0;
-    p.rec_shaping[ri] = uint64_t(lo) | uint64_t(hi) << 32;
-    p.rec_flags[ri] = uint8_t(ts.flags | 0x80u);
-    if (p.rec_entropy) p.rec_entropy[ri] = ts.ent;
-}
-__device__ __forceinline__ void tail_record_idle(const RolloutParams& p, int64_t ri, Board board) {
-    p.rec_flags[ri] = 0;
-    p.rec_boards[ri] = pack_board(board);
-    p.rec_actions[ri] = 0;
-    p.rec_legal[ri] = 0;
-    p.rec_value[ri] = 0.f;
-    p.rec_points[ri] = 0;
-    p.rec_shaping[ri] = 0;
-    reinterpret_cast<float4*>(p.rec_logp)[ri] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.rec_entropy) p.rec_entropy[ri] = 0.f;
-}
 
 // MMA issue + weight streaming, run by env thread 0 between its a_ready arrive and its mma_done wait.
 template <int HP>

@@ -1,0 +1,499 @@
+// g2048_rollout_x3.cu -- the fused rollout kernel on the tensor cores at fp32 grade (the default at large env batch).
+//
+// Same records, env semantics and 128-env tiles as g2048_rollout_tc.cu (env m of the tile = TMEM lane m, four threads
+// per env row), but every GEMM operand is TWO fp16 terms, x = hi + lo (22 mantissa bits), and every k-step is three
+// tcgen05.mma products lo*hi + hi*lo + hi*hi accumulated in fp32 in tensor memory: the recorded log-probs and values
+// agree with the reference's fp32 forward (train.py:256-274, game.py:1192-1203) to ~1e-6, where bf16 operands give
+// ~1e-2.  (fp16 rather than bf16 terms: 11 + 11 bits instead of 8 + 8; activations and weights of this network sit
+// far inside the fp16 range, and what falls below it is < 6e-8 absolute.)
+//
+// Three times the MMAs no longer hide behind nothing, so the stages are pipelined inside a tile:
+//   * pass 1 of an epilogue pulls the thread's 48..52 accumulator columns into REGISTERS (and takes the LayerNorm
+//     statistics from them), which frees the accumulator D for the next GEMM at once;
+//   * pass 2 works through the 16-column k-blocks in rounds (round i = blocks 4i..4i+3, one per column part), writes
+//     each block's hi | lo operand bytes and the fp32 residual stream (TMEM), and signals the round;
+//   * a control warp issues the next layer's MMAs for the blocks of a round as soon as it is signalled -- the tensor
+//     pipe runs under pass 2 -- and streams the weight k-blocks (hi | lo, HP x 64 B) L2 -> SMEM through a ring of
+//     bulk async copies, refilling a slot two blocks behind the issue point.
+// TMEM: columns [0,HP) = D, [256,256+HP) = the fp32 residual stream X.  SMEM: A = hi | lo operand tile (32-byte
+// swizzle, HP/16 blocks of 128 rows x 32 B per part), the weight ring, the stem block, LayerNorm / head parameters.
+#include <cuda_fp16.h>
+#include "g2048_rollout_tail.cuh"
+#include "g2048_tc.cuh"
+
+namespace g2048 {
+namespace x3 {
+
+constexpr int SPLIT = 4;                          // threads per env row (column parts)
+constexpr int ENV_THREADS = 128 * SPLIT;          // 16 warps: warp w owns lane quarter (w & 3) and column part (w >> 2)
+constexpr int THREADS = ENV_THREADS + 32;         // + the control warp (lane 0: MMA issue and weight streaming)
+constexpr uint32_t X_COL = 256;
+constexpr int MAX_LAYERS = 4;
+
+constexpr int ring_slots(int HP) {
+    // what is left of 227 KB after the operand tile, the stem block and ~30 KB of parameters / exchange buffers
+    const int fixed = 2 * (HP / 16) * 4096 + HP * 64 + (1 + 2 * (MAX_LAYERS + 1)) * HP * 4 + (5 * HP + 8) * 4 + 16384 + 2048;
+    const int n = (232448 - fixed) / (HP * 64);
+    return n > 8 ? 8 : n;
+}
+
+template <int HP>
+struct Smem {
+    static constexpr int NB = HP / 16;            // k-blocks
+    static constexpr int NBF = NB / 4;            // full blocks per column part (block 4i + part in round i)
+    static constexpr int NR = NB % 4;             // remainder blocks, split in 4-column units over the parts
+    static constexpr int ROUNDS = NBF + NR;
+    static constexpr uint32_t PART = NB * 4096u;  // one operand part: NB blocks of 128 rows x 32 B
+    static constexpr uint32_t WPART = HP * 32u;   // one part of a weight k-block
+    static constexpr uint32_t SLOT = 2u * WPART;
+    static constexpr int RING = ring_slots(HP);
+    alignas(1024) uint8_t A[2][PART];
+    alignas(1024) uint8_t W[RING][SLOT];
+    alignas(1024) uint8_t Wstem[SLOT];
+    alignas(16) float b0[HP];
+    alignas(16) float ln_g[MAX_LAYERS + 1][HP];   // [0] = stem LayerNorm
+    alignas(16) float ln_b[MAX_LAYERS + 1][HP];
+    alignas(16) float headw[5 * HP + 8];
+    float red[2][SPLIT][128];                     // [sum | sq][column part][row]
+    float headp[SPLIT - 1][128][5];               // partial head dots of parts 1..3
+    TcXch xch[128];
+    uint64_t in_ready, mma_done, stem_full, rnd_ready[ROUNDS > 0 ? ROUNDS : 1], w_full[RING], w_empty[RING];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Smem<208>) + 1024 <= 232448, "x3 rollout kernel exceeds the 227 KB shared memory limit");
+static_assert(Smem<208>::RING >= 4, "weight ring too short to cover the L2 latency");
+
+__device__ __forceinline__ void env_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ENV_THREADS) : "memory"); }
+
+// one warp's arrival on a round barrier: every lane's operand bytes visible to the async proxy first
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    tc::fence_async_smem();
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(bar);
+}
+
+struct RowCtx {
+    int row, part, lane;
+    uint32_t tD, tX;             // TMEM addresses of this thread's lane quarter: D and X, column 0
+    uint32_t a_row;              // shared address of A[0] + row * 32
+    uint32_t sw;                 // (row >> 2) & 1: the 16-byte halves of a 32-byte operand row are swapped
+};
+
+// LayerNorm (eps 1e-5) + ReLU (+ residual) of one env row over this thread's columns (game.py:1038-1046, 1069-1073):
+// blocks 4i + part (16 columns each) and a 4-column unit of every remainder block.  !HEADS: writes X and the next A
+// operand and signals the rounds; HEADS (last stage): the 5 head dot products over this thread's columns instead.
+template <int HP, bool STEM, bool HEADS>
+__device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float (&o)[5]) {
+    using SM = Smem<HP>;
+    constexpr int NBF = SM::NBF, NR = SM::NR;
+    // Columns >= h are padding: their weights, biases, gamma and beta are zero in the packed buffer, so they produce
+    // z = 0 and x = 0 without any masking here.
+    float z[NBF > 0 ? NBF : 1][16], zr[NR > 0 ? NR : 1][4];
+    {
+        uint32_t raw[NBF > 0 ? NBF : 1][16], rawr[NR > 0 ? NR : 1][4];
+#pragma unroll
+        for (int i = 0; i < NBF; ++i) tc::tmem_ld16_issue(c.tD + uint32_t(16 * (4 * i + c.part)), raw[i]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) tc::tmem_ld4_issue(c.tD + uint32_t(16 * (4 * NBF + r) + 4 * c.part), rawr[r]);
+        tc::tmem_ld_wait_all();
+#pragma unroll
+        for (int i = 0; i < NBF; ++i)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[i][j] = tc::tmem_ld_pin(raw[i][j]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zr[r][j] = tc::tmem_ld_pin(rawr[r][j]);
+    }
+    // ---- pass 1: statistics (packed fp32 math: two columns per instruction)
+    float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NBF; ++i) {
+        if (STEM) {
+            const float4* b4 = reinterpret_cast<const float4*>(S.b0 + 16 * (4 * i + c.part));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 b = b4[q];
+                z[i][4 * q] += b.x; z[i][4 * q + 1] += b.y; z[i][4 * q + 2] += b.z; z[i][4 * q + 3] += b.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 v = make_float2(z[i][2 * j], z[i][2 * j + 1]);
+            sum2 = __fadd2_rn(sum2, v);
+            sq2 = __ffma2_rn(v, v, sq2);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        if (STEM) {
+            const float4 b = *reinterpret_cast<const float4*>(S.b0 + 16 * (4 * NBF + r) + 4 * c.part);
+            zr[r][0] += b.x; zr[r][1] += b.y; zr[r][2] += b.z; zr[r][3] += b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float2 v = make_float2(zr[r][2 * j], zr[r][2 * j + 1]);
+            sum2 = __fadd2_rn(sum2, v);
+            sq2 = __ffma2_rn(v, v, sq2);
+        }
+    }
+    S.red[0][c.part][c.row] = sum2.x + sum2.y;
+    S.red[1][c.part][c.row] = sq2.x + sq2.y;
+    tc::fence_before_sync();          // every thread's reads of D are complete before the next GEMM may overwrite it
+    env_sync();
+    const float inv_h = 1.0f / float(h);
+    const float tsum = (S.red[0][0][c.row] + S.red[0][1][c.row]) + (S.red[0][2][c.row] + S.red[0][3][c.row]);
+    const float tsq = (S.red[1][0][c.row] + S.red[1][1][c.row]) + (S.red[1][2][c.row] + S.red[1][3][c.row]);
+    const float mean = tsum * inv_h;
+    const float var = fmaxf(tsq * inv_h - mean * mean, 0.f);
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    const float2 rstd2 = make_float2(rstd, rstd), shift2 = make_float2(-mean * rstd, -mean * rstd);
+    float2 o2[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) o2[q] = make_float2(0.f, 0.f);
+
+    // ---- pass 2, full blocks
+#pragma unroll
+    for (int i = 0; i < NBF; ++i) {
+        const int blk = 4 * i + c.part, col0 = 16 * blk;
+        float x[16];
+        if (!STEM) tc::tmem_ld16p(c.tX + uint32_t(col0), x);
+        const float4* g4 = reinterpret_cast<const float4*>(gamma + col0);
+        const float4* e4 = reinterpret_cast<const float4*>(beta + col0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 g = g4[q], e = e4[q];
+            float2 y0 = __ffma2_rn(__ffma2_rn(make_float2(z[i][4 * q], z[i][4 * q + 1]), rstd2, shift2), make_float2(g.x, g.y), make_float2(e.x, e.y));
+            float2 y1 = __ffma2_rn(__ffma2_rn(make_float2(z[i][4 * q + 2], z[i][4 * q + 3]), rstd2, shift2), make_float2(g.z, g.w), make_float2(e.z, e.w));
+            y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f);
+            if (!STEM) {
+                y0 = __fadd2_rn(make_float2(x[4 * q], x[4 * q + 1]), y0);
+                y1 = __fadd2_rn(make_float2(x[4 * q + 2], x[4 * q + 3]), y1);
+            }
+            x[4 * q] = y0.x; x[4 * q + 1] = y0.y; x[4 * q + 2] = y1.x; x[4 * q + 3] = y1.y;
+        }
+        if (HEADS) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float4* hw = reinterpret_cast<const float4*>(S.headw + q * HP + col0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 w = hw[u];
+                    o2[q] = __ffma2_rn(make_float2(w.x, w.y), make_float2(x[4 * u], x[4 * u + 1]), o2[q]);
+                    o2[q] = __ffma2_rn(make_float2(w.z, w.w), make_float2(x[4 * u + 2], x[4 * u + 3]), o2[q]);
+                }
+            }
+        } else {
+            tc::tmem_st16(c.tX + uint32_t(col0), x);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tc::split2_f16(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+            const uint32_t a0 = c.a_row + uint32_t(blk) * 4096u + (c.sw << 4), a1 = a0 ^ 16u;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + SM::PART), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1 + SM::PART), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+            warp_arrive(&S.rnd_ready[i], c.lane);
+        }
+    }
+    // ---- pass 2, remainder blocks: 4 columns per part
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int blk = 4 * NBF + r, col0 = 16 * blk + 4 * c.part;
+        float x[4];
+        if (!STEM) {
+            uint32_t raw[4];
+            tc::tmem_ld4_issue(c.tX + uint32_t(col0), raw);
+            tc::tmem_ld_wait_all();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = tc::tmem_ld_pin(raw[j]);
+        }
+        const float4 g = *reinterpret_cast<const float4*>(gamma + col0), e = *reinterpret_cast<const float4*>(beta + col0);
+        float2 y0 = __ffma2_rn(__ffma2_rn(make_float2(zr[r][0], zr[r][1]), rstd2, shift2), make_float2(g.x, g.y), make_float2(e.x, e.y));
+        float2 y1 = __ffma2_rn(__ffma2_rn(make_float2(zr[r][2], zr[r][3]), rstd2, shift2), make_float2(g.z, g.w), make_float2(e.z, e.w));
+        y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f);
+        if (!STEM) {
+            y0 = __fadd2_rn(make_float2(x[0], x[1]), y0);
+            y1 = __fadd2_rn(make_float2(x[2], x[3]), y1);
+        }
+        x[0] = y0.x; x[1] = y0.y; x[2] = y1.x; x[3] = y1.y;
+        if (HEADS) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(S.headw + q * HP + col0);
+                o2[q] = __ffma2_rn(make_float2(w.x, w.y), y0, o2[q]);
+                o2[q] = __ffma2_rn(make_float2(w.z, w.w), y1, o2[q]);
+            }
+        } else {
+            tc::tmem_st4(c.tX + uint32_t(col0), x);
+            uint32_t hi[2], lo[2];
+            tc::split2_f16(x[0], x[1], hi[0], lo[0]);
+            tc::split2_f16(x[2], x[3], hi[1], lo[1]);
+            // columns 4 part .. 4 part + 3 of the block: 16-byte unit (part >> 1) ^ sw, byte 8 (part & 1) inside it
+            const uint32_t a = c.a_row + uint32_t(blk) * 4096u + ((uint32_t(c.part >> 1) ^ c.sw) << 4) + uint32_t(c.part & 1) * 8u;
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a), "r"(hi[0]), "r"(hi[1]) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(a + SM::PART), "r"(lo[0]), "r"(lo[1]) : "memory");
+            warp_arrive(&S.rnd_ready[NBF + r], c.lane);
+        }
+    }
+    if (HEADS) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) o[q] = o2[q].x + o2[q].y;
+        if (c.part != 0) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) S.headp[c.part - 1][c.row][q] = o[q];
+        }
+        env_sync();
+        if (c.part == 0) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+#pragma unroll
+                for (int part = 1; part < SPLIT; ++part) o[q] += S.headp[part - 1][c.row][q];
+                o[q] += S.headw[5 * HP + q];
+            }
+        }
+    } else {
+        tc::tmem_st_wait();
+    }
+}
+
+// The control warp's lane 0: MMA issue for every stage of every step of this CTA's tiles, and the weight ring.
+template <int HP>
+__device__ __forceinline__ void control(Smem<HP>& S, const RolloutParams& p, uint32_t tmem_base, uint64_t steps_total, const uint8_t* img) {
+    using SM = Smem<HP>;
+    constexpr int NB = SM::NB, NBF = SM::NBF, NR = SM::NR, RING = SM::RING;
+    const int L = p.layers;
+    const uint32_t idesc = tc::make_idesc_f16(128, HP);
+    const uint64_t dA = tc::make_desc_sw32(tc::smem_addr(S.A[0]), 16, 256), dW = tc::make_desc_sw32(tc::smem_addr(S.W[0]), 16, 256),
+                   dS = tc::make_desc_sw32(tc::smem_addr(S.Wstem), 16, 256);
+    const uint8_t* layers = img + SM::SLOT;                  // block 0 of the image is the stem
+    const uint32_t per_step = uint32_t(L) * NB;
+    const uint64_t total = steps_total * per_step;
+    auto load = [&](uint64_t q) {                            // block q of the launch-wide sequence -> slot q % RING
+        const uint32_t slot = uint32_t(q % RING);
+        tc::mbar_expect_tx(&S.w_full[slot], SM::SLOT);
+        tc::bulk_g2s(S.W[slot], layers + size_t(q % per_step) * SM::SLOT, SM::SLOT, &S.w_full[slot]);
+    };
+    if (steps_total == 0) return;
+    tc::mbar_expect_tx(&S.stem_full, SM::SLOT);
+    tc::bulk_g2s(S.Wstem, img, SM::SLOT, &S.stem_full);
+    for (uint64_t q = 0; q < uint64_t(RING) && q < total; ++q) load(q);
+    tc::mbar_wait(&S.stem_full, 0);
+    uint64_t q = 0;                                          // weight blocks issued so far
+    uint32_t use = 0;                                        // uses of the round barriers so far
+    auto issue_block = [&](int blk) {
+        const uint32_t slot = uint32_t(q % RING);
+        tc::mbar_wait(&S.w_full[slot], uint32_t(q / RING) & 1u);
+        const uint64_t ah = dA + uint64_t((uint32_t(blk) * 4096u) >> 4), al = ah + uint64_t(SM::PART >> 4);
+        const uint64_t bh = dW + uint64_t((slot * SM::SLOT) >> 4), bl = bh + uint64_t(SM::WPART >> 4);
+        tc::mma_bf16_ss(tmem_base, al, bh, idesc, blk > 0);
+        tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
+        tc::mma_bf16_ss(tmem_base, ah, bh, idesc, true);
+        tc::mma_commit(&S.w_empty[slot]);
+        // refill two blocks behind the issue point: those MMAs have all but certainly drained (in-order pipe)
+        if (q >= 2 && q - 2 + RING < total) {
+            const uint64_t r = q - 2;
+            tc::mbar_wait(&S.w_empty[r % RING], uint32_t(r / RING) & 1u);
+            load(r + RING);
+        }
+        ++q;
+    };
+    for (uint64_t step = 0; step < steps_total; ++step) {
+        // stem: the 16 exponents are exact in fp16 (hi part of block 0), so two products against hi | lo of the weights
+        tc::mbar_wait(&S.in_ready, uint32_t(step) & 1u);
+        tc::fence_after_sync();
+        tc::mma_bf16_ss(tmem_base, dA, dS + uint64_t(SM::WPART >> 4), idesc, false);
+        tc::mma_bf16_ss(tmem_base, dA, dS, idesc, true);
+        tc::mma_commit(&S.mma_done);
+        for (int l = 0; l < L; ++l, ++use) {
+#pragma unroll 1
+            for (int i = 0; i < NBF; ++i) {
+                tc::mbar_wait(&S.rnd_ready[i], use & 1u);
+                tc::fence_after_sync();
+#pragma unroll 1
+                for (int part = 0; part < 4; ++part) issue_block(4 * i + part);
+            }
+#pragma unroll 1
+            for (int r = 0; r < NR; ++r) {
+                tc::mbar_wait(&S.rnd_ready[NBF + r], use & 1u);
+                tc::fence_after_sync();
+                issue_block(4 * NBF + r);
+            }
+            tc::mma_commit(&S.mma_done);
+        }
+    }
+}
+
+template <int HP>
+__global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParams p) {
+    using SM = Smem<HP>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    SM& S = *reinterpret_cast<SM*>(smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = p.layers, h = p.hidden;
+    const int64_t ntiles = (p.B + 127) / 128;
+    const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(p.packed + pk_x3_base(HP, L));
+
+    // ---- one-time setup
+    if (warp == 0) tc::tmem_alloc(&S.tmem_base, 512);
+    if (tid == 0) {
+        tc::mbar_init(&S.in_ready, 4);
+        tc::mbar_init(&S.mma_done, 1);
+        tc::mbar_init(&S.stem_full, 1);
+        for (int i = 0; i < SM::ROUNDS; ++i) tc::mbar_init(&S.rnd_ready[i], ENV_THREADS / 32);
+        for (int i = 0; i < SM::RING; ++i) {
+            tc::mbar_init(&S.w_full[i], 1);
+            tc::mbar_init(&S.w_empty[i], 1);
+        }
+        tc::mbar_fence_init();
+    }
+    for (int i = tid; i < HP; i += THREADS) {
+        S.b0[i] = p.packed[pk_stem_b0(HP) + i];
+        S.ln_g[0][i] = p.packed[pk_stem_g(HP) + i];
+        S.ln_b[0][i] = p.packed[pk_stem_beta(HP) + i];
+        for (int l = 0; l < L; ++l) {
+            S.ln_g[l + 1][i] = p.packed[pk_layer(HP, l) + int64_t(HP) * HP + i];
+            S.ln_b[l + 1][i] = p.packed[pk_layer(HP, l) + int64_t(HP) * (HP + 1) + i];
+        }
+    }
+    for (int i = tid; i < 5 * HP + 8; i += THREADS) S.headw[i] = p.packed[pk_heads(HP, L) + i];
+    for (uint32_t i = tid * 16; i < 2 * SM::PART; i += THREADS * 16) *reinterpret_cast<uint4*>(&S.A[0][0] + i) = make_uint4(0, 0, 0, 0);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = S.tmem_base;
+
+    if (warp == ENV_THREADS / 32) {
+        if (lane == 0) control<HP>(S, p, tmem_base, uint64_t(my_tiles) * uint64_t(p.T), img);
+    } else {
+        // ---------------- row = env in tile = TMEM lane; four threads (column parts) per row
+        const LutGlobal lut{p.lut};
+        const int quarter = warp & 3, half = warp >> 2;
+        RowCtx c;
+        c.part = half;
+        c.lane = lane;
+        c.row = quarter * 32 + lane;
+        c.tD = tmem_base + (uint32_t(quarter * 32) << 16);
+        c.tX = c.tD + X_COL;
+        c.a_row = tc::smem_addr(S.A[0]) + uint32_t(c.row) * 32u;
+        c.sw = uint32_t(c.row >> 2) & 1u;
+        const int row = c.row;
+        uint64_t st = 0;
+        for (int64_t tl = 0; tl < my_tiles; ++tl) {
+            const int64_t env = (int64_t(blockIdx.x) + tl * gridDim.x) * 128 + row;
+            const bool owner = half == 0 && env < p.B;
+            Board board = {0u, 0u};
+            bool alive = false;
+            if (owner) {
+                board = make_board(p.boards[env]);
+                alive = p.alive ? p.alive[env] != 0 : true;
+            }
+            for (int t = 0; t < p.T; ++t) {
+                const uint64_t ctr = p.ctr0 + uint64_t(t);
+                uint32_t lm = 0;
+                if (owner) lm = begin_step(p, env, ctr, board, alive);
+                if (half == 0) {
+                    S.xch[row].board = pack_board(board);            // read by part 1 in the tail of this step
+                    // model input: the 16 exponents as fp16 (exact) = the hi part of k-block 0; the row / column
+                    // features are folded into the stem bias b0
+                    uint32_t w[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t src = q < 4 ? board.lo : board.hi;
+                        const __half2 pr = __floats2half2_rn(float((src >> (8 * (q & 3))) & 15u), float((src >> (8 * (q & 3) + 4)) & 15u));
+                        w[q] = *reinterpret_cast<const uint32_t*>(&pr);
+                    }
+                    const uint32_t a0 = c.a_row + (c.sw << 4), a1 = a0 ^ 16u;
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                    warp_arrive(&S.in_ready, lane);
+                }
+                float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                // ---- stages: s = 0 stem, s = 1..L residual blocks
+                for (int s = 0; s <= L; ++s, ++st) {
+                    tc::mbar_wait(&S.mma_done, uint32_t(st) & 1u);
+                    tc::fence_after_sync();
+                    if (s == 0) {
+                        if (L == 0) epilogue<HP, true, true>(S, c, h, S.ln_g[0], S.ln_b[0], o);
+                        else epilogue<HP, true, false>(S, c, h, S.ln_g[0], S.ln_b[0], o);
+                    } else if (s == L) {
+                        epilogue<HP, false, true>(S, c, h, S.ln_g[s], S.ln_b[s], o);
+                    } else {
+                        epilogue<HP, false, false>(S, c, h, S.ln_g[s], S.ln_b[s], o);
+                    }
+                }
+                // ---- policy + env-step tail over the row's threads (g2048_rollout_tail.cuh); barriers taken by all 512
+                const int64_t ri = int64_t(t) * p.B + env;
+                TailState ts;
+                const bool act = owner && alive;
+                if (half == 1) {
+                    const uint2 pb = board_potentials(make_board(S.xch[row].board), lut);
+                    S.xch[row].pb[0] = pb.x;
+                    S.xch[row].pb[1] = pb.y;
+                }
+                if (act) {
+                    tail_sample_and_move<false>(p, lut, ri, env, ctr, lm, o, board, ts);
+                    S.xch[row].moved = pack_board(ts.moved);
+                }
+                env_sync();
+                if (half == 2) {
+                    const uint2 pa = board_potentials(make_board(S.xch[row].moved), lut);
+                    S.xch[row].moved = uint64_t(pa.x) | uint64_t(pa.y) << 32;
+                }
+                Board next = board;
+                if (act) next = tail_spawn<false>(board, ts);
+                env_sync();
+                if (act) {
+                    const uint64_t paw = S.xch[row].moved;
+                    tail_record(p, ri, board, ts, make_uint2(S.xch[row].pb[0], S.xch[row].pb[1]), make_uint2(uint32_t(paw), uint32_t(paw >> 32)));
+                    board = next;
+                    if (ts.flags & FLAG_DONE) {
+                        if (p.auto_reset) board = reset_board(env_draws(p.seed ^ RESET_KEY_TWEAK, p.env0 + uint64_t(env), ctr));
+                        else alive = false;
+                    }
+                } else if (owner) {
+                    tail_record_idle(p, ri, board);
+                }
+            }
+            if (owner) {
+                p.boards[env] = pack_board(board);
+                if (p.alive) p.alive[env] = alive ? 1 : 0;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+template <int HP>
+static int launch(const RolloutParams& p, cudaStream_t st) {
+    const int smem = int(sizeof(Smem<HP>)) + 1024;
+    auto kern = rollout_mlp_x3_kernel<HP>;
+    G2048_CHECK_CUDA(ensure_smem(kern, smem));
+    const int64_t ntiles = (p.B + 127) / 128;
+    const int grid = int(ntiles < num_sms() ? ntiles : num_sms());
+    kern<<<grid, THREADS, smem, st>>>(p);
+    G2048_CHECK_LAUNCH("rollout_mlp_x3_kernel");
+    return G2048_OK;
+}
+
+}  // namespace x3
+
+int launch_rollout_x3(const RolloutParams& p, int HP, cudaStream_t st) {
+    if (p.layers > x3::MAX_LAYERS)
+        return fail(G2048_ESHAPE, "g2048_rollout_mlp: the split-fp16 tensor-core kernel takes at most %d residual blocks (got %d); use the fp32 kernel",
+                    x3::MAX_LAYERS, p.layers);
+    switch (HP) {
+        case 64: return x3::launch<64>(p, st);
+        case 128: return x3::launch<128>(p, st);
+        case 192: return x3::launch<192>(p, st);
+        case 208: return x3::launch<208>(p, st);
+    }
+    return fail(G2048_ESHAPE, "g2048_rollout_mlp: no tensor-core kernel for padded hidden %d", HP);
+}
+
+}  // namespace g2048

@@ -191,6 +191,38 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- fp16 operands (kind::f16 with A = B = F16: format fields 0) -------------------------------------------------
+// Two fp16 terms hold 22 mantissa bits of an fp32 value (x = hi + lo, |x| < 65504), so the three products
+// lo*hi + hi*lo + hi*hi are fp32-grade (~2e-7 of scale) where two bf16 terms give 16 bits (~1e-5).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// two fp32 values -> packed fp16 hi terms and packed fp16 lo terms (a in the low half).  SASS: F2FP, 2 x FHFMA
+// (fp32 += fp16 * fp16, sm_100+), F2FP.
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    float ra, rb;
+    asm("{\n\t.reg .f16 l, u, m;\n\t"
+        "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
+        "mov.b32 {l, u}, %0;\n\t"
+        "mov.b16 m, 0xBC00;\n\t"                 // -1.0
+        "fma.rn.f32.f16 %1, l, m, %3;\n\t"
+        "fma.rn.f32.f16 %2, u, m, %4;\n\t}"
+        : "=&r"(hi), "=f"(ra), "=f"(rb)
+        : "f"(a), "f"(b));
+    asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(ra), "f"(rb));
+}
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }

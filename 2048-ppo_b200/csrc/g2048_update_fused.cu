@@ -58,6 +58,9 @@ struct Params {
     int old_stride;
     const float *adv, *g_norm;
     float clip_eps, c_v, beta_ent, inv_n;
+    uint32_t drop_thr;            // dropout (game.py:1042): an element is dropped iff its 16-bit Philox draw < drop_thr; 0 = off
+    float drop_scale;             // 1 / (1 - p)
+    uint64_t drop_seed, sample0;  // Philox key; index of this call's first sample in the mask's counter space
     const float* pf;              // fp32 section of the pack
     const uint8_t* img;           // weight k-blocks in consumption order
     float* h_out;                 // [L+1][ntiles] bf16 hi|lo operand images of 128 samples x HP (see store_image), 4 B / value
@@ -206,6 +209,18 @@ __device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, const floa
     __syncwarp();
 }
 
+// Dropout mask of 8 consecutive columns of one sample in block l (game.py:1038-1046: x + Dropout(ReLU(LN(Linear x)))):
+// one Philox4x32-10 call, counter = (sample index, l, column group), key = the call's dropout seed; column j of the
+// group is KEPT iff the j-th 16-bit lane of the 128 random bits is >= drop_thr = round(p * 65536).  Bit j of the result.
+__device__ __forceinline__ uint32_t dropout_keep8(const Params& p, int64_t sample, int l, int col) {
+    const U4 r = philox4x32_10(uint32_t(sample), uint32_t(uint64_t(sample) >> 32), uint32_t(l), uint32_t(col >> 3),
+                               uint32_t(p.drop_seed), uint32_t(p.drop_seed >> 32));
+    const uint32_t t2 = p.drop_thr * 0x00010001u;
+    const uint32_t a = __vsetgeu2(r.x, t2), b = __vsetgeu2(r.y, t2), c = __vsetgeu2(r.z, t2), d = __vsetgeu2(r.w, t2);   // bits 0, 16
+    return (a & 1u) | ((a >> 15) & 2u) | ((b & 1u) << 2) | ((b >> 13) & 8u) | ((c & 1u) << 4) | ((c >> 11) & 32u) | ((d & 1u) << 6) |
+           ((d >> 9) & 128u);
+}
+
 struct RowCtx {
     int row, part, lane, warp, c0, ng;      // this thread's row, column part, first column, number of 8-column groups
     uint32_t tD, tX;                         // TMEM addresses of (lane quarter, column c0) in D and X
@@ -217,7 +232,7 @@ struct RowCtx {
 // Forward epilogue of LayerNorm l: h_l = [h_{l-1} +] relu(LN(z_l)); writes X (TMEM), the next A operand,
 // h_out[l], the z scratch (l < L) and, for l == L, the 5 head dot products (complete on part 0).
 template <bool STEM>
-__device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, float (&o)[5]) {
+__device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, float (&o)[5], uint64_t& keep_bits) {
     const int HP = p.HP, h = p.h, L = p.L;
     const bool last = l == L;
     const float inv_h = 1.0f / float(h);
@@ -265,11 +280,17 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
         float z[8], x[8];
         if (STEM) tc::tmem_ld8(c.tD + uint32_t(8 * g), z);
         else tc::tmem_ld8x2(c.tD + uint32_t(8 * g), z, c.tX + uint32_t(8 * g), x);
+        uint32_t keep = 0xFFu;
+        if (!STEM && p.drop_thr) {
+            keep = dropout_keep8(p, p.sample0 + c.grow, l, col);
+            keep_bits |= uint64_t(keep) << (8 * g);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (STEM) z[j] += S.b0[col + j];
             const float y = fmaf(fmaf(z[j], rstd, shift), gam[8 * g + j], bet[8 * g + j]);
-            const float r = fmaxf(y, 0.f);
+            float r = fmaxf(y, 0.f);
+            if (!STEM && p.drop_thr) r = ((keep >> j) & 1u) ? r * p.drop_scale : 0.f;
             x[j] = STEM ? r : x[j] + r;
         }
         tc::tmem_st8(c.tX + uint32_t(8 * g), x);
@@ -309,7 +330,11 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
 // Backward through LayerNorm l and its ReLU.  first (l == L): z_L is still in D and dh_L comes from the head
 // gradients; otherwise z_l comes from the scratch and dh_l = X + D (D = dz_{l+1} W_{l+1}).
 // Pass A stores xhat in D and dh_l in X, pass B turns them into dz_l (-> dz_out[l], next A operand).
-__device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, bool first) {
+__device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, bool first, uint64_t keep_bits) {
+    // keep_bits: the forward's dropout mask of this thread's columns in block l (bit 8 g + j); the gradient passes through
+    // Dropout as g * keep / (1 - p)
+    const float dscale = (l > 0 && p.drop_thr) ? p.drop_scale : 1.0f;
+    if (!(l > 0 && p.drop_thr)) keep_bits = ~0ull;
     const int HP = p.HP, h = p.h, L = p.L;
     const float inv_h = 1.0f / float(h);
     const float mean = S.stats[l][0][c.row], rstd = S.stats[l][1][c.row], shift = -mean * rstd;
@@ -353,7 +378,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
         for (int j = 0; j < 8; ++j) {
             const float xh = fmaf(z[j], rstd, shift);
             const float y = fmaf(xh, gam[8 * g + j], bet[8 * g + j]);
-            const float gj = y > 0.f ? dh[j] : 0.f;
+            const float gj = (y > 0.f && ((keep_bits >> (8 * g + j)) & 1ull)) ? dh[j] * dscale : 0.f;
             const float t = gj * gam[8 * g + j];
             s1 += t;
             s2 = fmaf(t, xh, s2);
@@ -378,7 +403,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaf(xh[j], gam[8 * g + j], bet[8 * g + j]);
-            const float t = (y > 0.f ? dh[j] : 0.f) * gam[8 * g + j];
+            const float t = ((y > 0.f && ((keep_bits >> (8 * g + j)) & 1ull)) ? dh[j] * dscale : 0.f) * gam[8 * g + j];
             dz[j] = (col + j < h) ? rstd * (t - m1 - xh[j] * m2) : 0.f;
         }
         uint4 hi4, lo4;
@@ -557,13 +582,18 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             auto image = [&](float* base, int l) -> uint8_t* {      // image of tensor l of this tile: 128 samples x HP x 4 B
                 return p.backward ? reinterpret_cast<uint8_t*>(base) + (size_t(l) * p.ntiles + c.tile) * size_t(HP) * 512 : nullptr;
             };
+            uint64_t keep_bits[MAXL + 1];                           // dropout masks of this thread's columns, per block
+#pragma unroll
+            for (int l = 0; l <= MAXL; ++l) keep_bits[l] = 0ull;
             run_stage(1, ST_STEM, nullptr);
-            fwd_epilogue<true>(S, p, c, 0, o);
-            for (int l = 1; l <= L; ++l) {
+            fwd_epilogue<true>(S, p, c, 0, o, keep_bits[0]);
+#pragma unroll
+            for (int l = 1; l <= MAXL; ++l) {
+                if (l > L) break;
                 run_stage(KB, ST_FWD1, image(p.h_out, l - 1));     // the operand tile is h_{l-1}
                 write_residual_terms();
                 run_stage(KB, ST_FWD2, nullptr);
-                fwd_epilogue<false>(S, p, c, l, o);
+                fwd_epilogue<false>(S, p, c, l, o, keep_bits[l]);
             }
             if (issuer && p.backward) copy_out_tile(S, image(p.h_out, L), HP);   // h_L: ordered by the barriers of the last epilogue
             // ---- heads -> loss terms and their gradients (one thread per row)
@@ -599,10 +629,12 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             if (!p.backward) continue;
             row_sync();
             // ---- backward-data
-            bwd_epilogue(S, p, c, L, true);
-            for (int l = L; l >= 1; --l) {
+            bwd_epilogue(S, p, c, L, true, L == 2 ? keep_bits[2] : keep_bits[1]);
+#pragma unroll
+            for (int l = MAXL; l >= 1; --l) {
+                if (l > L) continue;
                 run_stage(KB, ST_BWD, image(p.dz_out, l));          // D = dz_l W_l; the operand tile is dz_l
-                bwd_epilogue(S, p, c, l - 1, false);
+                bwd_epilogue(S, p, c, l - 1, false, keep_bits[l - 1]);
             }
             // dz_0 has no MMA after it: copy it out between two barriers before the next tile's input overwrites block 0
             tc::fence_async_smem();
@@ -775,6 +807,7 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* u, void* stream) {
     G2048_REQUIRE(u != nullptr, "g2048_update_mlp_fwd_bwd: params is NULL");
     G2048_REQUIRE(u->n >= 0, "g2048_update_mlp_fwd_bwd: n < 0");
     if (!shape_ok(u->hidden, u->layers)) return fail(G2048_ESHAPE, "g2048_update_mlp_fwd_bwd: hidden=%d, layers=%d unsupported", u->hidden, u->layers);
+    G2048_REQUIRE(u->dropout_p >= 0.f && u->dropout_p < 1.f, "g2048_update_mlp_fwd_bwd: dropout_p must be in [0, 1)");
     const int L = u->layers, h = u->hidden, HP = padded(h);
     cudaStream_t st = cudaStream_t(stream);
     const bool bw = u->backward != 0;
@@ -802,6 +835,12 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* u, void* stream) {
     p.boards = u->boards; p.actions = u->actions; p.legal = u->legal; p.flags = u->flags;
     p.old_logp = u->old_logp; p.old_stride = u->old_logp_stride; p.adv = u->adv; p.g_norm = u->g_norm;
     p.clip_eps = u->clip_eps; p.c_v = u->critic_strength; p.beta_ent = u->entropy_strength; p.inv_n = u->inv_n;
+    if (u->dropout_p > 0.f) {
+        p.drop_thr = uint32_t(u->dropout_p * 65536.0f + 0.5f);
+        p.drop_scale = 1.0f / (1.0f - u->dropout_p);
+        p.drop_seed = u->dropout_seed;
+        p.sample0 = u->dropout_sample0;
+    }
     const uint8_t* base = static_cast<const uint8_t*>(u->packed);
     p.pf = reinterpret_cast<const float*>(base);
     p.img = base + img_offset_bytes(HP, L);

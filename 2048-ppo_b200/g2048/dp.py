@@ -39,7 +39,9 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class FlatGradBucket:
-    """One flat fp32 buffer for all gradients: a single all-reduce per update (latency-bound)."""
+    """One flat fp32 buffer holding every gradient: `p.grad` of each parameter IS a view into it, so the kernels and
+    autograd accumulate straight into the bucket and an update costs one all-reduce (latency-bound, 353 604 B at
+    h=196, L=2), one norm and one scale -- no per-parameter copies."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
@@ -50,21 +52,30 @@ class FlatGradBucket:
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
+        self.attach()
 
     def numel(self) -> int:
         return self.flat.numel()
 
+    def attach(self) -> None:
+        """(Re)point every p.grad at its slice of the flat buffer (after anything that set grads to None)."""
+        for p, v in zip(self.params, self.views):
+            if p.grad is not v:
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+
+    def zero(self) -> None:
+        self.attach()
+        self.flat.zero_()
+
     def allreduce(self, group=None) -> None:
-        if world()[1] == 1:
-            return
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-            else:
-                v.copy_(p.grad)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+        self.attach()
+        if world()[1] > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+
+    def clip_norm_(self, max_norm: float) -> torch.Tensor:
+        """torch.nn.utils.clip_grad_norm_ (train.py:561) on the flat buffer: returns the total norm before clipping."""
+        total = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        return total

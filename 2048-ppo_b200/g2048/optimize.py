@@ -9,8 +9,10 @@ backward through `g2048.update.loss_and_grads` (one tcgen05 kernel + tensor-core
 `clip_grad_norm_(1.0)`, `optimizer.step()`, `optimizer.zero_grad()`, then KL(old || new) from a forward-only
 pass of the same kernel (train.py:575-598).
 
-The model must be a GameMLP (the reference's or ours) on a CUDA device with dropout off (SURVEY section 7:
-the reference's p = 0.1 dropout is not reproducible across implementations).  No CPU path.
+The model must be a GameMLP (the reference's or ours) on a CUDA device.  Like the reference, the update runs in
+train() mode: the blocks' Dropout(MLPConfig.dropout, 0.1 by default) is active in the loss forward AND in the
+KL forward (train.py:483, 579), with Philox masks keyed from torch's global generator (g2048.update.dropout_mask
+restates them; torch's own dropout stream is not reproducible across implementations).  No CPU path.
 """
 from __future__ import annotations
 
@@ -115,7 +117,6 @@ def model_optimize_step(model, episodes, optimizer, lr_scheduler=None, kl_streng
     if next(model.parameters()).device != dev:
         model.to(dev)
     if not update.supported(model):
-        raise ValueError("g2048.optimize.model_optimize_step: GameMLP with hidden % 4 == 0 in [16, 208], 1-2 blocks and "
-                         "dropout 0 required")
+        raise ValueError("g2048.optimize.model_optimize_step: GameMLP with hidden % 4 == 0 in [16, 208] and 1-2 blocks required")
     return optimize_batch(model, episodes_to_batch(episodes, dev), optimizer, lr_scheduler, kl_strength, critic_strength,
                           batch_size, epochs)

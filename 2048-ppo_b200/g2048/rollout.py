@@ -43,8 +43,10 @@ _lib.register("g2048_urm_pack", [C.c_int32] + [C.c_void_p] * 16)
 _lib.register("g2048_rollout_urm", [C.POINTER(_RolloutStruct), C.c_int32, C.c_void_p])
 
 
-TC_MAX_LAYERS = 6      # residual blocks the tensor-core kernel keeps LayerNorm parameters for (fp32 kernel: 8)
+TC_MAX_LAYERS = 6      # residual blocks the bf16 tensor-core kernel keeps LayerNorm parameters for (fp32 kernel: 8)
+X3_MAX_LAYERS = 4      # same for the split-fp16 (fp32-grade) tensor-core kernel
 TC_MIN_ENVS = 16384   # "auto": envs per GPU from which the rollout GEMMs run on the tensor cores
+_PRECISION = {"fp32": 0, "bf16": 1, "x3": 2}     # G2048_ROLLOUT_* of include/g2048.h
 
 
 def _dp(t):
@@ -137,15 +139,24 @@ class RolloutBuffers:
         return tuple(self.flags.shape)
 
 
+def resolve_precision(precision: str, B: int, layers: int) -> str:
+    """What "auto" means for B envs per GPU: the fp32-grade tensor-core kernel at large env batch, else fp32 FFMA."""
+    if precision != "auto":
+        return precision
+    return "x3" if B >= TC_MIN_ENVS and layers <= X3_MAX_LAYERS else "fp32"
+
+
 def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, env0: int = 0, ctr0: int = 1,
             auto_reset: bool = True, alive: torch.Tensor | None = None, forced_actions: torch.Tensor | None = None,
             out: RolloutBuffers | None = None, precision: str = "auto") -> RolloutBuffers:
     """Play T steps of every board in `boards` (updated in place) with one fused kernel launch.
 
-    precision: "fp32" = FFMA GEMMs (parity-grade log-probs), "bf16" = tcgen05 tensor-core GEMMs with
-    fp32 accumulation, "auto" = bf16 from TC_MIN_ENVS envs up (tensor cores only at large env batch)."""
-    if precision not in ("auto", "fp32", "bf16"):
-        raise ValueError(f"precision must be auto, fp32 or bf16, got {precision!r}")
+    precision: "fp32" = FFMA GEMMs, "x3" = tcgen05 tensor-core GEMMs on split-fp16 operands (x = hi + lo, three
+    products, fp32 accumulation: fp32-grade like "fp32", log-probs / values within 2e-5 of the torch fp32 policy),
+    "bf16" = tcgen05 GEMMs on bf16-rounded operands (log-probs ~1e-2 off the fp32 policy: a labelled variant, never
+    chosen automatically), "auto" = "x3" from TC_MIN_ENVS envs up (tensor cores only at large env batch)."""
+    if precision not in ("auto", "fp32", "bf16", "x3"):
+        raise ValueError(f"precision must be auto, fp32, x3 or bf16, got {precision!r}")
     boards = env._req(boards, torch.int64, "boards")
     B = boards.numel()
     dev = env.init(boards.device)
@@ -161,7 +172,7 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
                            _dp(policy.weights), _dp(env.lut(dev)), _dp(boards), _dp(alive), _dp(forced_actions),
                            _dp(buf.boards), _dp(buf.actions), _dp(buf.legal), _dp(buf.logp), _dp(buf.value),
                            _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy),
-                           int(precision == "bf16" or (precision == "auto" and B >= TC_MIN_ENVS and policy.layers <= TC_MAX_LAYERS)), 0)
+                           _PRECISION[resolve_precision(precision, B, policy.layers)], 0)
         if policy.kind == "urm":
             _lib.call("g2048_rollout_urm", C.byref(s), policy.loops, _stream())
         else:
@@ -292,35 +303,3 @@ def save_best_checkpoint(path, model, eval_avg_score: float, train_step: int) ->
     cfg = model.config.model_dump() if hasattr(model.config, "model_dump") else dict(model.config)
     torch.save({"model_state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "config": cfg,
                 "eval_avg_score": eval_avg_score, "train_step": train_step}, path)
-
-
-def smoke(dev) -> None:
-    """Tiny fused rollouts on `dev` (fp32 FFMA, bf16 tcgen05, GameURM), checked against the oracle env
-    and the torch policy."""
-    from oracle import oracle as O
-    from .policy import GameMLP, GameURM, GameURMConfig, MLPConfig
-    torch.manual_seed(0)
-    mlp = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.0)).to(dev).eval()
-    urm = GameURM(GameURMConfig(dropout=0.0)).to(dev).eval()
-    for model, precision, tol in ((mlp, "fp32", 1e-4), (mlp, "bf16", 0.1), (urm, "bf16", 0.3)):
-        B, T, seed = 300, 12, 7
-        boards = env.reset(B, device=dev, seed=seed, env0=0, ctr=0)
-        start = boards.clone()
-        buf = rollout(pack_policy(model), boards, T, seed=seed, env0=0, ctr0=1, auto_reset=False,
-                      alive=torch.ones(B, dtype=torch.uint8, device=dev), precision=precision)
-        b = start.cpu().numpy().view(np.uint64)
-        for t in range(T):
-            valid = (buf.flags[t].cpu().numpy() & 0x80) != 0
-            np.testing.assert_array_equal(buf.boards[t].cpu().numpy().view(np.uint64)[valid], b[valid])
-            nb, info = O.step_batch(b, buf.actions[t].cpu().numpy(), seed=seed, env0=0, ctr=1 + t)
-            np.testing.assert_array_equal(buf.points[t].cpu().numpy()[valid], info["points"][valid])
-            with torch.no_grad():
-                logits, v = model(env.encode(buf.boards[t]))
-            lm = buf.legal[t].long()
-            illegal = ((lm[:, None] >> torch.arange(4, device=dev)) & 1) == 0
-            ref = torch.masked_fill(logits, illegal, float("-inf")).log_softmax(-1)
-            vt = torch.from_numpy(valid).to(dev)
-            fin = torch.isfinite(ref) & vt[:, None]
-            assert torch.allclose(buf.logp[t][fin], ref[fin], rtol=tol, atol=tol)
-            assert torch.allclose(buf.value[t][vt], v.squeeze(1)[vt], rtol=tol, atol=tol)
-            b = np.where(valid, nb, b)

@@ -100,8 +100,9 @@ class StepTimes:
     rollout_ms: float = 0.0
     advantage_ms: float = 0.0
     update_ms: float = 0.0
-    allreduce_ms: float = 0.0
+    allreduce_ms: float = 0.0       # the 3-scalar return-moment all-reduce (after the update)
     optimizer_ms: float = 0.0
+    grad_allreduce_ms: float = 0.0  # the flat-gradient all-reduce of the last optimizer step (0 on one GPU)
 
 
 class Trainer:
@@ -137,6 +138,14 @@ class Trainer:
         self._aug_gen = torch.Generator(device=self.device)
         self._aug_gen.manual_seed(cfg.seed * 1000003 + self.rank)
         self.n_update_samples = 0
+        self._ev_ar = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        self._dropout_calls = 0
+
+    def _dropout_seed(self) -> int:
+        """A fresh Philox key per fused-update call (identical on every rank: the masks are keyed by the sample's index
+        in its chunk, and ranks hold different samples)."""
+        self._dropout_calls += 1
+        return (self.cfg.seed * 0x9E3779B1 + self._dropout_calls * 0x85EBCA77 + self.rank * 0xC2B2AE3D) & 0xFFFFFFFFFFFFFFFF
 
     # -- phases ---------------------------------------------------------------------------
     def collect(self) -> rollout.RolloutBuffers:
@@ -170,19 +179,23 @@ class Trainer:
                 logp, a, g, flags = torch.cat([logp, aug["logp"]]), torch.cat([a, a[src]]), torch.cat([g, g[src]]), torch.cat([flags, flags[src]])
                 n_local = boards.numel()
         self.n_update_samples = n_local
-        counts = torch.tensor([float(n_local)], dtype=torch.float64, device=self.device)
-        n_global = int(dp.allreduce_stats(counts).item())
+        c_mb = c.minibatches
+        # minibatch m of this rank = samples [cut[m], cut[m+1]) of its (shuffled) shard: every rank runs exactly
+        # c.minibatches optimizer steps (matching all-reduces even when a shard is short or empty) and the loss divisor
+        # of a step is the all-reduced sample count of that minibatch, so the summed gradient is the global mean
+        # (train.py:554) whatever the shard sizes are
+        cut = [(n_local * m) // c_mb for m in range(c_mb + 1)]
+        counts = torch.tensor([float(cut[m + 1] - cut[m]) for m in range(c_mb)], dtype=torch.float64, device=self.device)
+        n_mb_global = [int(x) for x in dp.allreduce_stats(counts).tolist()]
         self.model.train()
         last = None
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = c.update_matmul == "tf32"
         for _ in range(c.epochs):
-            order = None if c.minibatches == 1 else torch.randperm(n_local, device=self.device)
-            mb = (n_local + c.minibatches - 1) // c.minibatches
-            for m0 in range(0, n_local, mb):
-                m1 = min(n_local, m0 + mb)
-                n_mb_global = n_global if c.minibatches == 1 else (m1 - m0) * self.world
-                self.opt.zero_grad()
+            order = None if c_mb == 1 else torch.randperm(n_local, device=self.device)
+            for m in range(c_mb):
+                m0, m1 = cut[m], cut[m + 1]
+                self.bucket.zero()
                 tot = torch.zeros(4, dtype=torch.float64, device=self.device)
                 use_fused = self.is_mlp and c.update_matmul == "fused" and update.supported(self.model)
                 packed = update.pack(self.model) if use_fused else None
@@ -192,7 +205,8 @@ class Trainer:
                     if use_fused:
                         tot += update.loss_and_grads(self.model, boards[sl], actions[sl], legal[sl], logp[sl], a[sl], g[sl],
                                                      flags=flags[sl], clip_eps=c.clip_eps, critic_strength=c.critic_strength,
-                                                     entropy_strength=c.entropy_strength, n_total=n_mb_global, packed=packed)
+                                                     entropy_strength=c.entropy_strength, n_total=max(n_mb_global[m], 1), packed=packed,
+                                                     dropout_p=c.dropout, dropout_seed=self._dropout_seed())
                         continue
                     if self.is_mlp:
                         logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
@@ -201,11 +215,14 @@ class Trainer:
                         logits, v = self.model(env.encode(boards[sl]))
                     loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],
                                                clip_eps=c.clip_eps, critic_strength=c.critic_strength,
-                                               entropy_strength=c.entropy_strength, n_total=n_mb_global)
+                                               entropy_strength=c.entropy_strength, n_total=max(n_mb_global[m], 1))
                     loss.backward()
                     tot += stats
+                e_ar = self._ev_ar
+                e_ar[0].record()
                 self.bucket.allreduce()
-                gn = torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)   # train.py:561
+                e_ar[1].record()
+                gn = self.bucket.clip_norm_(1.0)                                    # train.py:561
                 self.opt.step()
                 last = (tot, gn)
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
@@ -234,7 +251,7 @@ class Trainer:
         e[4].record()
         torch.cuda.synchronize(self.device)
         self.times = StepTimes(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3]),
-                               e[3].elapsed_time(e[4]), 0.0)
+                               e[3].elapsed_time(e[4]), 0.0, self._ev_ar[0].elapsed_time(self._ev_ar[1]))
         stats["env_steps"] = buf.flags.numel() * self.world
         stats["mean_points_per_step"] = float(buf.points.float().mean())
         return stats

@@ -1,8 +1,8 @@
 """The policy update's forward + loss + backward as hand-written kernels (no autograd graph).
 
 `loss_and_grads(model, ...)` is what train.model_optimize_step does between `optimizer.zero_grad()` and
-`clip_grad_norm_` (train.py:491-556) for a GameMLP with dropout off: it ADDS d loss / d parameter into every
-`p.grad` and returns the loss sums.  One fused tcgen05 kernel (g2048_update_mlp_fwd_bwd) runs the forward,
+`clip_grad_norm_` (train.py:491-556) for a GameMLP (the blocks' Dropout active in train() mode, as in the reference,
+with Philox masks -- see dropout_mask): it ADDS d loss / d parameter into every `p.grad` and returns the loss sums.  One fused tcgen05 kernel (g2048_update_mlp_fwd_bwd) runs the forward,
 the PPO-clip / critic / entropy terms and the backward-data chain per 128-sample tile; the weight gradients
 are split-bf16 tcgen05 reductions over samples (g2048_x3_wgrad).  There is no fallback: unsupported model
 shapes raise (use g2048.fused.mlp_forward + g2048.ppo.ppo_loss with autograd for those).
@@ -25,7 +25,8 @@ class _UpdateMlp(C.Structure):   # include/g2048.h: G2048UpdateMlp
                 ("old_logp_stride", i32), ("reserved_", i32), ("adv", vp), ("g_norm", vp),
                 ("clip_eps", f32), ("critic_strength", f32), ("entropy_strength", f32), ("inv_n", f32),
                 ("packed", vp), ("workspace", vp), ("h_out", vp), ("dz_out", vp), ("dhead", vp), ("logits", vp),
-                ("value", vp), ("ln_grad", vp), ("head_bias_grad", vp), ("stats", vp)]
+                ("value", vp), ("ln_grad", vp), ("head_bias_grad", vp), ("stats", vp),
+                ("dropout_p", f32), ("reserved2_", i32), ("dropout_seed", C.c_uint64), ("dropout_sample0", C.c_uint64)]
 
 
 _lib.register("g2048_update_mlp_pack", [i32, i32] + [vp] * 12)
@@ -39,8 +40,40 @@ _WS: dict[tuple[int, int, int], torch.Tensor] = {}
 
 def supported(model) -> bool:
     h, L = model.stem[0].weight.shape[0], len(model.backbone)
-    no_dropout = all(blk.mlp[3].p == 0 or not model.training for blk in model.backbone)
-    return 16 <= h <= 208 and h % 4 == 0 and 1 <= L <= 2 and no_dropout and model.stem[0].weight.shape[1] == 48
+    ps = {float(blk.mlp[3].p) for blk in model.backbone}
+    return 16 <= h <= 208 and h % 4 == 0 and 1 <= L <= 2 and len(ps) == 1 and 0.0 <= min(ps) < 1.0 and model.stem[0].weight.shape[1] == 48
+
+
+def model_dropout_p(model) -> float:
+    """The dropout probability the reference's forward would apply right now (nn.Dropout is the identity in eval mode)."""
+    return float(model.backbone[0].mlp[3].p) if model.training and len(model.backbone) else 0.0
+
+
+def fresh_dropout_seed() -> int:
+    """A 64-bit Philox key drawn from torch's global CPU generator (so torch.manual_seed makes the masks reproducible)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def dropout_mask(n: int, h: int, L: int, p: float, seed: int, sample0: int = 0):
+    """The keep mask the fused kernel applies, as a bool array [L, n, h] (include/g2048.h G2048UpdateMlp.dropout_p):
+    numpy restatement of Philox4x32-10 for tests and for anyone who needs to reproduce a step."""
+    import numpy as np
+    groups = (h + 7) // 8
+    thr = int(p * 65536.0 + 0.5)
+    i = (np.arange(n, dtype=np.uint64) + np.uint64(sample0))[None, :, None]
+    c0 = np.broadcast_to((i & np.uint64(0xFFFFFFFF)), (L, n, groups)).copy()
+    c1 = np.broadcast_to((i >> np.uint64(32)), (L, n, groups)).copy()
+    c2 = np.broadcast_to(np.arange(1, L + 1, dtype=np.uint64)[:, None, None], (L, n, groups)).copy()
+    c3 = np.broadcast_to(np.arange(groups, dtype=np.uint64)[None, None, :], (L, n, groups)).copy()
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> np.uint64(32)) ^ c3 ^ k1) & MASK, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    lanes = np.stack([c0 & np.uint64(0xFFFF), c0 >> np.uint64(16), c1 & np.uint64(0xFFFF), c1 >> np.uint64(16),
+                      c2 & np.uint64(0xFFFF), c2 >> np.uint64(16), c3 & np.uint64(0xFFFF), c3 >> np.uint64(16)], axis=-1)
+    return (lanes >= np.uint64(thr)).reshape(L, n, groups * 8)[:, :, :h]
 
 
 def _shape(model):
@@ -57,7 +90,7 @@ def _workspace(dev, h, L):
 def pack(model) -> torch.Tensor:
     """Kernel-side image of the model's current parameters (re-pack after every optimizer step)."""
     if not supported(model):
-        raise ValueError("g2048.update: GameMLP with hidden % 4 == 0 in [16, 208], 1-2 blocks and dropout off required")
+        raise ValueError("g2048.update: GameMLP with hidden % 4 == 0 in [16, 208] and 1-2 blocks required")
     h, L = _shape(model)
     dev = init(model.stem[0].weight.device)
     f = lambda t: _req(t.detach(), torch.float32, "parameter")
@@ -75,8 +108,10 @@ def pack(model) -> torch.Tensor:
     return packed
 
 
-def forward(model, boards: torch.Tensor, packed: torch.Tensor | None = None):
-    """(logits [n,4], value [n,1]) of GameMLP on packed boards through the fused kernel (forward only)."""
+def forward(model, boards: torch.Tensor, packed: torch.Tensor | None = None, *, dropout_p: float | None = None,
+            dropout_seed: int | None = None, dropout_sample0: int = 0):
+    """(logits [n,4], value [n,1]) of GameMLP on packed boards through the fused kernel (forward only).
+    dropout_p: None = what the model's mode implies (MLPConfig.dropout in train(), 0 in eval())."""
     h, L = _shape(model)
     boards = _req(boards.reshape(-1), torch.int64, "boards")
     n = boards.numel()
@@ -85,9 +120,12 @@ def forward(model, boards: torch.Tensor, packed: torch.Tensor | None = None):
     with torch.cuda.device(dev):
         logits = torch.empty((n, 4), dtype=torch.float32, device=dev)
         value = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        dp_ = model_dropout_p(model) if dropout_p is None else float(dropout_p)
         u = _UpdateMlp(n=n, hidden=h, layers=L, decouple_critic=int(model.decouple_critic), backward=0,
                        boards=boards.data_ptr(), packed=packed.data_ptr(), workspace=_workspace(dev, h, L).data_ptr(),
-                       logits=logits.data_ptr(), value=value.data_ptr())
+                       logits=logits.data_ptr(), value=value.data_ptr(), dropout_p=dp_,
+                       dropout_seed=(fresh_dropout_seed() if dropout_seed is None else dropout_seed) if dp_ > 0 else 0,
+                       dropout_sample0=dropout_sample0)
         _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
     return logits, value
 
@@ -103,13 +141,21 @@ def _acc(p: torch.nn.Parameter, g: torch.Tensor) -> None:
 def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flags=None, clip_eps=0.2,
                    critic_strength=1.0, entropy_strength=0.1, n_total: int | None = None,
                    packed: torch.Tensor | None = None, keep: dict | None = None,
-                   logits_out: torch.Tensor | None = None) -> torch.Tensor:
+                   logits_out: torch.Tensor | None = None, dropout_p: float | None = None, dropout_seed: int | None = None,
+                   dropout_sample0: int = 0) -> torch.Tensor:
     """Adds the gradients of the minibatch-mean loss (train.py:554) over these samples into `p.grad` of every
     parameter and returns float64[4] = {sum ppo, sum smooth_l1, sum entropy, count} (device tensor).
     `n_total`: divisor of the mean when this call is a chunk / shard of a larger minibatch.
     `keep`: optional dict that receives the intermediate tensors (tests); `logits_out`: optional float32 [n, 4]
-    CUDA tensor that receives the forward's action logits."""
+    CUDA tensor that receives the forward's action logits.
+    dropout_p: None = what the model's mode implies (MLPConfig.dropout when model.training -- the reference updates in
+    train() mode, train.py:483 -- else 0); dropout_seed: Philox key of the masks (None: drawn from torch's global
+    generator); dropout_sample0: index of the first sample in the mask's counter space (chunks of one minibatch).
+    `dropout_mask` restates the mask."""
     h, L = _shape(model)
+    dp_ = model_dropout_p(model) if dropout_p is None else float(dropout_p)
+    if dp_ > 0 and dropout_seed is None:
+        dropout_seed = fresh_dropout_seed()
     boards = _req(boards.reshape(-1), torch.int64, "boards")
     n = boards.numel()
     dev = init(boards.device)
@@ -135,7 +181,8 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
                        inv_n=1.0 / float(n_total if n_total else max(n, 1)),
                        packed=packed.data_ptr(), workspace=_workspace(dev, h, L).data_ptr(),
                        h_out=h_out.data_ptr(), dz_out=dz_out.data_ptr(), dhead=dhead.data_ptr(),
-                       ln_grad=ln_grad.data_ptr(), head_bias_grad=hb_grad.data_ptr(), stats=stats.data_ptr())
+                       ln_grad=ln_grad.data_ptr(), head_bias_grad=hb_grad.data_ptr(), stats=stats.data_ptr(),
+                       dropout_p=dp_, dropout_seed=(dropout_seed or 0) if dp_ > 0 else 0, dropout_sample0=dropout_sample0)
         if logits_out is not None:
             assert logits_out.shape == (n, 4) and logits_out.is_contiguous()
             u.logits = _req(logits_out, torch.float32, "logits_out").data_ptr()

@@ -167,6 +167,10 @@ int g2048_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const fl
                    const float* action_w, const float* action_b, const float* value_w, const float* value_b,
                    float* packed, void* stream);
 
+#define G2048_ROLLOUT_FP32 0
+#define G2048_ROLLOUT_BF16 1
+#define G2048_ROLLOUT_X3 2
+
 typedef struct G2048Rollout {
     int64_t B;                 /* environments */
     int32_t T;                 /* steps played by this call */
@@ -191,9 +195,12 @@ typedef struct G2048Rollout {
     uint64_t* rec_shaping;  /* packed G2048_SH_* record of the move */
     uint8_t* rec_flags;     /* g2048_step flags of the move | G2048_FLAG_VALID */
     float* rec_entropy;     /* entropy of the masked action distribution; may be NULL */
-    int32_t tensor_cores;   /* 0: fp32 FFMA GEMMs (log-probs within ~1e-6 of the torch policy);
-                               1: bf16 tcgen05 GEMMs with fp32 accumulation in tensor memory (large env
-                                  batches; recorded log-probs within ~1e-2 of the fp32 policy) */
+    int32_t tensor_cores;   /* G2048_ROLLOUT_FP32 (0): fp32 FFMA GEMMs (log-probs within ~1e-6 of the torch policy);
+                               G2048_ROLLOUT_BF16 (1): bf16 tcgen05 GEMMs with fp32 accumulation in tensor memory
+                                  (recorded log-probs within ~1e-2 of the fp32 policy: a labelled variant);
+                               G2048_ROLLOUT_X3 (2): split-fp16 tcgen05 GEMMs (every operand = hi + lo in fp16, three
+                                  products per k-step, fp32 accumulation): fp32-grade, log-probs / values within
+                                  2e-5 of the torch fp32 policy (game.py:1192-1203, train.py:256-274); <= 4 blocks */
     int32_t reserved_;
 } G2048Rollout;
 
@@ -272,7 +279,7 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
  * and returns the small gradients itself: ln_grad [L+1][2][hidden] (d LayerNorm weight | bias per layer,
  * stem first), head_bias_grad [5] (action_head.bias, value_head.bias) and stats double[4] = {sum ppo,
  * sum smooth_l1, sum entropy, count} as g2048_ppo_loss.  All per-SM partial sums are combined in a fixed
- * order (deterministic).  hidden: multiple of 4 in [16, 208]; layers 1..2; dropout must be off.
+ * order (deterministic).  hidden: multiple of 4 in [16, 208]; layers 1..2; dropout: see dropout_p.
  * backward = 0: forward only (writes logits [n,4] and/or value [n]; used by the parity tests). */
 int64_t g2048_update_mlp_pack_bytes(int32_t hidden, int32_t layers);
 int g2048_update_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
@@ -307,6 +314,15 @@ typedef struct G2048UpdateMlp {
     float* ln_grad;                /* [layers+1][2][hidden] */
     float* head_bias_grad;         /* [5] */
     double* stats;                 /* [4] */
+    /* Dropout of the residual blocks (game.py:1038-1046; the reference trains with MLPConfig.dropout = 0.1 active,
+     * train.py:483): element (sample i, block l, column c) is dropped iff lane (c & 7) of the 8 16-bit lanes of
+     * Philox4x32-10(counter = (dropout_sample0 + i [64 bit], l, c >> 3), key = dropout_seed) -- word order x, y, z, w,
+     * low half first -- is < round(dropout_p * 65536); kept elements are scaled by 1 / (1 - dropout_p).  The backward
+     * pass applies the same mask.  dropout_p = 0 (or the struct zero-filled): off. */
+    float dropout_p;
+    int32_t reserved2_;
+    uint64_t dropout_seed;
+    uint64_t dropout_sample0;
 } G2048UpdateMlp;
 
 int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* params, void* stream);

@@ -67,3 +67,18 @@ def test_shaping_decode_matches_header_macros():
     assert {k: int(v[0]) for k, v in d.items()} == dict(
         mono_before=30, mono_after=28, empt_before=3, empt_after=4, max_tile_created=5, max_exp_before=13,
         max_exp_after=12, corner_before=13, corner_after=-12, smooth_before=-42, smooth_after=-40)
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package may import, load or name it."""
+    pkg = os.path.join(ROOT, "2048-ppo_b200")
+    hits = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(d, f)).read()
+                if re.search(r"\boracle\b", text):
+                    hits.append(os.path.join(d, f))
+    assert hits == [], hits
+    shim = open(os.path.join(ROOT, "batched_rollout.py")).read()
+    assert "oracle" not in shim

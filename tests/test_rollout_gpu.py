@@ -40,9 +40,11 @@ def torch_policy_outputs(model, boards, legal):
     return lp, v.squeeze(1), ent
 
 
-def test_replays_reference_play_game_for_episode(golden):
+@pytest.mark.parametrize("precision", ["fp32", "x3"])
+def test_replays_reference_play_game_for_episode(golden, precision):
     """Same weights, same Philox spawn draws, the reference's sampled actions forced: every StepData
-    field the reference recorded must come back (ints bit-exact, floats to 1e-5)."""
+    field the reference recorded must come back (ints bit-exact, floats to 1e-5) -- from the fp32 FFMA kernel and
+    from the split-fp16 tensor-core kernel (the default at large env batch)."""
     from g2048 import env, rollout
     g = golden("rollout")
     a, (t, e) = rollout_as_tb(g)
@@ -52,7 +54,7 @@ def test_replays_reference_play_game_for_episode(golden):
     boards = env.reset(B, device=0, seed=seed, env0=0, ctr=0)
     forced = torch.from_numpy(a["action"]).cuda()
     buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=0, ctr0=1, auto_reset=False,
-                          alive=torch.ones(B, dtype=torch.uint8, device="cuda"), forced_actions=forced)
+                          alive=torch.ones(B, dtype=torch.uint8, device="cuda"), forced_actions=forced, precision=precision)
     h = lambda x: x.cpu().numpy()
     np.testing.assert_array_equal(h(buf.boards)[t, e].view(np.uint64), g["board"])
     np.testing.assert_array_equal(h(buf.legal)[t, e], g["legal"])
@@ -83,14 +85,16 @@ def test_replays_reference_play_game_for_episode(golden):
             assert h(boards).view(np.uint64)[env_i] == g["ep_final"][env_i]
 
 
-@pytest.mark.parametrize("h,L,B,T", [(196, 2, 1000, 48), (64, 1, 130, 40), (128, 3, 257, 16), (192, 2, 128, 8)])
-def test_rollout_matches_oracle_env_and_torch_policy(h, L, B, T):
+@pytest.mark.parametrize("precision", ["fp32", "x3"])
+@pytest.mark.parametrize("h,L,B,T", [(196, 2, 1000, 48), (64, 1, 130, 40), (128, 3, 257, 16), (192, 2, 128, 8), (196, 0, 128, 4),
+                                     (200, 4, 300, 6)])
+def test_rollout_matches_oracle_env_and_torch_policy(h, L, B, T, precision):
     from g2048 import env, rollout
     model = random_model(h, L, seed=h + L)
     seed, env0 = 99, 12345
     boards = env.reset(B, device=0, seed=seed, env0=env0, ctr=0)
     start = boards.clone()
-    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=env0, ctr0=1, auto_reset=True)
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=env0, ctr0=1, auto_reset=True, precision=precision)
     b = start.cpu().numpy().view(np.uint64)
     n_done = 0
     for t in range(T):
@@ -273,7 +277,7 @@ def test_tensor_core_rollout(h, L, B, T):
     assert err_lp < 0.1 and err_v < 0.1
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "x3"])
 def test_full_size_rollout_properties(precision):
     """C3-sized env batch (65 536 envs): size-independent properties instead of a CPU replay --
     the rollout kernel's inlined env agrees with the standalone g2048_step kernel fed the recorded
@@ -336,14 +340,16 @@ def test_tensor_core_rollout_forced_actions_and_idle_envs():
     B, T, seed = 200, 320, 11
     start = env.reset(B, device=0, seed=seed, env0=3, ctr=0)
     ones = lambda: torch.ones(B, dtype=torch.uint8, device="cuda")
-    a1, a2 = ones(), ones()
+    a1 = ones()
     ref = rollout.rollout(pol, start.clone(), T, seed=seed, env0=3, ctr0=1, auto_reset=False, alive=a1, precision="fp32")
-    tcb = rollout.rollout(pol, start.clone(), T, seed=seed, env0=3, ctr0=1, auto_reset=False, alive=a2, precision="bf16",
-                          forced_actions=ref.actions.clone())
     assert int(a1.sum()) < B, "the horizon should outlive some games"
-    assert torch.equal(a1, a2)
     assert bool((ref.flags[-1] == 0).any()) and bool((ref.flags[0] & 0x80).all())
-    for name in ("boards", "actions", "legal", "points", "shaping", "flags"):
-        assert torch.equal(getattr(ref, name), getattr(tcb, name)), name
     idle = ref.flags == 0
-    assert bool((tcb.value[idle] == 0).all()) and bool((tcb.logp[idle] == 0).all())
+    for precision in ("bf16", "x3"):
+        a2 = ones()
+        tcb = rollout.rollout(pol, start.clone(), T, seed=seed, env0=3, ctr0=1, auto_reset=False, alive=a2, precision=precision,
+                              forced_actions=ref.actions.clone())
+        assert torch.equal(a1, a2)
+        for name in ("boards", "actions", "legal", "points", "shaping", "flags"):
+            assert torch.equal(getattr(ref, name), getattr(tcb, name)), (precision, name)
+        assert bool((tcb.value[idle] == 0).all()) and bool((tcb.logp[idle] == 0).all())

@@ -184,8 +184,92 @@ def test_rejects_unsupported_models():
     assert not update.supported(m)
     with pytest.raises(ValueError):
         update.pack(m)
-    m = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.1)).cuda().train()
-    assert not update.supported(m)
+    m = GameMLP(MLPConfig(hidden_dim=196, num_layers=2, dropout=0.1)).cuda().train()      # the reference's default model
+    assert update.supported(m) and update.model_dropout_p(m) == pytest.approx(0.1)
+    assert update.model_dropout_p(m.eval()) == 0.0
+
+
+def _forward64_dropout(m, x48, keep, p):
+    """_forward64 with the blocks' Dropout applied as `keep` [L, n, h] (bool) / (1 - p): game.py:1038-1046."""
+    F = torch.nn.functional
+    P = {k: v.detach().double().requires_grad_(True) for k, v in m.named_parameters()}
+    h = P["stem.0.weight"].shape[0]
+    x = F.relu(F.layer_norm(x48.double() @ P["stem.0.weight"].T, (h,), P["stem.1.weight"], P["stem.1.bias"], 1e-5))
+    for l in range(len(m.backbone)):
+        pre = f"backbone.{l}.mlp."
+        y = F.relu(F.layer_norm(x @ P[pre + "0.weight"].T, (h,), P[pre + "1.weight"], P[pre + "1.bias"], 1e-5))
+        x = x + y * keep[l].double() / (1.0 - p)
+    logits = x @ P["action_head.weight"].T + P["action_head.bias"]
+    xv = x.detach() if m.decouple_critic else x
+    return logits, xv @ P["value_head.weight"].T + P["value_head.bias"], P
+
+
+@pytest.mark.parametrize("h,L,n,p", [(196, 2, 5000, 0.1), (64, 1, 1300, 0.25), (196, 2, 128 * 40 + 3, 0.5)])
+def test_dropout_masked_replay_matches_float64_autograd(h, L, n, p):
+    """Dropout(p) active in the update forward, as in the reference (train.py:483, game.py:1042): the kernel's Philox
+    mask, restated on the host by update.dropout_mask, applied identically in float64 torch gives the same loss sums
+    and the same gradients (the backward uses the same mask); the mask has the right density; forward-only calls with
+    the same key see the same mask; another key gives another mask."""
+    from g2048 import env, update
+    m = _model(h, L, 29).train()
+    for blk in m.backbone:
+        blk.mlp[3].p = p
+    boards = _boards(n, 31)
+    old, actions, legal, adv, g_norm = _samples(n, 37)
+    seed, s0 = 0x1234_5678_9ABC_DEF0, 77
+    keep = torch.from_numpy(update.dropout_mask(n, h, L, p, seed, s0)).cuda()
+    assert abs(float(keep.float().mean()) - (1 - p)) < 4 * (p * (1 - p) / keep.numel()) ** 0.5 + 1e-4
+    m.zero_grad()
+    stats = update.loss_and_grads(m, boards, actions, legal, old, adv, g_norm, clip_eps=0.2, critic_strength=0.2,
+                                  entropy_strength=0.02, dropout_seed=seed, dropout_sample0=s0)
+    logits, v, P = _forward64_dropout(m, env.encode(boards), keep, p)
+    loss, parts = ref_ppo_loss_torch(logits, v, old.double(), actions, legal, adv.double(), g_norm.double(), 0.2, 0.2, 0.02)
+    loss.backward()
+    s = stats.cpu().numpy()
+    np.testing.assert_allclose(s[:3] / n, [float(parts["ppo"]), float(parts["vl"]), float(parts["ent"])], rtol=1e-5, atol=1e-7)
+    for k, q in m.named_parameters():
+        _grad_check(q.grad, P[k].grad, f"dropout {p} {k}")
+    fl, fv = update.forward(m, boards, dropout_seed=seed, dropout_sample0=s0)
+    assert _rel(fl, logits.detach()) < 5e-6 and _rel(fv, v.detach()) < 5e-6
+    fl2, _ = update.forward(m, boards, dropout_seed=seed + 1, dropout_sample0=s0)
+    assert float((fl2 - fl).abs().max()) > 1e-3
+    el, _ = update.forward(m.eval(), boards)                                   # eval mode: Dropout is the identity
+    rl, _, _ = _forward64(m, env.encode(boards))
+    assert _rel(el, rl) < 5e-6
+
+
+def test_model_optimize_step_accepts_the_reference_default_model():
+    """train.model_optimize_step's model is built with MLPConfig's default dropout 0.1 (train.py:1522, game.py:27) and
+    updated in train() mode; the drop-in runs on exactly that (it raised in round 1)."""
+    from g2048 import optimize
+    from g2048.policy import GameMLP, MLPConfig
+    torch.manual_seed(3)
+    m = GameMLP(MLPConfig(hidden_dim=196)).cuda()
+    assert m.backbone[0].mlp[3].p == pytest.approx(0.1)
+    n = 300
+    boards = _boards(n, 41)
+    old, actions, legal, adv, g_norm = _samples(n, 43)
+    batch = dict(boards=boards, actions=actions, legal=legal, adv=adv, g_norm=g_norm, logp=old)
+
+    class Opt:
+        def __init__(self, params): self.o = torch.optim.SGD(params, lr=1e-3)
+        def step(self): self.o.step()
+        def zero_grad(self): self.o.zero_grad()
+        def scheduler_step(self): pass
+    w0 = m.backbone[0].mlp[0].weight.detach().clone()
+    torch.manual_seed(5)
+    st = optimize.optimize_batch(m, batch, Opt(m.parameters()), batch_size=128, epochs=1, critic_strength=0.2, kl_strength=0.02)
+    assert m.training and all(np.isfinite(v) for v in st.values())
+    assert st["kl_average"] > 0                      # two different dropout masks: the KL forward differs even before learning
+    w1 = m.backbone[0].mlp[0].weight.detach().clone()
+    assert not torch.equal(w0, w1)
+    # reproducible under torch.manual_seed (the Philox keys come from torch's global generator)
+    m2 = GameMLP(MLPConfig(hidden_dim=196)).cuda()
+    torch.manual_seed(3)
+    m2 = GameMLP(MLPConfig(hidden_dim=196)).cuda()
+    torch.manual_seed(5)
+    optimize.optimize_batch(m2, batch, Opt(m2.parameters()), batch_size=128, epochs=1, critic_strength=0.2, kl_strength=0.02)
+    assert torch.equal(m2.backbone[0].mlp[0].weight, w1)
 
 
 @pytest.mark.parametrize("h,L,n", [(196, 2, 1000), (64, 1, 300)])
