@@ -26,7 +26,8 @@ namespace x3 {
 
 constexpr int SPLIT = 4;                          // threads per env row (column parts)
 constexpr int ENV_THREADS = 128 * SPLIT;          // 16 warps: warp w owns lane quarter (w & 3) and column part (w >> 2)
-constexpr int THREADS = ENV_THREADS + 32;         // + the control warp (lane 0: MMA issue and weight streaming)
+constexpr int THREADS = ENV_THREADS + 64;         // + two control warps: MMA issuer, weight producer (5 warps on a scheduler
+                                                  // cap the registers at 96 per thread whether there are 17 or 20 of them)
 constexpr uint32_t X_COL = 256;
 constexpr int MAX_LAYERS = 4;
 
@@ -153,49 +154,51 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
 #pragma unroll
     for (int q = 0; q < 5; ++q) o2[q] = make_float2(0.f, 0.f);
 
-    // ---- pass 2, full blocks
+    // ---- pass 2, full blocks, 8 columns (one 16-byte operand unit per part) at a time
 #pragma unroll
     for (int i = 0; i < NBF; ++i) {
-        const int blk = 4 * i + c.part, col0 = 16 * blk;
-        float x[16];
-        if (!STEM) tc::tmem_ld16p(c.tX + uint32_t(col0), x);
-        const float4* g4 = reinterpret_cast<const float4*>(gamma + col0);
-        const float4* e4 = reinterpret_cast<const float4*>(beta + col0);
+        const int blk = 4 * i + c.part;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 g = g4[q], e = e4[q];
-            float2 y0 = __ffma2_rn(__ffma2_rn(make_float2(z[i][4 * q], z[i][4 * q + 1]), rstd2, shift2), make_float2(g.x, g.y), make_float2(e.x, e.y));
-            float2 y1 = __ffma2_rn(__ffma2_rn(make_float2(z[i][4 * q + 2], z[i][4 * q + 3]), rstd2, shift2), make_float2(g.z, g.w), make_float2(e.z, e.w));
-            y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f);
-            if (!STEM) {
-                y0 = __fadd2_rn(make_float2(x[4 * q], x[4 * q + 1]), y0);
-                y1 = __fadd2_rn(make_float2(x[4 * q + 2], x[4 * q + 3]), y1);
-            }
-            x[4 * q] = y0.x; x[4 * q + 1] = y0.y; x[4 * q + 2] = y1.x; x[4 * q + 3] = y1.y;
-        }
-        if (HEADS) {
+        for (int u = 0; u < 2; ++u) {
+            const int col0 = 16 * blk + 8 * u;
+            float x[8];
+            if (!STEM) tc::tmem_ld8(c.tX + uint32_t(col0), x);
+            const float4* g4 = reinterpret_cast<const float4*>(gamma + col0);
+            const float4* e4 = reinterpret_cast<const float4*>(beta + col0);
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                const float4* hw = reinterpret_cast<const float4*>(S.headw + q * HP + col0);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 w = hw[u];
-                    o2[q] = __ffma2_rn(make_float2(w.x, w.y), make_float2(x[4 * u], x[4 * u + 1]), o2[q]);
-                    o2[q] = __ffma2_rn(make_float2(w.z, w.w), make_float2(x[4 * u + 2], x[4 * u + 3]), o2[q]);
+            for (int q = 0; q < 2; ++q) {
+                const float4 g = g4[q], e = e4[q];
+                const float* zz = &z[i][8 * u + 4 * q];
+                float2 y0 = __ffma2_rn(__ffma2_rn(make_float2(zz[0], zz[1]), rstd2, shift2), make_float2(g.x, g.y), make_float2(e.x, e.y));
+                float2 y1 = __ffma2_rn(__ffma2_rn(make_float2(zz[2], zz[3]), rstd2, shift2), make_float2(g.z, g.w), make_float2(e.z, e.w));
+                y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f);
+                if (!STEM) {
+                    y0 = __fadd2_rn(make_float2(x[4 * q], x[4 * q + 1]), y0);
+                    y1 = __fadd2_rn(make_float2(x[4 * q + 2], x[4 * q + 3]), y1);
                 }
+                x[4 * q] = y0.x; x[4 * q + 1] = y0.y; x[4 * q + 2] = y1.x; x[4 * q + 3] = y1.y;
             }
-        } else {
-            tc::tmem_st16(c.tX + uint32_t(col0), x);
-            uint32_t hi[8], lo[8];
+            if (HEADS) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tc::split2_f16(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
-            const uint32_t a0 = c.a_row + uint32_t(blk) * 4096u + (c.sw << 4), a1 = a0 ^ 16u;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + SM::PART), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1 + SM::PART), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
-            warp_arrive(&S.rnd_ready[i], c.lane);
+                for (int q = 0; q < 5; ++q) {
+                    const float4* hw = reinterpret_cast<const float4*>(S.headw + q * HP + col0);
+                    const float4 w0 = hw[0], w1 = hw[1];
+                    o2[q] = __ffma2_rn(make_float2(w0.x, w0.y), make_float2(x[0], x[1]), o2[q]);
+                    o2[q] = __ffma2_rn(make_float2(w0.z, w0.w), make_float2(x[2], x[3]), o2[q]);
+                    o2[q] = __ffma2_rn(make_float2(w1.x, w1.y), make_float2(x[4], x[5]), o2[q]);
+                    o2[q] = __ffma2_rn(make_float2(w1.z, w1.w), make_float2(x[6], x[7]), o2[q]);
+                }
+            } else {
+                tc::tmem_st8(c.tX + uint32_t(col0), x);
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc::split2_f16(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+                const uint32_t a = c.a_row + uint32_t(blk) * 4096u + ((uint32_t(u) ^ c.sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a + SM::PART), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            }
         }
+        if (!HEADS) warp_arrive(&S.rnd_ready[i], c.lane);
     }
     // ---- pass 2, remainder blocks: 4 columns per part
 #pragma unroll
@@ -258,69 +261,99 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
     }
 }
 
-// The control warp's lane 0: MMA issue for every stage of every step of this CTA's tiles, and the weight ring.
+// Two control warps, both running warp-uniform code with one elected lane doing the asynchronous issue (so that the
+// descriptors live in uniform registers and a tcgen05.mma is one predicated instruction, not a per-lane waterfall loop):
+//   issuer   -- the MMAs of every stage of every step of this CTA's tiles.  One instruction stream paces the tensor pipe
+//               (a k-block is 3 MMAs = 312 tensor-pipe clocks), so it carries its ring position, barrier parities and
+//               descriptors incrementally and does nothing else.  (History, ncu in profiles/: with the weight refill and
+//               64-bit block counters in the same thread a block took ~1000 clocks to issue and the pipe idled 80 %.)
+//   producer -- the weight ring: block k of the launch-wide sequence (period L * NB) goes to slot k % RING once the MMAs
+//               that read the slot's previous block have completed (w_empty).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 template <int HP>
-__device__ __forceinline__ void control(Smem<HP>& S, const RolloutParams& p, uint32_t tmem_base, uint64_t steps_total, const uint8_t* img) {
+__device__ __forceinline__ void producer(Smem<HP>& S, const RolloutParams& p, uint32_t steps_total, const uint8_t* img) {
     using SM = Smem<HP>;
-    constexpr int NB = SM::NB, NBF = SM::NBF, NR = SM::NR, RING = SM::RING;
+    constexpr int RING = SM::RING;
+    const uint32_t per_step = uint32_t(p.layers) * SM::NB;
+    const uint8_t* const layers = img + SM::SLOT;            // block 0 of the image is the stem
+    if (steps_total == 0) return;
+    if (elect_one()) {
+        tc::mbar_expect_tx(&S.stem_full, SM::SLOT);
+        tc::bulk_g2s(S.Wstem, img, SM::SLOT, &S.stem_full);
+    }
+    uint32_t slot = 0, par = 1, idx = 0;                     // par: parity of the w_empty phase that frees `slot` (none the first time round)
+    const uint8_t* src = layers;
+    bool first_lap = true;
+    for (uint32_t k = steps_total * per_step; k > 0; --k) {
+        if (!first_lap) tc::mbar_wait(&S.w_empty[slot], par);
+        if (elect_one()) {
+            tc::mbar_expect_tx(&S.w_full[slot], SM::SLOT);
+            tc::bulk_g2s(S.W[slot], src, SM::SLOT, &S.w_full[slot]);
+        }
+        src += SM::SLOT;
+        if (++idx == per_step) { idx = 0; src = layers; }
+        if (++slot == uint32_t(RING)) { slot = 0; par ^= 1u; first_lap = false; }
+    }
+}
+
+template <int HP>
+__device__ __forceinline__ void issuer(Smem<HP>& S, const RolloutParams& p, uint32_t tmem_base, uint32_t steps_total) {
+    using SM = Smem<HP>;
+    constexpr int NBF = SM::NBF, NR = SM::NR, RING = SM::RING;
     const int L = p.layers;
     const uint32_t idesc = tc::make_idesc_f16(128, HP);
+    // descriptors: the address field (bits 0..13, 16-byte units) is the only part that moves, and it never carries out
     const uint64_t dA = tc::make_desc_sw32(tc::smem_addr(S.A[0]), 16, 256), dW = tc::make_desc_sw32(tc::smem_addr(S.W[0]), 16, 256),
                    dS = tc::make_desc_sw32(tc::smem_addr(S.Wstem), 16, 256);
-    const uint8_t* layers = img + SM::SLOT;                  // block 0 of the image is the stem
-    const uint32_t per_step = uint32_t(L) * NB;
-    const uint64_t total = steps_total * per_step;
-    auto load = [&](uint64_t q) {                            // block q of the launch-wide sequence -> slot q % RING
-        const uint32_t slot = uint32_t(q % RING);
-        tc::mbar_expect_tx(&S.w_full[slot], SM::SLOT);
-        tc::bulk_g2s(S.W[slot], layers + size_t(q % per_step) * SM::SLOT, SM::SLOT, &S.w_full[slot]);
-    };
+    const uint32_t dA_lo = uint32_t(dA), dW_lo = uint32_t(dW), d_hi = uint32_t(dA >> 32);
+    auto desc = [&](uint32_t lo) { return uint64_t(lo) | uint64_t(d_hi) << 32; };
     if (steps_total == 0) return;
-    tc::mbar_expect_tx(&S.stem_full, SM::SLOT);
-    tc::bulk_g2s(S.Wstem, img, SM::SLOT, &S.stem_full);
-    for (uint64_t q = 0; q < uint64_t(RING) && q < total; ++q) load(q);
     tc::mbar_wait(&S.stem_full, 0);
-    uint64_t q = 0;                                          // weight blocks issued so far
-    uint32_t use = 0;                                        // uses of the round barriers so far
-    auto issue_block = [&](int blk) {
-        const uint32_t slot = uint32_t(q % RING);
-        tc::mbar_wait(&S.w_full[slot], uint32_t(q / RING) & 1u);
-        const uint64_t ah = dA + uint64_t((uint32_t(blk) * 4096u) >> 4), al = ah + uint64_t(SM::PART >> 4);
-        const uint64_t bh = dW + uint64_t((slot * SM::SLOT) >> 4), bl = bh + uint64_t(SM::WPART >> 4);
-        tc::mma_bf16_ss(tmem_base, al, bh, idesc, blk > 0);
-        tc::mma_bf16_ss(tmem_base, ah, bl, idesc, true);
-        tc::mma_bf16_ss(tmem_base, ah, bh, idesc, true);
-        tc::mma_commit(&S.w_empty[slot]);
-        // refill two blocks behind the issue point: those MMAs have all but certainly drained (in-order pipe)
-        if (q >= 2 && q - 2 + RING < total) {
-            const uint64_t r = q - 2;
-            tc::mbar_wait(&S.w_empty[r % RING], uint32_t(r / RING) & 1u);
-            load(r + RING);
+    uint32_t slot = 0, full_par = 0, w_off = 0;              // slot of the next block, parity of its w_full phase, slot * (SLOT >> 4)
+    auto issue_block = [&](uint32_t a_off, bool first) {     // a_off = (block * 4096) >> 4
+        tc::mbar_wait(&S.w_full[slot], full_par);
+        if (elect_one()) {
+            const uint32_t ah = dA_lo + a_off, al = ah + (SM::PART >> 4), bh = dW_lo + w_off, bl = bh + (SM::WPART >> 4);
+            tc::mma_bf16_ss(tmem_base, desc(al), desc(bh), idesc, !first);
+            tc::mma_bf16_ss(tmem_base, desc(ah), desc(bl), idesc, true);
+            tc::mma_bf16_ss(tmem_base, desc(ah), desc(bh), idesc, true);
+            tc::mma_commit(&S.w_empty[slot]);
         }
-        ++q;
+        w_off += SM::SLOT >> 4;
+        if (++slot == uint32_t(RING)) { slot = 0; w_off = 0; full_par ^= 1u; }
     };
-    for (uint64_t step = 0; step < steps_total; ++step) {
+    uint32_t in_par = 0, rnd_par = 0;
+    for (uint32_t step = 0; step < steps_total; ++step) {
         // stem: the 16 exponents are exact in fp16 (hi part of block 0), so two products against hi | lo of the weights
-        tc::mbar_wait(&S.in_ready, uint32_t(step) & 1u);
+        tc::mbar_wait(&S.in_ready, in_par);
+        in_par ^= 1u;
         tc::fence_after_sync();
-        tc::mma_bf16_ss(tmem_base, dA, dS + uint64_t(SM::WPART >> 4), idesc, false);
-        tc::mma_bf16_ss(tmem_base, dA, dS, idesc, true);
-        tc::mma_commit(&S.mma_done);
-        for (int l = 0; l < L; ++l, ++use) {
-#pragma unroll 1
-            for (int i = 0; i < NBF; ++i) {
-                tc::mbar_wait(&S.rnd_ready[i], use & 1u);
-                tc::fence_after_sync();
-#pragma unroll 1
-                for (int part = 0; part < 4; ++part) issue_block(4 * i + part);
-            }
-#pragma unroll 1
-            for (int r = 0; r < NR; ++r) {
-                tc::mbar_wait(&S.rnd_ready[NBF + r], use & 1u);
-                tc::fence_after_sync();
-                issue_block(4 * NBF + r);
-            }
+        if (elect_one()) {
+            tc::mma_bf16_ss(tmem_base, dA, dS + uint64_t(SM::WPART >> 4), idesc, false);
+            tc::mma_bf16_ss(tmem_base, dA, dS, idesc, true);
             tc::mma_commit(&S.mma_done);
+        }
+        for (int l = 0; l < L; ++l) {
+#pragma unroll
+            for (int i = 0; i < NBF; ++i) {
+                tc::mbar_wait(&S.rnd_ready[i], rnd_par);
+                tc::fence_after_sync();
+#pragma unroll
+                for (int part = 0; part < 4; ++part) issue_block(uint32_t(4 * i + part) * 256u, i == 0 && part == 0);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                tc::mbar_wait(&S.rnd_ready[NBF + r], rnd_par);
+                tc::fence_after_sync();
+                issue_block(uint32_t(4 * NBF + r) * 256u, NBF == 0 && r == 0);
+            }
+            if (elect_one()) tc::mma_commit(&S.mma_done);
+            rnd_par ^= 1u;
         }
     }
 }
@@ -367,7 +400,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
     const uint32_t tmem_base = S.tmem_base;
 
     if (warp == ENV_THREADS / 32) {
-        if (lane == 0) control<HP>(S, p, tmem_base, uint64_t(my_tiles) * uint64_t(p.T), img);
+        issuer<HP>(S, p, tmem_base, uint32_t(my_tiles) * uint32_t(p.T));
+    } else if (warp == ENV_THREADS / 32 + 1) {
+        producer<HP>(S, p, uint32_t(my_tiles) * uint32_t(p.T), img);
     } else {
         // ---------------- row = env in tile = TMEM lane; four threads (column parts) per row
         const LutGlobal lut{p.lut};
@@ -381,7 +416,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
         c.a_row = tc::smem_addr(S.A[0]) + uint32_t(c.row) * 32u;
         c.sw = uint32_t(c.row >> 2) & 1u;
         const int row = c.row;
-        uint64_t st = 0;
+        uint32_t mma_par = 0;                       // parity of the mma_done phase the next stage waits for
         for (int64_t tl = 0; tl < my_tiles; ++tl) {
             const int64_t env = (int64_t(blockIdx.x) + tl * gridDim.x) * 128 + row;
             const bool owner = half == 0 && env < p.B;
@@ -413,8 +448,8 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                 }
                 float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                 // ---- stages: s = 0 stem, s = 1..L residual blocks
-                for (int s = 0; s <= L; ++s, ++st) {
-                    tc::mbar_wait(&S.mma_done, uint32_t(st) & 1u);
+                for (int s = 0; s <= L; ++s, mma_par ^= 1u) {
+                    tc::mbar_wait(&S.mma_done, mma_par);
                     tc::fence_after_sync();
                     if (s == 0) {
                         if (L == 0) epilogue<HP, true, true>(S, c, h, S.ln_g[0], S.ln_b[0], o);
@@ -476,6 +511,9 @@ static int launch(const RolloutParams& p, cudaStream_t st) {
     G2048_CHECK_CUDA(ensure_smem(kern, smem));
     const int64_t ntiles = (p.B + 127) / 128;
     const int grid = int(ntiles < num_sms() ? ntiles : num_sms());
+    const int64_t tiles_per_cta = (ntiles + grid - 1) / grid;
+    if (tiles_per_cta * p.T * (int64_t(p.layers) * (HP / 16) + 1) >= (int64_t(1) << 31))
+        return fail(G2048_ESHAPE, "g2048_rollout_mlp: B * T too large for one launch of the tensor-core kernel; split the horizon");
     kern<<<grid, THREADS, smem, st>>>(p);
     G2048_CHECK_LAUNCH("rollout_mlp_x3_kernel");
     return G2048_OK;
