@@ -85,6 +85,46 @@ __device__ __forceinline__ void tail_sample_and_move(const RolloutParams& p, con
     merge_stats(mv, ts.points, ts.max_tile, ts.ovf);
     ts.moved = from_canonical(moved_c, a);
 }
+// masked softmax + categorical sample only (train.py:266-291), for kernels that computed the Philox draws and the moves
+// ahead of time: `dz` = word 2 of the step's draws
+template <bool FAST = true>
+__device__ __forceinline__ void tail_softmax_sample(const RolloutParams& p, int64_t ri, uint32_t lm, const float (&o)[5], uint32_t dz,
+                                                    TailState& ts) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if ((lm >> j) & 1u) mx = fmaxf(mx, o[j]);
+    float e[4], se = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        e[j] = ((lm >> j) & 1u) ? (FAST ? __expf(o[j] - mx) : expf(o[j] - mx)) : 0.f;
+        se += e[j];
+        ts.lp[j] = o[j];
+        ts.e[j] = e[j];
+    }
+    ts.mx = mx;
+    ts.se = se;
+    uint32_t a;
+    if (p.forced_actions) {
+        a = p.forced_actions[ri] & 3u;
+    } else {
+        const float thr = float(dz >> 8) * (1.0f / 16777216.0f) * se;
+        float cum = 0.f;
+        a = 31u - uint32_t(__clz(int(lm)));
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cum += e[j];
+            if (!found && ((lm >> j) & 1u) && thr < cum) {
+                a = uint32_t(j);
+                found = true;
+            }
+        }
+    }
+    ts.a = a;
+    ts.lm = lm;
+    ts.value = o[4];
+}
 // part 0, second third: spawn, legal mask, flags (game.py:1005-1006)
 template <bool FAST = true>
 __device__ __forceinline__ Board tail_spawn(Board board, TailState& ts) {

@@ -31,9 +31,25 @@ constexpr int THREADS = ENV_THREADS + 64;         // + two control warps: MMA is
 constexpr uint32_t X_COL = 256;
 constexpr int MAX_LAYERS = 4;
 
+// The move of one env in one direction, computed ahead of the policy's choice (see precompute_moves).
+struct MovePre {
+    uint64_t moved;          // board after the move, before the spawn
+    uint32_t pa[2];          // packed potentials of `moved`
+    int32_t points;          // merge points
+    uint32_t meta;           // bit 0 valid (the move changes the board), bit 1 nibble overflow, bits 8.. largest exponent created
+};
+// Per-env exchange between the four threads of a row.
+struct Xch {
+    uint64_t board;          // the board the step starts from (part 0, at the start of the step)
+    uint32_t pb[2];          // packed potentials of `board` (part 2)
+    uint32_t draw[3];        // the step's Philox draws: spawn cell, spawn value, action (part 1)
+    uint32_t pad_;
+};
+
 constexpr int ring_slots(int HP) {
-    // what is left of 227 KB after the operand tile, the stem block and ~30 KB of parameters / exchange buffers
-    const int fixed = 2 * (HP / 16) * 4096 + HP * 64 + (1 + 2 * (MAX_LAYERS + 1)) * HP * 4 + (5 * HP + 8) * 4 + 16384 + 2048;
+    // what is left of 227 KB after the operand tile, the stem block, the parameters and the exchange buffers
+    const int fixed = 2 * (HP / 16) * 4096 + HP * 64 + (1 + 2 * (MAX_LAYERS + 1)) * HP * 4 + (5 * HP + 8) * 4 +
+                      2 * 4 * 128 * 4 + 3 * 128 * 5 * 4 + 128 * int(sizeof(Xch)) + 128 * 4 * int(sizeof(MovePre)) + 1024;
     const int n = (232448 - fixed) / (HP * 64);
     return n > 8 ? 8 : n;
 }
@@ -57,7 +73,8 @@ struct Smem {
     alignas(16) float headw[5 * HP + 8];
     float red[2][SPLIT][128];                     // [sum | sq][column part][row]
     float headp[SPLIT - 1][128][5];               // partial head dots of parts 1..3
-    TcXch xch[128];
+    Xch xch[128];
+    alignas(8) MovePre pre[128][4];
     uint64_t in_ready, mma_done, stem_full, rnd_ready[ROUNDS > 0 ? ROUNDS : 1], w_full[RING], w_empty[RING];
     uint32_t tmem_base;
 };
@@ -71,6 +88,47 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     tc::fence_async_smem();
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(bar);
+}
+
+// While the tensor pipe runs the first residual block, the four threads of a row play the env's move in all four
+// directions (thread `dir` = its column part: lookups, merge points, potentials of the moved board) and park the results
+// in shared memory; part 1 also draws the step's Philox numbers, part 2 (LEFT: its lookups are the board's own rows) the
+// potentials of the current board.  The tail of the step -- after the heads -- then only samples, picks the chosen
+// direction's result, spawns and records: ~1000 dependent instructions with three rounds of L2 table reads and two
+// 512-thread barriers left the critical path (they sat there with one active warp per scheduler; ncu, profiles/).
+template <int HP>
+__device__ __forceinline__ void precompute_moves(Smem<HP>& S, const RolloutParams& p, const LutGlobal& lut, int row, uint32_t dir,
+                                                 int64_t env, uint64_t ctr) {
+    const Board board = make_board(S.xch[row].board);
+    const Board bt = transpose(board);
+    const Board canon = to_canonical(board, bt, dir);
+    const Lines mv = lookup_rows(canon, lut);
+    Lines cols = mv;
+    if (dir == 2u) cols = lookup_rows(bt, lut);          // in flight with the rows
+    if (dir == 1u) {
+        const U4 d = env_draws(p.seed, p.env0 + uint64_t(env), ctr);
+        S.xch[row].draw[0] = d.x;
+        S.xch[row].draw[1] = d.y;
+        S.xch[row].draw[2] = d.z;
+    }
+    const Board moved_c = result_of(mv);
+    const bool valid = !same(moved_c, canon);
+    int points, max_tile;
+    bool ovf;
+    merge_stats(mv, points, max_tile, ovf);
+    const Board moved = from_canonical(moved_c, dir);
+    const uint2 pa = pack_potentials(potentials(moved, lookup_rows(moved_c, lut), lookup_rows(transpose(moved_c), lut)));
+    if (dir == 2u) {
+        const uint2 pb = pack_potentials(potentials(board, mv, cols));
+        S.xch[row].pb[0] = pb.x;
+        S.xch[row].pb[1] = pb.y;
+    }
+    MovePre& m = S.pre[row][dir];
+    m.moved = pack_board(moved);
+    m.pa[0] = pa.x;
+    m.pa[1] = pa.y;
+    m.points = points;
+    m.meta = uint32_t(valid) | uint32_t(ovf) << 1 | uint32_t(max_tile) << 8;
 }
 
 struct RowCtx {
@@ -447,6 +505,10 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                     warp_arrive(&S.in_ready, lane);
                 }
                 float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                if (L == 0) {                                        // no MMA shadow to hide in: play the moves up front
+                    env_sync();
+                    precompute_moves<HP>(S, p, lut, row, uint32_t(half), env, ctr);
+                }
                 // ---- stages: s = 0 stem, s = 1..L residual blocks
                 for (int s = 0; s <= L; ++s, mma_par ^= 1u) {
                     tc::mbar_wait(&S.mma_done, mma_par);
@@ -454,36 +516,30 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                     if (s == 0) {
                         if (L == 0) epilogue<HP, true, true>(S, c, h, S.ln_g[0], S.ln_b[0], o);
                         else epilogue<HP, true, false>(S, c, h, S.ln_g[0], S.ln_b[0], o);
+                        // the board of this step is visible to the whole row since the barrier inside the epilogue; what
+                        // is written here is read after the barriers of the later epilogues
+                        if (L > 0) precompute_moves<HP>(S, p, lut, row, uint32_t(half), env, ctr);
                     } else if (s == L) {
                         epilogue<HP, false, true>(S, c, h, S.ln_g[s], S.ln_b[s], o);
                     } else {
                         epilogue<HP, false, false>(S, c, h, S.ln_g[s], S.ln_b[s], o);
                     }
                 }
-                // ---- policy + env-step tail over the row's threads (g2048_rollout_tail.cuh); barriers taken by all 512
+                // ---- tail (part 0): sample, take the chosen direction's move, spawn, record (train.py:266-326)
                 const int64_t ri = int64_t(t) * p.B + env;
-                TailState ts;
-                const bool act = owner && alive;
-                if (half == 1) {
-                    const uint2 pb = board_potentials(make_board(S.xch[row].board), lut);
-                    S.xch[row].pb[0] = pb.x;
-                    S.xch[row].pb[1] = pb.y;
-                }
-                if (act) {
-                    tail_sample_and_move<false>(p, lut, ri, env, ctr, lm, o, board, ts);
-                    S.xch[row].moved = pack_board(ts.moved);
-                }
-                env_sync();
-                if (half == 2) {
-                    const uint2 pa = board_potentials(make_board(S.xch[row].moved), lut);
-                    S.xch[row].moved = uint64_t(pa.x) | uint64_t(pa.y) << 32;
-                }
-                Board next = board;
-                if (act) next = tail_spawn<false>(board, ts);
-                env_sync();
-                if (act) {
-                    const uint64_t paw = S.xch[row].moved;
-                    tail_record(p, ri, board, ts, make_uint2(S.xch[row].pb[0], S.xch[row].pb[1]), make_uint2(uint32_t(paw), uint32_t(paw >> 32)));
+                if (owner && alive) {
+                    TailState ts;
+                    tail_softmax_sample<false>(p, ri, lm, o, S.xch[row].draw[2], ts);
+                    const MovePre m = S.pre[row][ts.a];
+                    ts.u0 = S.xch[row].draw[0];
+                    ts.u1 = S.xch[row].draw[1];
+                    ts.moved = make_board(m.moved);
+                    ts.points = m.points;
+                    ts.valid = (m.meta & 1u) != 0u;
+                    ts.ovf = (m.meta & 2u) != 0u;
+                    ts.max_tile = int(m.meta >> 8);
+                    const Board next = tail_spawn<false>(board, ts);
+                    tail_record(p, ri, board, ts, make_uint2(S.xch[row].pb[0], S.xch[row].pb[1]), make_uint2(m.pa[0], m.pa[1]));
                     board = next;
                     if (ts.flags & FLAG_DONE) {
                         if (p.auto_reset) board = reset_board(env_draws(p.seed ^ RESET_KEY_TWEAK, p.env0 + uint64_t(env), ctr));
