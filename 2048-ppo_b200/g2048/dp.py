@@ -18,6 +18,9 @@ import torch
 import torch.distributed as dist
 
 
+COLLECTIVES = True      # bench.py switches the all-reduces off to time a rank alone on its shard
+
+
 def world() -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -33,7 +36,7 @@ def shard_range(total: int, rank: int, world_size: int) -> tuple[int, int]:
 
 def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """Sum a small float64 vector over ranks (in place); no-op without a process group."""
-    if world()[1] > 1:
+    if world()[1] > 1 and COLLECTIVES:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats
 
@@ -71,7 +74,7 @@ class FlatGradBucket:
 
     def allreduce(self, group=None) -> None:
         self.attach()
-        if world()[1] > 1:
+        if world()[1] > 1 and COLLECTIVES:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
     def clip_norm_(self, max_norm: float) -> torch.Tensor:

@@ -41,6 +41,25 @@ BYTES_PER_TRANSITION = 30      # 8 board in + 1 action + 8 board out + 4 points 
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 70.5e6
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
+WORKLOAD = ("c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step "
+            "(move+merge points+shaping+Philox spawn+legal/done)")
+
+
+def python_reference(seconds: float = 2.0):
+    """BASELINE.md section 3 B1-B3 on the UNMODIFIED Python reference staged under baseline/_ref (own process: its worker
+    pool must not fork a CUDA context).  None when the reference is not staged."""
+    import subprocess
+    script = os.path.join(ROOT, "baseline", "time_reference.py")
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "game.py")):
+        return {"unavailable": "baseline/_ref is not staged on this box"}
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):     # torchrun exports OMP_NUM_THREADS=1
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, script, "--seconds", str(seconds)], capture_output=True, text=True, timeout=240, env=env)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:          # a baseline that cannot run is reported, not fatal
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def c2_boards(seed: int) -> np.ndarray:
@@ -150,15 +169,17 @@ def cpu_baseline(min_seconds: float = 10.0):
 
 
 def run_reference(args):
+    """The reference's CPU algorithm for the path on every host thread: the C port (oracle/oracle2048.c, OpenMP) steps the
+    same 4 194 304 C2 transitions per step as our arm; the UNMODIFIED Python reference (baseline/_ref) is timed beside it on
+    a bounded sample (it runs ~4e3 env-steps/s/core: a full step would take minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import oracle as O
     O.set_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every core
     boards, actions = c2_transitions(2048)
-    n = 1 << 20   # bounded sample of the 4M-transition step
-    idx = (np.arange(n) % MOVES) * N_BOARDS + (np.arange(n) // MOVES)
-    b, a = np.ascontiguousarray(boards.view(np.uint64)[idx]), np.ascontiguousarray(actions[idx])
+    b, a = np.ascontiguousarray(boards.view(np.uint64)), np.ascontiguousarray(actions)
+    n = N_TRANS
     for w in range(args.warmup):
         O.step_batch(b, a, seed=1, env0=0, ctr=w)
     t0 = time.perf_counter()
@@ -166,77 +187,124 @@ def run_reference(args):
         O.step_batch(b, a, seed=1, env0=0, ctr=100 + k)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
-    sample = f"each step = {n} of the {N_TRANS} C2 transitions, oracle/oracle2048.c orc_step_batch, {O.num_threads()} OpenMP threads"
+    sample = f"each step = all {N_TRANS} C2 transitions, oracle/oracle2048.c orc_step_batch, {O.num_threads()} OpenMP threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "c2_env_step: 2^20 boards x 4 moves, full Game2048.step", "sample_per_step": n},
+        "config": {"workload": WORKLOAD, "boards": N_BOARDS, "moves": MOVES},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "python_reference": python_reference(2.0),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def rollout_section(args, dev, world, rank, barrier):
-    """Config C3 (per GPU; C4 when world > 1): GameMLP h=196 L=2, 65536 envs x 512 steps, Kaiming init
-    with non-zero heads, README reward flags.  Times the fused rollout kernel alone and the full
-    rollout + advantage + update (+ gradient / moment all-reduce) train step."""
+    """BASELINE configs C3 / C4 / C5.
+      C3 (N = 1 only): GameMLP h=196 L=2, 65536 envs x 512 steps on one GPU, Kaiming init with non-zero heads, README reward
+          flags: the fused rollout kernel alone (the fp32-grade split-fp16 tcgen05 kernel that `auto` selects, with the fp32
+          FFMA kernel and the bf16 tcgen05 kernel as labelled variants) and the full rollout + advantage + update train step.
+      C4 (every N): 2^20 envs x 512 steps in total, sharded contiguously over the N ranks (N = 1: the one-GPU time of the same
+          job, the denominator of the strong-scaling figure), rollout + update with the flat-gradient and moment all-reduces;
+          the same step with the collectives switched off (each rank on its own shard: what one GPU does with that per-GPU
+          env count) and the gradient all-reduce timed on its own.
+      C5: GameURM rollout."""
     import torch
     import torch.distributed as dist
 
-    from g2048 import trainer as tr
+    from g2048 import dp, trainer as tr
 
-    envs_per_gpu, horizon = args.rollout_envs, args.rollout_steps
-    cfg = tr.TrainConfig(hidden_dim=196, num_layers=2, envs=envs_per_gpu * world, horizon=horizon, zero_heads=False,
-                         seed=2048)
-    t = tr.Trainer(cfg, dev)
-    n_local = envs_per_gpu * horizon
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 2
+    flops = 2 * (48 * 196 + 2 * 196 * 196 + 5 * 196)
 
-    def time_rollout(precision):
-        cfg.rollout_precision = precision
-        t.collect()
-        barrier()
-        ev0.record()
-        for _ in range(reps):
-            t.collect()
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1) / reps
-        if world > 1:
-            v = torch.tensor([ms], device=dev)
-            dist.all_reduce(v, op=dist.ReduceOp.MAX)
-            ms = float(v.item())
-        return ms
-
-    # rollout only: fp32 FFMA kernel (parity-grade) and bf16 tcgen05 kernel (what "auto" picks at this size)
-    ro_fp32_ms = time_rollout("fp32")
-    ro_ms = time_rollout("bf16")
-    cfg.rollout_precision = "auto"
-    # rollout + update: the headline is the fused tcgen05 update (g2048.update); the autograd variants with the
-    # x3 GEMM kernels, cuBLAS fp32 and cuBLAS TF32 are reported beside it
-    def time_train(matmul):
-        cfg.update_matmul = matmul
-        t.train_step()
-        barrier()
-        ev0.record()
-        for _ in range(reps):
-            st = t.train_step()
-        ev1.record()
-        barrier()
-        return ev0.elapsed_time(ev1) / reps, st, t.times
-
-    tf32_ms, _, _ = time_train("tf32")
-    fp32_ms, _, _ = time_train("fp32")
-    x3_ms, _, _ = time_train("x3")
-    step_ms, stats, times = time_train("fused")
-    if world > 1:
-        v = torch.tensor([step_ms, tf32_ms, fp32_ms, x3_ms], device=dev)
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals if len(vals) > 1 else vals[0]
+        v = torch.tensor(list(vals), device=dev, dtype=torch.float64)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        step_ms, tf32_ms, fp32_ms, x3_ms = (float(x) for x in v.tolist())
-    # ---- C5: GameURM rollout (default config), a few steps at the configured env count
-    urm = None
+        out = tuple(float(x) for x in v.tolist())
+        return out if len(out) > 1 else out[0]
+
+    def timed(fn, reps):
+        fn()                       # warm-up (allocations, first-launch costs)
+        barrier()
+        ev0.record()
+        for _ in range(reps):
+            r = fn()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1) / reps, r
+
+    def measure(envs_total, horizon, reps, variants):
+        cfg = tr.TrainConfig(hidden_dim=196, num_layers=2, envs=envs_total, horizon=horizon, zero_heads=False, seed=2048)
+        t = tr.Trainer(cfg, dev)
+        n_global = envs_total * horizon
+        res = {"envs_total": envs_total, "envs_per_gpu": t.B, "horizon": horizon, "timing_reps": reps}
+
+        def time_rollout(precision, r):
+            cfg.rollout_precision = precision
+            ms, _ = timed(t.collect, r)
+            return max_over_ranks(ms)
+
+        ro_ms = time_rollout("auto", reps)
+        res["rollout_ms"] = ro_ms
+        res["env_steps_per_sec"] = n_global / (ro_ms * 1e-3)
+        res["rollout_kernel"] = ("rollout_mlp_x3_kernel<208> (tcgen05.mma on split-fp16 operands: hi*hi + hi*lo + lo*hi, fp32 accumulate "
+                                 "in TMEM; log-probs / values within 2e-5 of the fp32 policy)")
+        res["rollout_model_tflops"] = res["env_steps_per_sec"] * flops / 1e12
+        res["rollout_mma_tflops"] = 3 * res["rollout_model_tflops"]
+        res["rollout_frac_of_bf16_peak_mma"] = 3 * (res["env_steps_per_sec"] / world) * flops / 1e12 / bf16_peak()
+        if variants:
+            ms = time_rollout("fp32", max(3, reps // 3))
+            res["fp32_ffma_rollout_variant"] = {"ms": ms, "env_steps_per_sec": n_global / (ms * 1e-3), "kernel": "rollout_mlp_kernel<208>"}
+            ms = time_rollout("bf16", reps)
+            res["bf16_rollout_variant"] = {"ms": ms, "env_steps_per_sec": n_global / (ms * 1e-3), "kernel": "rollout_mlp_tc_kernel<208>",
+                                           "note": "bf16-rounded operands: log-probs ~1e-2 off the fp32 policy -- NOT reference precision, never selected by `auto`"}
+        cfg.rollout_precision = "auto"
+        step_ms, stats = timed(t.train_step, reps)
+        times = t.times
+        step_ms = max_over_ranks(step_ms)
+        res["train_step_ms"] = step_ms
+        res["rollout_update_steps_per_sec"] = n_global / (step_ms * 1e-3)
+        res["phase_ms_rank0"] = {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
+                                 "grad_allreduce_last_step": times.grad_allreduce_ms, "moments_allreduce": times.allreduce_ms}
+        res["loss"] = stats["loss"]
+        if world > 1:
+            # the same train step without the collectives: every rank alone on its shard
+            dp.COLLECTIVES = False
+            local_ms, _ = timed(t.train_step, reps)
+            dp.COLLECTIVES = True
+            local_ms = max_over_ranks(local_ms)
+            res["train_step_ms_without_collectives"] = local_ms
+            res["weak_scaling_efficiency_vs_same_per_gpu_envs"] = local_ms / step_ms
+            ar_ms, _ = timed(lambda: t.bucket.allreduce(), 50)
+            res["grad_allreduce_ms"] = max_over_ranks(ar_ms)
+            res["grad_allreduce_bytes"] = t.bucket.numel() * 4
+        if variants and args.update_variants:
+            for name in ("tf32", "fp32", "x3"):
+                cfg.update_matmul = name
+                ms, _ = timed(t.train_step, 2)
+                res[f"{name}_autograd_update_variant"] = {"train_step_ms": max_over_ranks(ms)}
+            cfg.update_matmul = "fused"
+        del t
+        torch.cuda.empty_cache()
+        return res
+
+    out = {"model_flops_per_env_step": flops,
+           "update": "update_mlp_kernel (one tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-bf16 GEMMs: x6 forward, "
+                     "x3 backward) + x3_wgrad_kernel weight gradients, Muon+AdamW"}
+    if world == 1:
+        c3 = measure(args.rollout_envs, args.rollout_steps, 10, True)
+        c3["workload"] = (f"c3: GameMLP h=196 L=2 fused rollout, {args.rollout_envs} envs x {args.rollout_steps} steps on one GPU, "
+                          "auto-reset, Philox seed 2048")
+        out["c3"] = c3
+    if args.c4_envs > 0:
+        per_gpu = args.c4_envs // world
+        c4 = measure(args.c4_envs, args.rollout_steps, 3 if per_gpu >= (1 << 19) else 5, False)
+        c4["workload"] = (f"c4: {args.c4_envs} envs x {args.rollout_steps} steps in total, sharded over {world} GPU(s) "
+                          f"({per_gpu} envs per GPU), rollout + advantage + fused update + flat-gradient all-reduce (NCCL) + Muon/AdamW")
+        out["c4"] = c4
+    # ---- C5: GameURM rollout (default config) at the configured env count
     if args.urm_envs > 0:
         from g2048 import env as genv, rollout as gro
         from g2048.policy import GameURM, GameURMConfig
@@ -245,46 +313,18 @@ def rollout_section(args, dev, world, rank, barrier):
         upol = gro.pack_policy(um)
         ub = genv.reset(args.urm_envs, device=dev, seed=5, env0=rank * args.urm_envs, ctr=0)
         ubuf = gro.RolloutBuffers.allocate(args.urm_steps, args.urm_envs, dev)
-        gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=1, out=ubuf)
-        barrier()
-        ev0.record()
-        gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=1 + args.urm_steps, out=ubuf)
-        ev1.record()
-        barrier()
-        ums = ev0.elapsed_time(ev1)
-        if world > 1:
-            v = torch.tensor([ums], device=dev)
-            dist.all_reduce(v, op=dist.ReduceOp.MAX)
-            ums = float(v.item())
-        urm = {"workload": f"c5: GameURM (hidden 64, 2 layers, 4 heads, 4 loops) fused rollout, {args.urm_envs} envs x {args.urm_steps} steps per GPU",
-               "env_steps_per_sec": world * args.urm_envs * args.urm_steps / (ums * 1e-3), "ms": ums,
-               "kernel": "rollout_urm_kernel (bf16 tcgen05.mma projections, CUDA-core attention)"}
-        del ubuf, ub
+        ctr = [1]
 
-    flops = 2 * (48 * 196 + 2 * 196 * 196 + 5 * 196)
-    env_sps = world * n_local / (ro_ms * 1e-3)
-    return {
-        "workload": f"c3: GameMLP h=196 L=2 fused rollout, {envs_per_gpu} envs x {horizon} steps per GPU, auto-reset, Philox seed 2048",
-        "env_steps_per_sec": env_sps,
-        "rollout_ms": ro_ms,
-        "rollout_kernel": "rollout_mlp_tc_kernel<208> (bf16 tcgen05.mma, fp32 accumulate in TMEM)",
-        "fp32_ffma_rollout": {"ms": ro_fp32_ms, "env_steps_per_sec": world * n_local / (ro_fp32_ms * 1e-3),
-                              "kernel": "rollout_mlp_kernel<208>"},
-        "rollout_update_steps_per_sec": world * n_local / (step_ms * 1e-3),
-        "train_step_ms": step_ms,
-        "update": "update_mlp_kernel (one tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-bf16 GEMMs: x6 forward, x3 backward) + x3_wgrad_kernel weight gradients, Muon+AdamW",
-        "x3_autograd_update_variant": {"train_step_ms": x3_ms, "rollout_update_steps_per_sec": world * n_local / (x3_ms * 1e-3)},
-        "cublas_fp32_update_variant": {"train_step_ms": fp32_ms, "rollout_update_steps_per_sec": world * n_local / (fp32_ms * 1e-3)},
-        "cublas_tf32_update_variant": {"train_step_ms": tf32_ms, "rollout_update_steps_per_sec": world * n_local / (tf32_ms * 1e-3)},
-        "phase_ms_rank0": {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
-                           "moments_allreduce": times.allreduce_ms},
-        "model_flops_per_env_step": flops,
-        "rollout_model_tflops": env_sps * flops / 1e12,
-        "rollout_frac_of_bf16_peak": (env_sps / world) * flops / 1e12 / bf16_peak(),
-        "grad_allreduce_bytes": 88401 * 4,
-        "urm": urm,
-        "loss": stats["loss"],
-    }
+        def urm_once():
+            gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=ctr[0], out=ubuf)
+            ctr[0] += args.urm_steps
+        ums, _ = timed(urm_once, 2)
+        ums = max_over_ranks(ums)
+        out["urm"] = {"workload": f"c5: GameURM (hidden 64, 2 layers, 4 heads, 4 loops) fused rollout, {args.urm_envs} envs x {args.urm_steps} steps per GPU",
+                      "env_steps_per_sec": world * args.urm_envs * args.urm_steps / (ums * 1e-3), "ms": ums,
+                      "kernel": "rollout_urm_kernel (bf16 tcgen05.mma projections, CUDA-core attention)"}
+        del ubuf, ub
+    return out
 
 
 def run_ours(args):
@@ -512,8 +552,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step (move+merge points+shaping+Philox spawn+legal/done), one g2048_step launch",
-                       "boards": N_BOARDS, "moves": MOVES, "l2": f"ring of {RING} distinct 120 MiB buffer sets (> 126 MB L2) used round-robin",
+            "config": {"workload": WORKLOAD, "boards": N_BOARDS, "moves": MOVES, "kernel_launches_per_step": 1, "l2": f"ring of {RING} distinct 120 MiB buffer sets (> 126 MB L2) used round-robin",
                        "spawn": "philox4x32-10", "launch": "the K timed launches are one replay of a CUDA graph (after one untimed replay that uploads it)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -530,6 +569,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
             line["rollout"] = ro
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            line["cpu_baseline"]["python_reference"] = python_reference(2.0)
         print(json.dumps(line))
 
 
@@ -545,8 +585,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     ap.add_argument("--rollout-envs", type=int, default=65536)
     ap.add_argument("--rollout-steps", type=int, default=512)
+    ap.add_argument("--c4-envs", type=int, default=1 << 20, help="config #4: total env count sharded over the GPUs (0 = skip)")
+    ap.add_argument("--update-variants", action="store_true", help="also time the autograd update variants (cuBLAS fp32 / TF32, x3 GEMMs)")
     ap.add_argument("--urm-envs", type=int, default=262144, help="config #5 env count per GPU (0 = skip)")
-    ap.add_argument("--urm-steps", type=int, default=4)
+    ap.add_argument("--urm-steps", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
