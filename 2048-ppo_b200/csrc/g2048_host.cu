@@ -57,8 +57,7 @@ int g2048_init(int device) {
     int major = 0;
     G2048_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     if (major != 10) return g2048::fail(G2048_EARCH, "device %d has compute capability %d.x; this library is sm_100a only", device, major);
-    G2048_CHECK_CUDA(cudaSetDevice(device));
-    return G2048_OK;
+    return G2048_OK;      // a check only: the caller's current device is left alone (every entry point runs on the stream it is given)
 }
 
 }  // extern "C"

@@ -2,13 +2,15 @@
 // operands staged in 128B-swizzled K-major shared memory and the fp32 accumulator in TMEM.
 // Exists to pin the descriptor / swizzle / TMEM conventions of g2048_tc.cuh on real hardware
 // (tests/test_tc_gpu.py) before the fused rollout kernel relies on them.
+#include <cuda_fp16.h>
 #include "g2048_host.h"
 #include "g2048_tc.cuh"
 
 namespace g2048 {
 
 __global__ void __launch_bounds__(128, 1)
-tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C, int K, int N) {
+tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ C, int K, int N, int a_f16,
+                        int w_f16) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -31,18 +33,21 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W
 
     for (int i = tid; i < 128 * K; i += 128) {
         const int r = i / K, k = i % K;
-        *reinterpret_cast<__nv_bfloat16*>(sA + tc::sw128_offset(128, r, k)) = __float2bfloat16(A[i]);
+        if (a_f16) *reinterpret_cast<__half*>(sA + tc::sw128_offset(128, r, k)) = __float2half_rn(A[i]);
+        else *reinterpret_cast<__nv_bfloat16*>(sA + tc::sw128_offset(128, r, k)) = __float2bfloat16(A[i]);
     }
     for (int i = tid; i < N * K; i += 128) {
         const int r = i / K, k = i % K;
-        *reinterpret_cast<__nv_bfloat16*>(sB + tc::sw128_offset(N, r, k)) = __float2bfloat16(W[i]);
+        if (w_f16) *reinterpret_cast<__half*>(sB + tc::sw128_offset(N, r, k)) = __float2half_rn(W[i]);
+        else *reinterpret_cast<__nv_bfloat16*>(sB + tc::sw128_offset(N, r, k)) = __float2bfloat16(W[i]);
     }
     tc::fence_async_smem();
     __syncthreads();
 
     if (tid == 0) {
         tc::fence_after_sync();
-        const uint32_t idesc = tc::make_idesc_bf16(128, N);
+        // kind::f16 takes the A and B formats separately (bits 7..9 / 10..12: 0 = f16, 1 = bf16)
+        const uint32_t idesc = tc::make_idesc_f16(128, N) | (a_f16 ? 0u : 1u << 7) | (w_f16 ? 0u : 1u << 10);
         const uint32_t a0 = tc::smem_addr(sA), b0 = tc::smem_addr(sB);
         for (int ks = 0; ks < K / tc::UMMA_K; ++ks) {
             const uint32_t blk = ks >> 2, j = ks & 3;
@@ -67,6 +72,11 @@ tc_gemm_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W
 }  // namespace g2048
 
 extern "C" int g2048_tc_gemm_selftest(const float* A, const float* W, float* C, int32_t K, int32_t N, void* stream) {
+    return g2048_tc_gemm_selftest_fmt(A, W, C, K, N, 0, 0, stream);
+}
+
+extern "C" int g2048_tc_gemm_selftest_fmt(const float* A, const float* W, float* C, int32_t K, int32_t N, int32_t a_f16, int32_t w_f16,
+                                          void* stream) {
     using namespace g2048;
     G2048_REQUIRE(A && W && C, "g2048_tc_gemm_selftest: NULL pointer argument");
     G2048_REQUIRE(K >= 16 && K <= 256 && K % 16 == 0, "g2048_tc_gemm_selftest: K must be a multiple of 16 in [16,256]");
@@ -75,7 +85,7 @@ extern "C" int g2048_tc_gemm_selftest(const float* A, const float* W, float* C, 
     const int smem = kblocks * 128 * (128 + N);
     G2048_REQUIRE(smem <= 220 * 1024, "g2048_tc_gemm_selftest: tile does not fit shared memory");
     G2048_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    tc_gemm_selftest_kernel<<<1, 128, smem, cudaStream_t(stream)>>>(A, W, C, K, N);
+    tc_gemm_selftest_kernel<<<1, 128, smem, cudaStream_t(stream)>>>(A, W, C, K, N, a_f16, w_f16);
     G2048_CHECK_LAUNCH("tc_gemm_selftest_kernel");
     return G2048_OK;
 }

@@ -70,13 +70,15 @@ __global__ void final_reduce_kernel(const double* __restrict__ partials, int nbl
 __global__ void __launch_bounds__(128)
 rtg_adv_kernel(const int32_t* __restrict__ points, const uint64_t* __restrict__ shaping,
                const uint8_t* __restrict__ flags, const float* __restrict__ value, int T, int64_t B, double gamma,
-               double w_points, double w_mono, double w_empt, double mu_c, double inv_sd,
+               double w_points, double w_mono, double w_empt, double mu_c, double inv_sd, const float* __restrict__ bootstrap,
                float* __restrict__ reward_out, float* __restrict__ g_raw_out, float* __restrict__ g_norm_out,
                float* __restrict__ adv_out, double* __restrict__ partials) {
     int64_t b = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     double acc[3] = {0.0, 0.0, 0.0};
     if (b < B) {
-        double g = 0.0;
+        // return-to-go after the last slot: 0 as in the reference (an episode cut by max_steps, train.py:724-728), or the
+        // caller's estimate for a game that continues past the buffer; a DONE move or an invalid slot resets it either way
+        double g = bootstrap ? double(bootstrap[b]) : 0.0;
 #pragma unroll 4
         for (int t = T - 1; t >= 0; --t) {
             const int64_t i = int64_t(t) * B + b;
@@ -167,6 +169,14 @@ int g2048_rtg_advantage(const int32_t* points, const uint64_t* shaping, const ui
                         int32_t T, int64_t B, double gamma, double w_points, double w_mono, double w_empt,
                         double mu_corrected, double stddev, float* reward_out, float* g_raw_out, float* g_norm_out,
                         float* adv_out, double* stats_out, void* workspace, void* stream) {
+    return g2048_rtg_advantage_bootstrap(points, shaping, flags, value, nullptr, T, B, gamma, w_points, w_mono, w_empt, mu_corrected,
+                                         stddev, reward_out, g_raw_out, g_norm_out, adv_out, stats_out, workspace, stream);
+}
+
+int g2048_rtg_advantage_bootstrap(const int32_t* points, const uint64_t* shaping, const uint8_t* flags, const float* value,
+                                  const float* bootstrap, int32_t T, int64_t B, double gamma, double w_points, double w_mono,
+                                  double w_empt, double mu_corrected, double stddev, float* reward_out, float* g_raw_out,
+                                  float* g_norm_out, float* adv_out, double* stats_out, void* workspace, void* stream) {
     G2048_REQUIRE(T >= 0 && B >= 0, "g2048_rtg_advantage: negative shape");
     G2048_REQUIRE(stats_out != nullptr, "g2048_rtg_advantage: stats_out is NULL");
     cudaStream_t st = cudaStream_t(stream);
@@ -183,7 +193,7 @@ int g2048_rtg_advantage(const int32_t* points, const uint64_t* shaping, const ui
         return fail(G2048_EINVAL, "g2048_rtg_advantage: B=%lld exceeds the %lld-column limit of one call", (long long)B,
                     (long long)(MAX_REDUCE_BLOCKS * threads));
     rtg_adv_kernel<<<unsigned(blocks), threads, 0, st>>>(points, shaping, flags, value, T, B, gamma, w_points, w_mono,
-                                                         w_empt, mu_corrected, 1.0 / (stddev + 1e-8), reward_out,
+                                                         w_empt, mu_corrected, 1.0 / (stddev + 1e-8), bootstrap, reward_out,
                                                          g_raw_out, g_norm_out, adv_out, partials);
     G2048_CHECK_LAUNCH("rtg_adv_kernel");
     final_reduce_kernel<3><<<1, 256, 0, st>>>(partials, int(blocks), stats_out);

@@ -231,7 +231,7 @@ struct RowCtx {
 
 // Forward epilogue of LayerNorm l: h_l = [h_{l-1} +] relu(LN(z_l)); writes X (TMEM), the next A operand,
 // h_out[l], the z scratch (l < L) and, for l == L, the 5 head dot products (complete on part 0).
-template <bool STEM>
+template <bool STEM, bool DROP>
 __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, float (&o)[5], uint64_t& keep_bits) {
     const int HP = p.HP, h = p.h, L = p.L;
     const bool last = l == L;
@@ -281,7 +281,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
         if (STEM) tc::tmem_ld8(c.tD + uint32_t(8 * g), z);
         else tc::tmem_ld8x2(c.tD + uint32_t(8 * g), z, c.tX + uint32_t(8 * g), x);
         uint32_t keep = 0xFFu;
-        if (!STEM && p.drop_thr) {
+        if (!STEM && DROP) {
             keep = dropout_keep8(p, p.sample0 + c.grow, l, col);
             keep_bits |= uint64_t(keep) << (8 * g);
         }
@@ -290,7 +290,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
             if (STEM) z[j] += S.b0[col + j];
             const float y = fmaf(fmaf(z[j], rstd, shift), gam[8 * g + j], bet[8 * g + j]);
             float r = fmaxf(y, 0.f);
-            if (!STEM && p.drop_thr) r = ((keep >> j) & 1u) ? r * p.drop_scale : 0.f;
+            if (!STEM && DROP) r = ((keep >> j) & 1u) ? r * p.drop_scale : 0.f;
             x[j] = STEM ? r : x[j] + r;
         }
         tc::tmem_st8(c.tX + uint32_t(8 * g), x);
@@ -330,11 +330,12 @@ __device__ __forceinline__ void fwd_epilogue(Smem& S, const Params& p, const Row
 // Backward through LayerNorm l and its ReLU.  first (l == L): z_L is still in D and dh_L comes from the head
 // gradients; otherwise z_l comes from the scratch and dh_l = X + D (D = dz_{l+1} W_{l+1}).
 // Pass A stores xhat in D and dh_l in X, pass B turns them into dz_l (-> dz_out[l], next A operand).
+template <bool DROP>
 __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const RowCtx& c, int l, bool first, uint64_t keep_bits) {
     // keep_bits: the forward's dropout mask of this thread's columns in block l (bit 8 g + j); the gradient passes through
     // Dropout as g * keep / (1 - p)
-    const float dscale = (l > 0 && p.drop_thr) ? p.drop_scale : 1.0f;
-    if (!(l > 0 && p.drop_thr)) keep_bits = ~0ull;
+    const float dscale = (DROP && l > 0) ? p.drop_scale : 1.0f;
+    if (!(DROP && l > 0)) keep_bits = ~0ull;
     const int HP = p.HP, h = p.h, L = p.L;
     const float inv_h = 1.0f / float(h);
     const float mean = S.stats[l][0][c.row], rstd = S.stats[l][1][c.row], shift = -mean * rstd;
@@ -378,7 +379,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
         for (int j = 0; j < 8; ++j) {
             const float xh = fmaf(z[j], rstd, shift);
             const float y = fmaf(xh, gam[8 * g + j], bet[8 * g + j]);
-            const float gj = (y > 0.f && ((keep_bits >> (8 * g + j)) & 1ull)) ? dh[j] * dscale : 0.f;
+            const float gj = DROP ? ((y > 0.f && ((keep_bits >> (8 * g + j)) & 1ull)) ? dh[j] * dscale : 0.f) : (y > 0.f ? dh[j] : 0.f);
             const float t = gj * gam[8 * g + j];
             s1 += t;
             s2 = fmaf(t, xh, s2);
@@ -403,7 +404,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaf(xh[j], gam[8 * g + j], bet[8 * g + j]);
-            const float t = ((y > 0.f && ((keep_bits >> (8 * g + j)) & 1ull)) ? dh[j] * dscale : 0.f) * gam[8 * g + j];
+            const float t = (DROP ? ((y > 0.f && ((keep_bits >> (8 * g + j)) & 1ull)) ? dh[j] * dscale : 0.f) : (y > 0.f ? dh[j] : 0.f)) * gam[8 * g + j];
             dz[j] = (col + j < h) ? rstd * (t - m1 - xh[j] * m2) : 0.f;
         }
         uint4 hi4, lo4;
@@ -413,6 +414,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem& S, const Params& p, const Row
     }
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u));
@@ -586,14 +588,14 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
 #pragma unroll
             for (int l = 0; l <= MAXL; ++l) keep_bits[l] = 0ull;
             run_stage(1, ST_STEM, nullptr);
-            fwd_epilogue<true>(S, p, c, 0, o, keep_bits[0]);
+            fwd_epilogue<true, DROP>(S, p, c, 0, o, keep_bits[0]);
 #pragma unroll
             for (int l = 1; l <= MAXL; ++l) {
                 if (l > L) break;
                 run_stage(KB, ST_FWD1, image(p.h_out, l - 1));     // the operand tile is h_{l-1}
                 write_residual_terms();
                 run_stage(KB, ST_FWD2, nullptr);
-                fwd_epilogue<false>(S, p, c, l, o, keep_bits[l]);
+                fwd_epilogue<false, DROP>(S, p, c, l, o, keep_bits[l]);
             }
             if (issuer && p.backward) copy_out_tile(S, image(p.h_out, L), HP);   // h_L: ordered by the barriers of the last epilogue
             // ---- heads -> loss terms and their gradients (one thread per row)
@@ -629,12 +631,12 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_kernel(const Params p) 
             if (!p.backward) continue;
             row_sync();
             // ---- backward-data
-            bwd_epilogue(S, p, c, L, true, L == 2 ? keep_bits[2] : keep_bits[1]);
+            bwd_epilogue<DROP>(S, p, c, L, true, L == 2 ? keep_bits[2] : keep_bits[1]);
 #pragma unroll
             for (int l = MAXL; l >= 1; --l) {
                 if (l > L) continue;
                 run_stage(KB, ST_BWD, image(p.dz_out, l));          // D = dz_l W_l; the operand tile is dz_l
-                bwd_epilogue(S, p, c, l - 1, false, keep_bits[l - 1]);
+                bwd_epilogue<DROP>(S, p, c, l - 1, false, keep_bits[l - 1]);
             }
             // dz_0 has no MMA after it: copy it out between two barriers before the next tile's input overwrites block 0
             tc::fence_async_smem();
@@ -853,8 +855,13 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* u, void* stream) {
     p.loss_part = reinterpret_cast<double*>(ws + z_bytes + ln_bytes + size_t(num_sms()) * 8 * 4);
     if (bw) G2048_CHECK_CUDA(cudaMemsetAsync(p.ln_part, 0, ln_bytes, st));
     const int smem = int(sizeof(Smem)) + 1024;
-    G2048_CHECK_CUDA(ensure_smem(update_mlp_kernel, smem));
-    update_mlp_kernel<<<grid, THREADS, smem, st>>>(p);
+    if (p.drop_thr) {
+        G2048_CHECK_CUDA(ensure_smem(update_mlp_kernel<true>, smem));
+        update_mlp_kernel<true><<<grid, THREADS, smem, st>>>(p);
+    } else {
+        G2048_CHECK_CUDA(ensure_smem(update_mlp_kernel<false>, smem));
+        update_mlp_kernel<false><<<grid, THREADS, smem, st>>>(p);
+    }
     G2048_CHECK_LAUNCH("update_mlp_kernel");
     if (bw) {
         const int work = (L + 1) * 2 * h + 9;

@@ -41,6 +41,9 @@ def episodes_to_batch(episodes, device) -> dict:
         raise ValueError("model_optimize_step: no moves in the episodes")
     x = torch.stack([m["game_state"].detach().to("cpu", torch.float32) for m in moves]).numpy()
     exps = np.rint(x[:, 0::3]).astype(np.uint64)                        # to_model_format: [exp, r/3, c/3] per cell
+    if exps.size and int(exps.max()) > 15:
+        raise ValueError("model_optimize_step: a board holds exponent 16 (a 65536 tile); the packed 4-bit board format of the "
+                         "kernels stops at 15 (32768) -- game.py's own ceiling is 16 (game.py:59-60)")
     boards = np.zeros(n, dtype=np.uint64)
     for i in range(16):
         boards |= exps[:, i] << np.uint64(4 * i)

@@ -17,6 +17,8 @@ from .env import _ptr, _req, _stream, init
 
 _lib.register("g2048_rtg_advantage",
               [C.c_void_p] * 4 + [C.c_int32, C.c_int64] + [C.c_double] * 6 + [C.c_void_p] * 6 + [C.c_void_p])
+_lib.register("g2048_rtg_advantage_bootstrap",
+              [C.c_void_p] * 5 + [C.c_int32, C.c_int64] + [C.c_double] * 6 + [C.c_void_p] * 6 + [C.c_void_p])
 _lib.register("g2048_ppo_loss",
               [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 5 + [C.c_int64] + [C.c_float] * 4 + [C.c_void_p] * 5)
 _lib.lib().g2048_reduce_workspace_bytes.restype = C.c_int64
@@ -56,9 +58,11 @@ class RtgMoments:
 
 
 def rtg_advantage(points, shaping, flags, value, *, gamma, w_points, w_mono, w_empt, mu_c, stddev,
-                  want_raw: bool = False) -> dict:
+                  want_raw: bool = False, bootstrap: torch.Tensor | None = None) -> dict:
     """Time-major [T,B] rollout buffers -> g_norm, adv (float32 [T,B]) and stats (float64[3] on
-    the device: sum G, sum G^2, count).  want_raw also returns reward and the raw return."""
+    the device: sum G, sum G^2, count).  want_raw also returns reward and the raw return.
+    bootstrap: optional float32 [B], the raw return-to-go expected after the last slot of every column (games that
+    continue past a fixed-horizon buffer); None = 0, the reference's truncation (train.py:724-728)."""
     points = _req(points, torch.int32, "points")
     shaping = _req(shaping, torch.int64, "shaping")
     flags = _req(flags, torch.uint8, "flags")
@@ -71,7 +75,10 @@ def rtg_advantage(points, shaping, flags, value, *, gamma, w_points, w_mono, w_e
         reward = torch.empty_like(g_norm) if want_raw else None
         g_raw = torch.empty_like(g_norm) if want_raw else None
         stats = torch.empty(3, dtype=torch.float64, device=dev)
-        _lib.call("g2048_rtg_advantage", _ptr(points), _ptr(shaping), _ptr(flags), _ptr(value), T, B,
+        if bootstrap is not None:
+            bootstrap = _req(bootstrap.reshape(-1), torch.float32, "bootstrap")
+            assert bootstrap.numel() == B
+        _lib.call("g2048_rtg_advantage_bootstrap", _ptr(points), _ptr(shaping), _ptr(flags), _ptr(value), _ptr(bootstrap), T, B,
                   float(gamma), float(w_points), float(w_mono), float(w_empt), float(mu_c), float(stddev),
                   _ptr(reward), _ptr(g_raw), _ptr(g_norm), _ptr(adv), _ptr(stats), _ptr(_workspace(dev)), _stream())
     return dict(g_norm=g_norm, adv=adv, reward=reward, g_raw=g_raw, stats=stats)

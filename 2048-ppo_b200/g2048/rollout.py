@@ -180,6 +180,13 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
     return buf
 
 
+def _check_overflow(flags: torch.Tensor) -> None:
+    """A merge of two 32768 tiles would need exponent 16, which the packed 4-bit cells cannot hold (the kernels saturate
+    the cell and raise G2048_FLAG_OVERFLOW; everything else of that transition is unspecified): never silent."""
+    if bool(((flags & env.FLAG_OVERFLOW) != 0).any()):
+        raise OverflowError("a rollout merged two 32768 tiles: the packed board format stops at exponent 15 (game.py allows 16)")
+
+
 # ----------------------------------------------------------------------------- drop-in
 
 _GAMES_PLAYED = itertools.count()
@@ -191,6 +198,7 @@ def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, devic
     cat = lambda name: torch.cat([getattr(b, name) for b in bufs], dim=0)
     boards, flags = cat("boards"), cat("flags")
     T, B = flags.shape
+    _check_overflow(flags)
     game_state = env.encode(boards.reshape(-1)).reshape(T, B, 48)
     ex = env.expand4(boards.reshape(-1))
     pts_possible = ex["points"].reshape(T, B, 4).cpu().numpy()
@@ -249,7 +257,8 @@ def play_games_batched(model, num_games: int, max_steps: int | None = None, devi
         raise RuntimeError("play_games_batched runs on a CUDA device only (no CPU fallback); pass --gpu / device='cuda'")
     dev = env.init(device)
     policy = pack_policy(model, dev)
-    seed = int(os.environ.get("G2048_SEED", "2048")) if seed is None else seed
+    if seed is None:      # like the reference's unseeded `random`: a fresh stream per process unless the caller seeds torch
+        seed = int(os.environ["G2048_SEED"]) if "G2048_SEED" in os.environ else torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
     env0 = next(_GAMES_PLAYED) * (1 << 32)
     boards = env.reset(num_games, device=dev, seed=seed, env0=env0, ctr=0)
     alive = torch.ones(num_games, dtype=torch.uint8, device=dev)
@@ -286,6 +295,7 @@ def evaluate(model, eval_games: int = 100, max_steps: int | None = None, device=
         if T <= 0:
             break
         buf = rollout(policy, boards, T, seed=seed, env0=0, ctr0=1 + played, auto_reset=False, alive=alive)
+        _check_overflow(buf.flags)
         scores += (buf.points.long() * ((buf.flags & 0x80) != 0)).sum(0)
         played += T
         if not bool(alive.any()):

@@ -46,7 +46,11 @@ class TrainConfig:
     chunk: int = 1 << 22           # samples per forward/backward chunk (measured: 4M is 7.6 % faster than 1M; ~26 GB live)
     seed: int = 2048
     zero_heads: bool = True        # train.py:1559-1567
-    dropout: float = 0.0           # the update forward is deterministic here (parity with dropout off)
+    dropout: float = 0.0           # Dropout of the residual blocks in the update forward (the reference's MLPConfig default is 0.1)
+    bootstrap: bool = True         # the envs persist across train steps (auto-reset), so a buffer usually ends in the middle of
+                                   # a game: start the return-to-go scan of such a column from the critic's value of the
+                                   # carried-over board, V * sd + mu_c, instead of 0 (which biases the last ~1/(1-gamma) targets
+                                   # low).  False = the reference's truncation, as for an episode cut by max_steps.
     upsample_ratio: float = 0.0    # symmetry augmentation (train.py:774-881; the README recipe uses 0.25): that share of the
                                    # recorded steps is drawn and mirrored / rotated copies join the update batch
     rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
@@ -159,9 +163,18 @@ class Trainer:
     def advantages(self, buf) -> dict:
         c = self.cfg
         mu_c, sd = self.moments.corrected(c.rtg_beta)
+        boot = None
+        if c.bootstrap:
+            with torch.no_grad():
+                self.model.eval()
+                if self.is_mlp and update.supported(self.model):
+                    _, v = update.forward(self.model, self.boards)
+                else:
+                    _, v = self.model(env.encode(self.boards))
+                boot = v.reshape(-1).float() * (sd + 1e-8) + mu_c        # the critic predicts the NORMALISED return (train.py:760-772)
         return ppo.rtg_advantage(buf.points, buf.shaping, buf.flags, buf.value, gamma=c.gamma,
                                  w_points=c.points_weight, w_mono=c.mono_weight, w_empt=c.emptiness_weight,
-                                 mu_c=mu_c, stddev=sd)
+                                 mu_c=mu_c, stddev=sd, bootstrap=boot)
 
     def update(self, buf, adv) -> dict:
         c = self.cfg

@@ -138,6 +138,16 @@ int g2048_rtg_advantage(const int32_t* points, const uint64_t* shaping, const ui
                         double mu_corrected, double stddev, float* reward_out, float* g_raw_out, float* g_norm_out,
                         float* adv_out, double* stats_out, void* workspace, void* stream);
 
+/* The same scan for rollouts of a FIXED horizon over games that continue past the buffer (persistent auto-reset envs):
+ * bootstrap[b] (may be NULL = 0) is the raw, un-normalised return-to-go expected after the last slot of column b -- e.g. the
+ * critic's value of the carried-over board, V * (stddev + 1e-8) + mu_corrected.  It only reaches the slots after the last
+ * DONE move of the column; a column whose last slot is DONE or invalid ignores it.  The reference itself truncates with 0
+ * (train.py:724-728: an episode cut by max_steps is simply shorter), which is what g2048_rtg_advantage does. */
+int g2048_rtg_advantage_bootstrap(const int32_t* points, const uint64_t* shaping, const uint8_t* flags, const float* value,
+                                  const float* bootstrap, int32_t T, int64_t B, double gamma, double w_points, double w_mono,
+                                  double w_empt, double mu_corrected, double stddev, float* reward_out, float* g_raw_out,
+                                  float* g_norm_out, float* adv_out, double* stats_out, void* workspace, void* stream);
+
 /* train.py:497-554: masked log-softmax, PPO-clip surrogate (eps = clip_eps), entropy of the
  * clamped masked logits, smooth-L1 critic loss; loss = -(1/N) sum(ppo - c_v*vl + beta_ent*H).
  * Forward and analytic backward in one pass: dlogits f32[n,4] and dvalue f32[n] hold
@@ -331,6 +341,10 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* params, void* stream);
  * A[128,K] * W[N,K]^T with bf16-rounded operands and fp32 accumulation in tensor memory.
  * K, N multiples of 16, <= 256.  Pins the UMMA descriptor / swizzle conventions on hardware. */
 int g2048_tc_gemm_selftest(const float* A, const float* W, float* C, int32_t K, int32_t N, void* stream);
+/* the same with the operand formats chosen per operand (1 = fp16, 0 = bf16): pins that kind::f16 takes A and B formats
+ * independently (the fused update multiplies bf16 gradient images with fp16 activation images) */
+int g2048_tc_gemm_selftest_fmt(const float* A, const float* W, float* C, int32_t K, int32_t N, int32_t a_f16, int32_t w_f16,
+                               void* stream);
 
 #ifdef __cplusplus
 }

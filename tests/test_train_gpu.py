@@ -71,6 +71,46 @@ def test_rtg_advantage_matches_oracle_random(T, B):
     np.testing.assert_allclose([mom.mu, mom.m2], [want["rtg_mu"], want["rtg_m2"]], rtol=1e-9)
 
 
+def test_rtg_bootstrap_continues_games_past_the_buffer():
+    """bootstrap[b] seeds the scan of column b (a game that continues past the buffer); a DONE move or an invalid slot at the
+    end of the column cuts it off, and NULL is the reference's truncation with 0."""
+    from g2048 import ppo
+    rng = np.random.default_rng(5)
+    T, B, gamma = 37, 301, 0.97
+    points = (rng.integers(0, 64, (T, B)) * 4).astype(np.int32)
+    mono_b, mono_a = rng.integers(0, 49, (T, B)), rng.integers(0, 49, (T, B))
+    empt_b, empt_a = rng.integers(0, 17, (T, B)), rng.integers(0, 17, (T, B))
+    done = (rng.random((T, B)) < 0.03).astype(np.uint8)
+    valid = np.ones((T, B), dtype=np.uint8)
+    valid[-3:, ::7] = 0                                   # some columns end with invalid slots
+    done[-1, 1::7] = 1                                    # some end exactly on a DONE move
+    flags = (valid << 7) | (done << 4)
+    boot = rng.normal(size=B).astype(np.float32) * 50
+    value = rng.normal(size=(T, B)).astype(np.float32)
+    kw = dict(gamma=gamma, w_points=0.1, w_mono=1.0, w_empt=0.5, mu_c=3.0, stddev=20.0, want_raw=True)
+    args = (cu(points), cu(shaping_words(mono_b, mono_a, empt_b, empt_a)), cu(flags.astype(np.uint8)), cu(value))
+    got = ppo.rtg_advantage(*args, bootstrap=cu(boot), **kw)
+    base = ppo.rtg_advantage(*args, **kw)
+    # float64 restatement of the scan with a seeded return
+    G = np.zeros((T, B))
+    g = boot.astype(np.float64).copy()
+    for t in range(T - 1, -1, -1):
+        d, v = done[t].astype(bool), valid[t].astype(bool)
+        g = np.where(d | ~v, 0.0, g)
+        r = points[t] * 0.1 + (gamma * np.where(d, 0, mono_a[t]) - mono_b[t]) + 0.5 * (gamma * np.where(d, 0, empt_a[t]) - empt_b[t])
+        g = np.where(v, r + gamma * g, 0.0)
+        G[t] = g
+    np.testing.assert_allclose(got["g_raw"].cpu().numpy(), G, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(got["g_norm"].cpu().numpy(), np.where(valid, (G - 3.0) / (20.0 + 1e-8), 0.0), rtol=1e-5, atol=1e-5)
+    # the bootstrap only reaches the slots after the last DONE / invalid slot of its column
+    diff = (got["g_raw"] - base["g_raw"]).cpu().numpy()
+    cut = np.zeros(B, dtype=bool)
+    for t in range(T - 1, -1, -1):
+        cut |= done[t].astype(bool) | ~valid[t].astype(bool)
+        want = np.where(cut, 0.0, boot * gamma ** (T - t))
+        np.testing.assert_allclose(diff[t], want, rtol=1e-4, atol=1e-3)
+
+
 def test_rtg_linearity_property_full_size():
     """C3-sized scan (512 x 65536): returns are linear in the reward weights."""
     from g2048 import ppo
