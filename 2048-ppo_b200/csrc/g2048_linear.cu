@@ -22,6 +22,7 @@
 // MN-major descriptors (rows = samples = the MMA's K index), accumulates a CTA's whole sample range in
 // tensor memory (flushed to an fp32 partial every 8192 samples to bound the accumulation error) and a
 // second kernel adds the per-CTA partials in a fixed order (deterministic).
+#include <cuda_fp16.h>
 #include "g2048_host.h"
 #include "g2048_tc.cuh"
 
@@ -42,6 +43,15 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
     const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
     hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+// the same with fp16 terms (22 mantissa bits; for operands of O(1) magnitude: the fused update's activations and its
+// loss-scaled gradients)
+__device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo) {
+    uint32_t h0, l0, h1, l1;
+    tc::split2_f16(v.x, v.y, h0, l0);
+    tc::split2_f16(v.z, v.w, h1, l1);
+    hi = make_uint2(h0, h1);
+    lo = make_uint2(l0, l1);
 }
 // byte offset of float4 `f` (0..3) of row `row` inside a 32-byte-swizzled block
 __device__ __forceinline__ uint32_t f4_offset(int row, int f) {
@@ -235,7 +245,7 @@ struct WgradBars {
 template <bool DY_IMG, bool X_IMG, bool X_BOARDS = false>
 __global__ void __launch_bounds__(W_THREADS, 1)
 x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float* __restrict__ partial, int64_t M, int N,
-                int K, int dy_hp, int x_hp) {
+                int K, int dy_hp, int x_hp, int f16) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sW = align1024(smem_raw);
     WgradBars& S = *reinterpret_cast<WgradBars*>(sW + W_STAGES * W_STAGE);
@@ -328,7 +338,8 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
                 if ((mat ? X_IMG : DY_IMG) || b >= (mat ? KPB : NPB)) continue;
                 const int row = rg * 8 + (lane >> 2), f = lane & 3;
                 uint2 hi, lo;
-                split4(v[i], hi, lo);
+                if (f16) split4_f16(v[i], hi, lo);
+                else split4(v[i], hi, lo);
                 const uint32_t off = uint32_t(mat) * 2u * W_PART + uint32_t(b) * W_BLOCK + f4_offset(row, f);
                 *reinterpret_cast<uint2*>(dst + off) = hi;
                 *reinterpret_cast<uint2*>(dst + W_PART + off) = lo;
@@ -370,7 +381,8 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
         }
     } else if (lane == 0) {
         // ---------------- MMA issuer
-        const uint32_t idesc = tc::make_idesc_bf16_major(128, KPB * 16, true, true);
+        // both operands bf16, or both fp16 (f16: the images of the pipelined fused update; kind::f16 does not mix formats)
+        const uint32_t idesc = f16 ? (tc::make_idesc_f16(128, KPB * 16) | (1u << 15) | (1u << 16)) : tc::make_idesc_bf16_major(128, KPB * 16, true, true);
         // one descriptor for the ring base; every operand of every MMA is that plus a byte offset (>> 4) in the
         // address field: the issuing thread's descriptor arithmetic is one 64-bit add per operand
         const uint64_t d0 = tc::make_desc_sw32(tc::smem_addr(sW), W_BLOCK, 256);
@@ -472,6 +484,11 @@ int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, 
 
 int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                          int32_t dy_hp, int32_t x_hp, void* stream) {
+    return g2048_x3_wgrad_images(dY, X, dW, workspace, M, N, K, dy_hp, x_hp, 0, stream);
+}
+
+int g2048_x3_wgrad_images(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
+                          int32_t dy_hp, int32_t x_hp, int32_t fp16, void* stream) {
     G2048_REQUIRE(M >= 0, "g2048_x3_wgrad: M < 0");
     G2048_REQUIRE(x_hp >= 0 || K == 48, "g2048_x3_wgrad: x_hp < 0 (X = packed boards) needs K == 48");
     G2048_REQUIRE((dy_hp == 0 || (dy_hp % 16 == 0 && dy_hp >= N && dy_hp <= MAXF)) && (x_hp <= 0 || (x_hp % 16 == 0 && x_hp >= K && x_hp <= MAXF)),
@@ -493,7 +510,7 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
                 : dy_hp  ? (x_hp ? x3_wgrad_kernel<true, true> : x3_wgrad_kernel<true, false>)
                          : (x_hp ? x3_wgrad_kernel<false, true> : x3_wgrad_kernel<false, false>);
     G2048_CHECK_CUDA(ensure_smem(kern, smem));
-    kern<<<grid, W_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp);
+    kern<<<grid, W_THREADS, smem, st>>>(dY, X, static_cast<float*>(workspace), M, N, K, dy_hp, x_hp, fp16 ? 1 : 0);
     G2048_CHECK_LAUNCH("x3_wgrad_kernel");
     x3_wgrad_reduce_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), dW, N, K, grid);
     G2048_CHECK_LAUNCH("x3_wgrad_reduce_kernel");

@@ -24,6 +24,8 @@ _lib.register("g2048_x3_gemm", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C
 _lib.register("g2048_x3_wgrad", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p])
 _lib.register("g2048_x3_wgrad_tiled", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p])
+_lib.register("g2048_x3_wgrad_images", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_void_p])
 _lib.lib().g2048_x3_image_bytes.restype = C.c_int64
 _lib.lib().g2048_x3_image_bytes.argtypes = [C.c_int32, C.c_int32]
 _lib.lib().g2048_x3_wgrad_workspace_bytes.restype = C.c_int64
@@ -82,8 +84,9 @@ def wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def wgrad_tiled(dy: torch.Tensor, x: torch.Tensor, m: int, n: int, k: int, dy_hp: int = 0, x_hp: int = 0) -> torch.Tensor:
-    """dy^T x over m samples where either operand may be a bf16 hi|lo operand image written by the fused update kernel
+def wgrad_tiled(dy: torch.Tensor, x: torch.Tensor, m: int, n: int, k: int, dy_hp: int = 0, x_hp: int = 0, fp16: bool = False) -> torch.Tensor:
+    """dy^T x over m samples where either operand may be a hi|lo operand image written by the fused update kernel (fp16 = True:
+    the terms are fp16 -- the fused update's images and loss-scaled gradients -- else bf16)
     (`*_hp` = its padded column count; the kernel bulk-copies it straight into its operand ring), 0 = row-major fp32
     [m, features] (loaded, split and stored by the loader warps); x_hp = -1: `x` is int64 packed boards [m] and k == 48 --
     the model input [exponent, row/3, col/3] per cell is formed in the loader (no g2048_encode pass)."""
@@ -92,7 +95,7 @@ def wgrad_tiled(dy: torch.Tensor, x: torch.Tensor, m: int, n: int, k: int, dy_hp
         if dev.index not in _WS:
             _WS[dev.index] = torch.empty(int(_lib.lib().g2048_x3_wgrad_workspace_bytes()), dtype=torch.uint8, device=dev)
         out = torch.empty((n, k), dtype=torch.float32, device=dev)
-        _lib.call("g2048_x3_wgrad_tiled", _ptr(dy), _ptr(x), _ptr(out), _ptr(_WS[dev.index]), m, n, k, dy_hp, x_hp, _stream())
+        _lib.call("g2048_x3_wgrad_images", _ptr(dy), _ptr(x), _ptr(out), _ptr(_WS[dev.index]), m, n, k, dy_hp, x_hp, int(fp16), _stream())
     return out
 
 

@@ -4,7 +4,7 @@
 `clip_grad_norm_` (train.py:491-556) for a GameMLP (the blocks' Dropout active in train() mode, as in the reference,
 with Philox masks -- see dropout_mask): it ADDS d loss / d parameter into every `p.grad` and returns the loss sums.  One fused tcgen05 kernel (g2048_update_mlp_fwd_bwd) runs the forward,
 the PPO-clip / critic / entropy terms and the backward-data chain per 128-sample tile; the weight gradients
-are split-bf16 tcgen05 reductions over samples (g2048_x3_wgrad).  There is no fallback: unsupported model
+are split-fp16 tcgen05 reductions over samples (g2048_x3_wgrad_images).  There is no fallback: unsupported model
 shapes raise (use g2048.fused.mlp_forward + g2048.ppo.ppo_loss with autograd for those).
 """
 from __future__ import annotations
@@ -34,6 +34,20 @@ _lib.register("g2048_update_mlp_fwd_bwd", [C.POINTER(_UpdateMlp), vp])
 for _name in ("g2048_update_mlp_pack_bytes", "g2048_update_mlp_workspace_bytes"):
     getattr(_lib.lib(), _name).restype = i64
     getattr(_lib.lib(), _name).argtypes = [i32, i32]
+_lib.lib().g2048_update_mlp_padded.restype = i32
+_lib.lib().g2048_update_mlp_padded.argtypes = [i32]
+
+
+def padded_width(h: int) -> int:
+    """Column count of the kernel's operand tiles / images for hidden size h (64, 128, 192 or 208)."""
+    return int(_lib.lib().g2048_update_mlp_padded(h))
+
+
+def loss_scale(n_total: int) -> float:
+    """Power-of-two factor the gradient chain is multiplied with inside the kernels, so that its fp16 operand terms sit at
+    O(1) like the activations: the per-sample gradients carry 1 / n_total (train.py:554 is a mean), which for 3e7 samples
+    is below the fp16 range.  Everything the kernels emit is divided by it again (exactly) when it is added to p.grad."""
+    return float(2 ** max(0, int(n_total).bit_length() - 1))
 
 _WS: dict[tuple[int, int, int], torch.Tensor] = {}
 
@@ -130,12 +144,12 @@ def forward(model, boards: torch.Tensor, packed: torch.Tensor | None = None, *, 
     return logits, value
 
 
-def _acc(p: torch.nn.Parameter, g: torch.Tensor) -> None:
+def _acc(p: torch.nn.Parameter, g: torch.Tensor, alpha: float = 1.0) -> None:
     g = g.reshape(p.shape)
     if p.grad is None:
-        p.grad = g.clone()
+        p.grad = g * alpha
     else:
-        p.grad.add_(g)
+        p.grad.add_(g, alpha=alpha)
 
 
 def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flags=None, clip_eps=0.2,
@@ -163,9 +177,12 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
     old_logp = _req(old_logp, torch.float32, "old_logp")
     stride = 4 if old_logp.numel() == 4 * n else 1
     assert old_logp.numel() == stride * n
+    n_div = int(n_total if n_total else max(n, 1))
+    scale = loss_scale(n_div)
     with torch.cuda.device(dev):
-        hp, per_layer = (h + 15) // 16 * 16, (n + 127) // 128 * 128 * ((h + 15) // 16 * 16)
-        h_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)    # bf16 hi|lo operand images (4 B / value), see untile()
+        hp = padded_width(h)
+        per_layer = (n + 127) // 128 * 128 * hp
+        h_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)    # fp16 hi|lo operand images (4 B / value), see untile()
         dz_out = torch.empty((L + 1, per_layer), dtype=torch.float32, device=dev)
         dhead = torch.empty((n, 8), dtype=torch.float32, device=dev)
         ln_grad = torch.empty((L + 1, 2, h), dtype=torch.float32, device=dev)
@@ -178,7 +195,7 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
                        old_logp=old_logp.data_ptr(), old_logp_stride=stride,
                        adv=_req(adv, torch.float32, "adv").data_ptr(), g_norm=_req(g_norm, torch.float32, "g_norm").data_ptr(),
                        clip_eps=clip_eps, critic_strength=critic_strength, entropy_strength=entropy_strength,
-                       inv_n=1.0 / float(n_total if n_total else max(n, 1)),
+                       inv_n=scale / float(n_div),
                        packed=packed.data_ptr(), workspace=_workspace(dev, h, L).data_ptr(),
                        h_out=h_out.data_ptr(), dz_out=dz_out.data_ptr(), dhead=dhead.data_ptr(),
                        ln_grad=ln_grad.data_ptr(), head_bias_grad=hb_grad.data_ptr(), stats=stats.data_ptr(),
@@ -188,32 +205,36 @@ def loss_and_grads(model, boards, actions, legal, old_logp, adv, g_norm, *, flag
             u.logits = _req(logits_out, torch.float32, "logits_out").data_ptr()
         _lib.call("g2048_update_mlp_fwd_bwd", C.byref(u), _stream())
         if n > 0:
-            # weight gradients: reductions over samples on the tensor cores
-            _acc(model.stem[0].weight, linear.wgrad_tiled(dz_out[0], boards, n, h, 48, dy_hp=hp, x_hp=-1))   # X = the packed boards
+            # weight gradients: reductions over samples on the tensor cores (fp16 terms; every operand carries `scale`)
+            inv = 1.0 / scale
+            wg = lambda dy, x, nn, kk, **kw: linear.wgrad_tiled(dy, x, n, nn, kk, fp16=True, **kw)
+            _acc(model.stem[0].weight, wg(dz_out[0], boards, h, 48, dy_hp=hp, x_hp=-1), inv)   # X = the packed boards
             for l, blk in enumerate(model.backbone):
-                _acc(blk.mlp[0].weight, linear.wgrad_tiled(dz_out[l + 1], h_out[l], n, h, h, dy_hp=hp, x_hp=hp))
-            dwh = linear.wgrad_tiled(dhead, h_out[L], n, 8, h, x_hp=hp)
-            _acc(model.action_head.weight, dwh[:4])
-            _acc(model.value_head.weight, dwh[4:5])
+                _acc(blk.mlp[0].weight, wg(dz_out[l + 1], h_out[l], h, h, dy_hp=hp, x_hp=hp), inv)
+            dwh = wg(dhead, h_out[L], 8, h, x_hp=hp)
+            _acc(model.action_head.weight, dwh[:4], inv)
+            _acc(model.value_head.weight, dwh[4:5], inv)
             lns = [model.stem[1]] + [blk.mlp[1] for blk in model.backbone]
             for l, ln in enumerate(lns):
-                _acc(ln.weight, ln_grad[l, 0])
-                _acc(ln.bias, ln_grad[l, 1])
-            _acc(model.action_head.bias, hb_grad[:4])
-            _acc(model.value_head.bias, hb_grad[4:5])
+                _acc(ln.weight, ln_grad[l, 0], inv)
+                _acc(ln.bias, ln_grad[l, 1], inv)
+            _acc(model.action_head.bias, hb_grad[:4], inv)
+            _acc(model.value_head.bias, hb_grad[4:5], inv)
     if keep is not None:
-        keep.update(h_out=torch.stack([untile(t, n, h) for t in h_out]), dz_out=torch.stack([untile(t, n, h) for t in dz_out]),
-                    dhead=dhead, ln_grad=ln_grad, head_bias_grad=hb_grad)
+        inv = 1.0 / scale
+        keep.update(h_out=torch.stack([untile(t, n, h) for t in h_out]), dz_out=torch.stack([untile(t, n, h) for t in dz_out]) * inv,
+                    dhead=dhead * inv, ln_grad=ln_grad * inv, head_bias_grad=hb_grad * inv, loss_scale=scale)
     return stats
 
 
-def untile(t: torch.Tensor, n: int, h: int) -> torch.Tensor:
-    """[n, h] fp32 copy of a tensor the fused kernel wrote as a bf16 hi|lo operand image: per tile of 128 samples
+def untile(t: torch.Tensor, n: int, h: int, hp: int | None = None, dtype=torch.float16) -> torch.Tensor:
+    """[n, h] fp32 copy of a tensor the fused kernel wrote as an fp16 hi|lo operand image: per tile of 128 samples
     [hi | lo][16-feature block][sample 0..127][32 B with the 16-byte halves swapped on (sample >> 2) & 1]
-    (csrc/g2048_update_fused.cu copy_out_tile).  Returns hi + lo (16 mantissa bits of the value)."""
-    hp = (h + 15) // 16 * 16
+    (csrc/g2048_update_x3.cu storer).  Returns hi + lo (22 mantissa bits of the value).  hp: padded column count of the
+    image (default: the update kernel's); dtype: the term format (the weight-gradient kernel also takes bf16 images)."""
+    hp = padded_width(h) if hp is None else hp
     tiles = (n + 127) // 128
-    x = t.contiguous().view(torch.uint8)[: tiles * 128 * hp * 4].view(torch.bfloat16).view(tiles, 2, hp // 16, 128, 2, 8)
+    x = t.contiguous().view(torch.uint8)[: tiles * 128 * hp * 4].view(dtype).view(tiles, 2, hp // 16, 128, 2, 8)
     swap = ((torch.arange(128, device=t.device) >> 2) & 1).view(1, 1, 1, 128, 1, 1).bool()
     x = torch.where(swap, x.flip(-2), x)
     v = x[:, 0].float() + x[:, 1].float()                            # [tiles, blocks, 128, 2, 8]

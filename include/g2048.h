@@ -274,6 +274,12 @@ int g2048_x3_wgrad(const float* dY, const float* X, float* dW, void* workspace, 
 int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                          int32_t dy_hp, int32_t x_hp, void* stream);
 
+/* The same with the term format chosen: fp16 != 0 -- both operands are split (or arrive as images) in fp16 terms, x = hi + lo
+ * with 22 mantissa bits, for operands of O(1) magnitude such as the fused update's activations and its loss-scaled
+ * gradients; 0 = bf16 terms (16 bits, the range of fp32).  kind::f16 does not mix the two formats in one product. */
+int g2048_x3_wgrad_images(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
+                          int32_t dy_hp, int32_t x_hp, int32_t fp16, void* stream);
+
 /* ---- policy update: fused forward + loss + backward-data of GameMLP (csrc/g2048_update_fused.cu) ----
  * One persistent tcgen05 kernel runs, per 128-sample tile and without leaving the SM, what
  * model_optimize_step does between `model(x)` and the weight gradients (train.py:491-556): the GameMLP
@@ -291,6 +297,7 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
  * sum smooth_l1, sum entropy, count} as g2048_ppo_loss.  All per-SM partial sums are combined in a fixed
  * order (deterministic).  hidden: multiple of 4 in [16, 208]; layers 1..2; dropout: see dropout_p.
  * backward = 0: forward only (writes logits [n,4] and/or value [n]; used by the parity tests). */
+int32_t g2048_update_mlp_padded(int32_t hidden);   /* HP: column count of the operand tiles / images (64, 128, 192 or 208) */
 int64_t g2048_update_mlp_pack_bytes(int32_t hidden, int32_t layers);
 int g2048_update_mlp_pack(int32_t hidden, int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
                           const float* const* block_w, const float* const* block_ln_w, const float* const* block_ln_b,

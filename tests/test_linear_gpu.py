@@ -89,15 +89,15 @@ def test_linear_rejects_unsupported_inputs():
         linear.gemm(torch.zeros(4, 16), torch.zeros(16, dtype=torch.uint8), 16)
 
 
-def operand_image(x: torch.Tensor, hp: int) -> torch.Tensor:
-    """[m, f] fp32 -> the bf16 hi|lo operand image the fused update kernel writes (copy_out_tile) and x3_wgrad_kernel
+def operand_image(x: torch.Tensor, hp: int, dtype=torch.bfloat16) -> torch.Tensor:
+    """[m, f] fp32 -> the hi|lo operand image (bf16 or fp16 terms) the fused update kernel writes and x3_wgrad_kernel
     bulk-copies: per tile of 128 samples [hi | lo][16-feature block][sample][32 B, halves swapped on (sample >> 2) & 1]."""
     m, f = x.shape
     tiles = (m + 127) // 128
     xp = torch.zeros((tiles * 128, hp), dtype=torch.float32, device=x.device)
     xp[:m, :f] = x
-    hi = xp.bfloat16()
-    lo = (xp - hi.float()).bfloat16()
+    hi = xp.to(dtype)
+    lo = (xp - hi.float()).to(dtype)
     parts = torch.stack([hi, lo], 0).view(2, tiles, 128, hp // 16, 2, 8)          # [part, tile, row, block, half, 8]
     swap = ((torch.arange(128, device=x.device) >> 2) & 1).view(1, 1, 128, 1, 1, 1).bool()
     parts = torch.where(swap, parts.flip(-2), parts)
@@ -105,24 +105,27 @@ def operand_image(x: torch.Tensor, hp: int) -> torch.Tensor:
     return img.view(torch.uint8).view(-1).view(torch.float32)
 
 
+@pytest.mark.parametrize("fp16", [False, True])
 @pytest.mark.parametrize("m,n,k", [(1000, 196, 196), (70000, 196, 48), (333, 8, 196), (4096, 64, 64)])
 @pytest.mark.parametrize("dy_img,x_img", [(True, False), (False, True), (True, True)])
-def test_wgrad_with_operand_images(m, n, k, dy_img, x_img):
-    """dW = dY^T X with either operand as a bf16 hi|lo operand image (bulk-copied into the ring) instead of row-major
-    fp32: same x3 bound as the fp32 path, and the image decodes back (g2048.update.untile) to hi + lo."""
+def test_wgrad_with_operand_images(m, n, k, dy_img, x_img, fp16):
+    """dW = dY^T X with either operand as a hi|lo operand image (bulk-copied into the ring) instead of row-major fp32, in bf16
+    terms (the x3 bound of the fp32 path) or in fp16 terms (the fused update's images; 22 mantissa bits: a bound 30 times
+    tighter); the image decodes back (g2048.update.untile) to hi + lo."""
     from g2048 import linear, update
     g = torch.Generator(device="cuda").manual_seed(m + n + k)
     dy = torch.randn((m, n), generator=g, device="cuda") * 0.3
     x = torch.randn((m, k), generator=g, device="cuda")
     hp_n, hp_k = (n + 15) // 16 * 16, (k + 15) // 16 * 16
-    a = operand_image(dy, hp_n) if dy_img else dy
-    b = operand_image(x, hp_k) if x_img else x
+    dt = torch.float16 if fp16 else torch.bfloat16
+    a = operand_image(dy, hp_n, dt) if dy_img else dy
+    b = operand_image(x, hp_k, dt) if x_img else x
     if dy_img:
-        back = update.untile(a, m, n)
-        torch.testing.assert_close(back, dy, rtol=2e-5, atol=1e-6)
-    got = linear.wgrad_tiled(a, b, m, n, k, dy_hp=hp_n if dy_img else 0, x_hp=hp_k if x_img else 0)
+        back = update.untile(a, m, n, hp=hp_n, dtype=dt)
+        torch.testing.assert_close(back, dy, rtol=1e-6 if fp16 else 2e-5, atol=1e-6)
+    got = linear.wgrad_tiled(a, b, m, n, k, dy_hp=hp_n if dy_img else 0, x_hp=hp_k if x_img else 0, fp16=fp16)
     want = dy.double().T @ x.double()
-    bound = 2e-5 * (dy.double().abs().T @ x.double().abs()) + 1e-9
+    bound = (6e-7 if fp16 else 2e-5) * (dy.double().abs().T @ x.double().abs()) + 1e-9
     assert bool(((got.double() - want).abs() <= bound).all())
 
 

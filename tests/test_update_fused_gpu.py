@@ -1,9 +1,9 @@
-"""Fused update kernel (csrc/g2048_update_fused.cu: GameMLP forward + PPO loss + backward-data on tcgen05,
-weight gradients by g2048_x3_wgrad) against float64 torch autograd of the reference's formulas and against
+"""Fused update kernel (csrc/g2048_update_x3.cu: GameMLP forward + PPO loss + backward-data on tcgen05,
+weight gradients by g2048_x3_wgrad_images) against float64 torch autograd of the reference's formulas and against
 the reference's own recorded model_optimize_step gradients (tests/golden/loss.npz).
 
-Tolerance: the forward GEMMs are three-term split-bf16 ("x6", ~1e-6 of the output scale), the backward GEMMs
-two-term ("x3", ~1e-5, see test_linear_gpu.py); gradients are compared by relative Frobenius error per tensor."""
+Tolerance: every GEMM operand is two fp16 terms (22 mantissa bits, three products: ~2e-7 of the output scale, see
+test_linear_gpu.py), forward and backward; gradients are compared by relative Frobenius error per tensor."""
 import numpy as np
 import pytest
 import torch
@@ -274,8 +274,8 @@ def test_model_optimize_step_accepts_the_reference_default_model():
 
 @pytest.mark.parametrize("h,L,n", [(196, 2, 1000), (64, 1, 300)])
 def test_operand_images_hold_the_activations(h, L, n):
-    """The h_l tensors the fused kernel leaves in HBM are its MMA operand tiles (bf16 hi|lo images, bulk-copied out of
-    shared memory): decoded (update.untile -> hi + lo, 16 mantissa bits) they are the float64 model's activations, rows
+    """The h_l tensors the fused kernel leaves in HBM are its MMA operand tiles (fp16 hi|lo images, bulk-copied out of
+    shared memory): decoded (update.untile -> hi + lo, 22 mantissa bits) they are the float64 model's activations, rows
     past n are zero, and dz_l decodes to finite values that vanish past n."""
     from g2048 import env, update
     F = torch.nn.functional
