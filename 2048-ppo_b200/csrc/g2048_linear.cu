@@ -275,7 +275,7 @@ x3_wgrad_kernel(const float* __restrict__ dY, const float* __restrict__ X, float
 
     if (warp < W_EPI_WARP0) {
         // ---------------- loaders: group (warp / 8) takes the stages q = group, group + W_GROUPS, ...
-        // A matrix with hp > 0 is a bf16 hi|lo operand image written by update_mlp_kernel (store_image): its two
+        // A matrix with hp > 0 is a hi|lo operand image written by update_mlp_x3_kernel (its storer warp): its two
         // parts of a stage are bulk-copied straight into the ring (no registers, no conversion); hp == 0 is
         // row-major fp32, loaded, split and stored by the loader threads.
         constexpr int PER_WARP = W_UNITS / 8;     // 13

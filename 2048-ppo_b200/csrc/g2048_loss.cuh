@@ -1,6 +1,6 @@
 // g2048_loss.cuh -- per-sample PPO-clip + critic + entropy terms and their analytic gradients
 // (train.py:497-554), shared by ppo_loss_kernel (g2048_train.cu) and the fused update kernel
-// (g2048_update_fused.cu).
+// (g2048_update_x3.cu).
 #pragma once
 #include <cmath>
 #include <cstdint>

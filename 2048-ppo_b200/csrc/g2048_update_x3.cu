@@ -153,12 +153,12 @@ __device__ __forceinline__ void ld256(const float* p, float* v) {
 
 // Column sums over the 32 rows of a warp for 4 columns of two tensors; the 8 totals go to `dst_a[0..3]` and `dst_b[0..3]`
 // with single-writer red.global (the same lane writes the same address every tile).
-__device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, const float* a, const float* b, float* dst_a, float* dst_b) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        scr[j][lane] = a[j];
-        scr[4 + j][lane] = b[j];
-    }
+// (not inlined, like the Philox call of the dropout mask: the epilogues below are unrolled over a thread's 6-7 column units,
+// and a kernel body of 230 KB spent 38 % of its stall samples waiting for instruction fetches -- ncu, profiles/)
+__device__ __noinline__ void colsum4x2(float (*scr)[32], int lane, float a0, float a1, float a2, float a3, float b0, float b1, float b2,
+                                       float b3, float* dst_a, float* dst_b) {
+    scr[0][lane] = a0; scr[1][lane] = a1; scr[2][lane] = a2; scr[3][lane] = a3;
+    scr[4][lane] = b0; scr[5][lane] = b1; scr[6][lane] = b2; scr[7][lane] = b3;
     __syncwarp();
     const int v = lane >> 2, seg = lane & 3;
     const float4 p0 = *reinterpret_cast<const float4*>(&scr[v][seg * 8]), p1 = *reinterpret_cast<const float4*>(&scr[v][seg * 8 + 4]);
@@ -172,7 +172,7 @@ __device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, const floa
 // Dropout mask of 8 consecutive columns of one sample in block l (game.py:1038-1046: x + Dropout(ReLU(LN(Linear x)))):
 // one Philox4x32-10 call, counter = (sample index, l, column group), key = the call's dropout seed; column j of the
 // group is KEPT iff the j-th 16-bit lane of the 128 random bits is >= drop_thr = round(p * 65536).  Bit j of the result.
-__device__ __forceinline__ uint32_t dropout_keep8(const Params& p, int64_t sample, int l, int col) {
+__device__ __noinline__ uint32_t dropout_keep8(const Params& p, int64_t sample, int l, int col) {
     const U4 r = philox4x32_10(uint32_t(sample), uint32_t(uint64_t(sample) >> 32), uint32_t(l), uint32_t(col >> 3),
                                uint32_t(p.drop_seed), uint32_t(p.drop_seed >> 32));
     const uint32_t t2 = p.drop_thr * 0x00010001u;
@@ -228,12 +228,13 @@ __device__ __forceinline__ void store_quad(const RowCtx& c, int blk, const float
 // LayerNorm l: h_l = [h_{l-1} +] Dropout(relu(LN(z_l))).  Pass 1: this thread's columns of D -> registers, statistics,
 // z -> scratch (backward, l < L).  Pass 2: X (TMEM), the next A operand / the image of h_l, rounds; for l == L the 5 head dot
 // products (complete on part 0).  Thread columns: blocks 4i + part (16 each) and 4 columns of every remainder block.
-template <int HP, bool STEM, bool DROP>
+// One copy of the code serves the stem (l == 0: bias b0, no residual, no dropout) and the residual blocks.
+template <int HP, bool DROP>
 __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCtx& c, int l, float (&o)[5], uint64_t& keep_bits) {
     using SM = Smem<HP>;
     constexpr int NBF = SM::NBF, NR = SM::NR;
     const int L = p.L;
-    const bool last = l == L;
+    const bool last = l == L, STEM = l == 0;
     float z[NBF > 0 ? NBF : 1][16], zr[NR > 0 ? NR : 1][4];
     {
         uint32_t raw[NBF > 0 ? NBF : 1][16], rawr[NR > 0 ? NR : 1][4];
@@ -301,13 +302,14 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
     if (write_a) wait_a_free(S, p, c);
 
     // ---- pass 2, 8 columns at a time
+    const float dscale = STEM ? 1.0f : p.drop_scale;
     auto unit8 = [&](const float* zz, int col, float* x, uint32_t keep) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaf(fmaf(zz[j], rstd, shift), gam[col + j], bet[col + j]);
             float r = fmaxf(y, 0.f);
-            if (!STEM && DROP) r = ((keep >> j) & 1u) ? r * p.drop_scale : 0.f;
-            x[j] = STEM ? r : x[j] + r;
+            if (DROP) r = ((keep >> j) & 1u) ? r * dscale : 0.f;
+            x[j] += r;                 // x = h_{l-1} (0 for the stem)
         }
         if (last) {
 #pragma unroll
@@ -329,6 +331,10 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
                 keep = dropout_keep8(p, p.sample0 + c.grow, l, col);
                 keep_bits |= uint64_t(keep) << (16 * i + 8 * u);
             }
+            if (STEM) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
             unit8(&z[i][8 * u], col, x, keep);
             if (!last) tc::tmem_st8(c.tX + uint32_t(col), x);
             if (write_a) store_unit<HP>(c, blk, u, x, !c.valid);
@@ -346,6 +352,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = tc::tmem_ld_pin(raw[j]);
         }
+        if (STEM) x[0] = x[1] = x[2] = x[3] = 0.f;
         uint32_t keep = 0xFu;
         if (!STEM && DROP) {
             keep = (dropout_keep8(p, p.sample0 + c.grow, l, col) >> (col & 7)) & 0xFu;
@@ -355,8 +362,8 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
         for (int j = 0; j < 4; ++j) {
             const float y = fmaf(fmaf(zr[r][j], rstd, shift), gam[col + j], bet[col + j]);
             float rr = fmaxf(y, 0.f);
-            if (!STEM && DROP) rr = ((keep >> j) & 1u) ? rr * p.drop_scale : 0.f;
-            x[j] = STEM ? rr : x[j] + rr;
+            if (DROP) rr = ((keep >> j) & 1u) ? rr * dscale : 0.f;
+            x[j] += rr;
         }
         if (last) {
 #pragma unroll
@@ -419,7 +426,8 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
     float xh[NBF > 0 ? NBF : 1][16], xhr[NR > 0 ? NR : 1][4];
     float s1 = 0.f, s2 = 0.f;
 
-    // ---- pass A, 8 columns at a time (4 for the remainder units)
+    // ---- pass A, 8 columns at a time (4 for the remainder units).  (Requesting z_l of all 52 columns up front, straight into
+    // the xhat registers, was measured: 5 % slower -- the longer live ranges spill.)
     auto unitA = [&](int col, int n, const float* z, const float* dh, float* xhat, uint32_t keep) {
         float gx[8], gg[8];
 #pragma unroll
@@ -436,8 +444,8 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             gg[j] = gj;
             gx[j] = gj * x;
         }
-        colsum4x2(scr, c.lane, gx, gg, lnp + col, lnp + HP + col);
-        if (n == 8) colsum4x2(scr, c.lane, gx + 4, gg + 4, lnp + col + 4, lnp + HP + col + 4);
+        colsum4x2(scr, c.lane, gx[0], gx[1], gx[2], gx[3], gg[0], gg[1], gg[2], gg[3], lnp + col, lnp + HP + col);
+        if (n == 8) colsum4x2(scr, c.lane, gx[4], gx[5], gx[6], gx[7], gg[4], gg[5], gg[6], gg[7], lnp + col + 4, lnp + HP + col + 4);
     };
 #pragma unroll
     for (int i = 0; i < NBF; ++i) {
@@ -743,20 +751,17 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_x3_kernel(const Params 
                 warp_arrive(&S.in_ready, lane);
             }
             float o[5];
-            uint64_t keep_bits[MAXL + 1];                           // dropout masks of this thread's columns, per block
-#pragma unroll
-            for (int l = 0; l <= MAXL; ++l) keep_bits[l] = 0ull;
-            tc::mbar_wait(&S.mma_done, mma_par);
-            mma_par ^= 1u;
-            tc::fence_after_sync();
-            fwd_epilogue<HP, true, DROP>(S, p, c, 0, o, keep_bits[0]);
-#pragma unroll
-            for (int l = 1; l <= MAXL; ++l) {
-                if (l > L) break;
+            uint64_t keep1 = 0ull, keep2 = 0ull;                    // dropout masks of this thread's columns in blocks 1 and 2
+            for (int l = 0; l <= L; ++l) {                          // z_l is in D once the stage's MMAs are done
                 tc::mbar_wait(&S.mma_done, mma_par);
                 mma_par ^= 1u;
                 tc::fence_after_sync();
-                fwd_epilogue<HP, false, DROP>(S, p, c, l, o, keep_bits[l]);
+                uint64_t kb = 0ull;
+                fwd_epilogue<HP, DROP>(S, p, c, l, o, kb);
+                if (DROP) {
+                    if (l == 1) keep1 = kb;
+                    if (l == 2) keep2 = kb;
+                }
             }
             // ---- heads -> loss terms and their gradients (one thread per row)
             if (c.part == 0) {
@@ -790,15 +795,14 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_x3_kernel(const Params 
             }
             if (!p.backward) continue;
             row_sync();
-            // ---- backward-data
-            bwd_epilogue<HP, DROP>(S, p, c, L, true, L == 2 ? keep_bits[2] : keep_bits[1]);
-#pragma unroll
-            for (int l = MAXL; l >= 1; --l) {
-                if (l > L) continue;
-                tc::mbar_wait(&S.mma_done, mma_par);               // D = dz_l W_l
-                mma_par ^= 1u;
-                tc::fence_after_sync();
-                bwd_epilogue<HP, DROP>(S, p, c, l - 1, false, keep_bits[l - 1]);
+            // ---- backward-data: LayerNorm L first (z_L still in D), then l = L-1 .. 0 once D = dz_{l+1} W_{l+1} is done
+            for (int l = L; l >= 0; --l) {
+                if (l < L) {
+                    tc::mbar_wait(&S.mma_done, mma_par);
+                    mma_par ^= 1u;
+                    tc::fence_after_sync();
+                }
+                bwd_epilogue<HP, DROP>(S, p, c, l, l == L, l == 2 ? keep2 : keep1);
             }
         }
         // ---- per-CTA loss sums and head-bias gradients, fixed order

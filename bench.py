@@ -291,8 +291,8 @@ def rollout_section(args, dev, world, rank, barrier):
         return res
 
     out = {"model_flops_per_env_step": flops,
-           "update": "update_mlp_kernel (one tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-bf16 GEMMs: x6 forward, "
-                     "x3 backward) + x3_wgrad_kernel weight gradients, Muon+AdamW"}
+           "update": "update_mlp_x3_kernel (one pipelined tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-fp16 GEMMs, "
+                     "three products per k-step in both directions) + x3_wgrad_kernel weight gradients on the fp16 operand images, Muon+AdamW"}
     if world == 1:
         c3 = measure(args.rollout_envs, args.rollout_steps, 10, True)
         c3["workload"] = (f"c3: GameMLP h=196 L=2 fused rollout, {args.rollout_envs} envs x {args.rollout_steps} steps on one GPU, "

@@ -280,15 +280,18 @@ int g2048_x3_wgrad_tiled(const float* dY, const float* X, float* dW, void* works
 int g2048_x3_wgrad_images(const float* dY, const float* X, float* dW, void* workspace, int64_t M, int32_t N, int32_t K,
                           int32_t dy_hp, int32_t x_hp, int32_t fp16, void* stream);
 
-/* ---- policy update: fused forward + loss + backward-data of GameMLP (csrc/g2048_update_fused.cu) ----
+/* ---- policy update: fused forward + loss + backward-data of GameMLP (csrc/g2048_update_x3.cu) ----
  * One persistent tcgen05 kernel runs, per 128-sample tile and without leaving the SM, what
  * model_optimize_step does between `model(x)` and the weight gradients (train.py:491-556): the GameMLP
  * forward (game.py:1145-1220) from packed boards, the PPO-clip + critic + entropy terms (train.py:497-554)
- * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-bf16: three terms per
- * operand in the forward (fp32-grade pre-activations, ~1e-6), two in the backward (~1e-5).
- * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], as the bf16 hi|lo
- * operand images of g2048_x3_wgrad_tiled (ceil(n/128) * 128 * HP * 4 bytes per l, HP = hidden rounded up to 16),
- * plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0), row-major; then (g2048_x3_wgrad_tiled)
+ * and autograd's backward down to every pre-LayerNorm gradient dz_l.  GEMMs are split-fp16: every operand is two fp16
+ * terms (22 mantissa bits) and every k-step three products, forward and backward (fp32-grade, ~2e-7 of scale).  fp16 terms
+ * want O(1) magnitudes, so the caller passes inv_n PRE-MULTIPLIED by a power-of-two loss scale S (for a mean over 3e7
+ * samples 1/n alone is below the fp16 range): dhead, dz_out, ln_grad, head_bias_grad and every weight gradient formed from
+ * the images then carry the factor S, which the caller divides out (stats do not).
+ * It emits what the weight-gradient GEMMs need, h_out[l] (l = 0 stem output .. L) and dz_out[l], as the fp16 hi|lo
+ * operand images of g2048_x3_wgrad_images (ceil(n/128) * 128 * HP * 4 bytes per l, HP = g2048_update_mlp_padded(hidden)),
+ * plus dhead [n, 8] = d loss / d (4 logits, V, 0, 0, 0), row-major; then (g2048_x3_wgrad_images, fp16 = 1)
  *     d stem.0.weight        = wgrad(dz_out[0], g2048_encode(boards))        [hidden, 48]
  *     d backbone.l.mlp.0.w   = wgrad(dz_out[l+1], h_out[l])                  [hidden, hidden]
  *     d (action|value) head  = wgrad(dhead, h_out[L]) rows 0..3 | 4          [8, hidden]
