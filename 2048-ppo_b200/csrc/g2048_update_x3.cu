@@ -155,7 +155,7 @@ __device__ __forceinline__ void ld256(const float* p, float* v) {
 // with single-writer red.global (the same lane writes the same address every tile).
 // (not inlined, like the Philox call of the dropout mask: the epilogues below are unrolled over a thread's 6-7 column units,
 // and a kernel body of 230 KB spent 38 % of its stall samples waiting for instruction fetches -- ncu, profiles/)
-__device__ __noinline__ void colsum4x2(float (*scr)[32], int lane, float a0, float a1, float a2, float a3, float b0, float b1, float b2,
+__device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, float a0, float a1, float a2, float a3, float b0, float b1, float b2,
                                        float b3, float* dst_a, float* dst_b) {
     scr[0][lane] = a0; scr[1][lane] = a1; scr[2][lane] = a2; scr[3][lane] = a3;
     scr[4][lane] = b0; scr[5][lane] = b1; scr[6][lane] = b2; scr[7][lane] = b3;
