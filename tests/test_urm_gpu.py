@@ -1,7 +1,7 @@
 """GameURM fused rollout kernel (BASELINE config #5) through the C ABI: the integer env path
 bit-exact against the oracle; log-probs / values against (a) a torch emulation of the kernel's
-arithmetic (bf16 GEMM operands and K/V, fp32 elsewhere) tightly and (b) the fp32 reference model
-(the reference-generated fixture tests/golden/model_urm.npz) at bf16 tolerance."""
+arithmetic (fp16 GEMM operands and K/V, fp32 elsewhere) tightly and (b) the fp32 reference model
+(the reference-generated fixture tests/golden/model_urm.npz) at the tolerance of 11-bit operands over 8 block applications."""
 import numpy as np
 import pytest
 import torch
@@ -22,9 +22,9 @@ def load_urm(golden):
     return m.cuda(), g
 
 
-def urm_bf16_emulation(model, x48):
+def urm_fp16_emulation(model, x48):
     from g2048.policy import rms_norm
-    r = lambda t: t.bfloat16().float()
+    r = lambda t: t.half().float()
     b = x48.shape[0]
     cfg = model.config
     emb = model.stem(x48.view(b, 16, 3))
@@ -73,13 +73,13 @@ def test_urm_rollout_first_step_matches_reference_fixture(golden):
     err_lp = float((got[fin] - want[fin]).abs().max())
     err_v = float((buf.value[0] - ref_v).abs().max())
     print(f"URM tensor-core rollout vs the reference's fp32 outputs: max |dlogp| = {err_lp:.4f}, max |dV| = {err_v:.4f}")
-    assert err_lp < 0.15 and err_v < 0.15
+    assert err_lp < 0.02 and err_v < 0.02      # bf16 operands (round 1): 0.10 / 0.08
     from g2048 import env
     with torch.no_grad():
-        el, ev = urm_bf16_emulation(model, env.encode(boards))
+        el, ev = urm_fp16_emulation(model, env.encode(boards))
     emu = masked_lp(el, buf.legal[0])
-    assert float((got[fin] - emu[fin]).abs().max()) < 8e-2 and float((buf.value[0] - ev).abs().max()) < 8e-2
-    assert float((got[fin] - emu[fin]).abs().mean()) < 1e-2 and float((buf.value[0] - ev).abs().mean()) < 1e-2
+    assert float((got[fin] - emu[fin]).abs().max()) < 2e-2 and float((buf.value[0] - ev).abs().max()) < 2e-2
+    assert float((got[fin] - emu[fin]).abs().mean()) < 2e-3 and float((buf.value[0] - ev).abs().mean()) < 2e-3
 
 
 @pytest.mark.parametrize("B,T,layers", [(100, 6, 2), (8, 3, 1), (1000, 2, 2)])
@@ -105,15 +105,15 @@ def test_urm_rollout_env_path_bit_exact(B, T, layers):
             nb = np.where(d, O.reset_batch(B, seed=seed ^ RESET_TWEAK, env0=env0, ctr=1 + t), nb)
         b = nb
     with torch.no_grad():
-        el, ev = urm_bf16_emulation(model, env.encode(buf.boards.reshape(-1)))
+        el, ev = urm_fp16_emulation(model, env.encode(buf.boards.reshape(-1)))
     emu = masked_lp(el, buf.legal)
     got = buf.logp.reshape(-1, 4)
     fin = torch.isfinite(emu)
     assert torch.equal(torch.isfinite(got), fin)
-    # 8 block applications of bf16-operand GEMMs: a rounding flip can move a single output by a few 1e-2
-    # (outlier bound), while the bulk agrees to ~1e-3 (mean bound)
-    assert float((got[fin] - emu[fin]).abs().max()) < 8e-2 and float((buf.value.reshape(-1) - ev).abs().max()) < 8e-2
-    assert float((got[fin] - emu[fin]).abs().mean()) < 1e-2 and float((buf.value.reshape(-1) - ev).abs().mean()) < 1e-2
+    # 8 block applications of fp16-operand GEMMs: a rounding flip can move a single output by ~1e-2
+    # (outlier bound), while the bulk agrees to a few 1e-4 (mean bound)
+    assert float((got[fin] - emu[fin]).abs().max()) < 2e-2 and float((buf.value.reshape(-1) - ev).abs().max()) < 2e-2
+    assert float((got[fin] - emu[fin]).abs().mean()) < 2e-3 and float((buf.value.reshape(-1) - ev).abs().mean()) < 2e-3
 
 
 def test_trainer_urm_train_steps_match_autograd_on_the_same_batch():
