@@ -212,7 +212,10 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
 #pragma unroll
     for (int q = 0; q < 5; ++q) o2[q] = make_float2(0.f, 0.f);
 
-    // ---- pass 2, full blocks, 8 columns (one 16-byte operand unit per part) at a time
+    // ---- pass 2, full blocks, 8 columns (one 16-byte operand unit per part) at a time; the residual stream of the next
+    // unit is requested from TMEM before this one is worked on
+    uint32_t xraw[8];
+    if (!STEM && NBF > 0) tc::tmem_ld8_issue(c.tX + uint32_t(16 * c.part), xraw);
 #pragma unroll
     for (int i = 0; i < NBF; ++i) {
         const int blk = 4 * i + c.part;
@@ -220,7 +223,13 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
         for (int u = 0; u < 2; ++u) {
             const int col0 = 16 * blk + 8 * u;
             float x[8];
-            if (!STEM) tc::tmem_ld8(c.tX + uint32_t(col0), x);
+            if (!STEM) {
+                tc::tmem_ld_wait_all();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = tc::tmem_ld_pin(xraw[j]);
+                if (u == 0) tc::tmem_ld8_issue(c.tX + uint32_t(col0 + 8), xraw);
+                else if (i + 1 < NBF) tc::tmem_ld8_issue(c.tX + uint32_t(16 * (blk + 4)), xraw);
+            }
             const float4* g4 = reinterpret_cast<const float4*>(gamma + col0);
             const float4* e4 = reinterpret_cast<const float4*>(beta + col0);
 #pragma unroll
