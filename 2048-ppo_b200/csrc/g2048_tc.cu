@@ -79,6 +79,9 @@ extern "C" int g2048_tc_gemm_selftest_fmt(const float* A, const float* W, float*
                                           void* stream) {
     using namespace g2048;
     G2048_REQUIRE(A && W && C, "g2048_tc_gemm_selftest: NULL pointer argument");
+    // measured on B200: a kind::f16 MMA whose A and B formats differ (bf16 x fp16) faults the launch, although the
+    // instruction descriptor has separate fields for them -- both operands take the same format here and everywhere else
+    G2048_REQUIRE((a_f16 != 0) == (w_f16 != 0), "g2048_tc_gemm_selftest: A and W must have the same term format (both fp16 or both bf16)");
     G2048_REQUIRE(K >= 16 && K <= 256 && K % 16 == 0, "g2048_tc_gemm_selftest: K must be a multiple of 16 in [16,256]");
     G2048_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "g2048_tc_gemm_selftest: N must be a multiple of 16 in [16,256]");
     const int kblocks = (K + 63) / 64;

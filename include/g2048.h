@@ -351,8 +351,8 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* params, void* stream);
  * A[128,K] * W[N,K]^T with bf16-rounded operands and fp32 accumulation in tensor memory.
  * K, N multiples of 16, <= 256.  Pins the UMMA descriptor / swizzle conventions on hardware. */
 int g2048_tc_gemm_selftest(const float* A, const float* W, float* C, int32_t K, int32_t N, void* stream);
-/* the same with the operand formats chosen per operand (1 = fp16, 0 = bf16): pins that kind::f16 takes A and B formats
- * independently (the fused update multiplies bf16 gradient images with fp16 activation images) */
+/* the same with the term format chosen (1 = fp16, 0 = bf16) for BOTH operands: a kind::f16 MMA with one bf16 and one fp16
+ * operand faults on B200 (measured), so a_f16 != w_f16 is rejected with G2048_EINVAL */
 int g2048_tc_gemm_selftest_fmt(const float* A, const float* W, float* C, int32_t K, int32_t N, int32_t a_f16, int32_t w_f16,
                                void* stream);
 
