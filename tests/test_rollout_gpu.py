@@ -309,6 +309,46 @@ def test_full_size_rollout_properties(precision):
             assert bool((tiles == 2).all())
 
 
+def test_c3_horizon_rollout_replayed_through_the_oracle():
+    """The C3 horizon (512 steps, auto-reset) on 4096 envs with the kernel `auto` selects at C3's env count: every one of the
+    2 097 152 transitions is replayed through the oracle env (boards, legal masks, points, flags, every shaping integer,
+    the reset boards), and every recorded log-prob / value / entropy is compared with the torch fp32 policy."""
+    from g2048 import env, rollout
+    model = random_model(196, 2, seed=17)
+    B, T, seed, env0 = 4096, 512, 2048, 1 << 20
+    assert rollout.resolve_precision("auto", 65536, 2) == "x3"
+    boards = env.reset(B, device=0, seed=seed, env0=env0, ctr=0)
+    start = boards.clone()
+    buf = rollout.rollout(rollout.pack_policy(model), boards, T, seed=seed, env0=env0, ctr0=1, auto_reset=True, precision="x3")
+    h = {k: getattr(buf, k).cpu().numpy() for k in ("boards", "actions", "legal", "points", "flags", "shaping")}
+    b = start.cpu().numpy().view(np.uint64)
+    resets = 0
+    for t in range(T):
+        np.testing.assert_array_equal(h["boards"][t].view(np.uint64), b, err_msg=f"t={t}")
+        nb, info = O.step_batch(b, h["actions"][t], seed=seed, env0=env0, ctr=1 + t)
+        assert (info["invalid"] == 0).all()
+        np.testing.assert_array_equal(h["legal"][t], info["legal_before"])
+        np.testing.assert_array_equal(h["points"][t], info["points"])
+        np.testing.assert_array_equal(h["flags"][t], 0x80 | info["legal_after"] | (info["done"] << 4))
+        sh = env.decode_shaping(h["shaping"][t])
+        for k in SH_KEYS:
+            np.testing.assert_array_equal(sh[k], info[k], err_msg=k)
+        d = info["done"].astype(bool)
+        if d.any():
+            resets += int(d.sum())
+            nb = np.where(d, O.reset_batch(B, seed=seed ^ RESET_TWEAK, env0=env0, ctr=1 + t), nb)
+        b = nb
+    np.testing.assert_array_equal(boards.cpu().numpy().view(np.uint64), b)
+    assert resets > 0, "a 512-step horizon must see finished games"
+    lp, v, ent = torch_policy_outputs(model, buf.boards, buf.legal)
+    got = buf.logp.reshape(-1, 4)
+    fin = torch.isfinite(lp)
+    assert torch.equal(torch.isfinite(got), fin)
+    torch.testing.assert_close(got[fin], lp[fin], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(buf.value.reshape(-1), v, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(buf.entropy.reshape(-1), ent, rtol=1e-4, atol=2e-5)
+
+
 def test_evaluate_reports_the_reference_metrics(golden, tmp_path):
     """rollout.evaluate = the eval block of train.py:1840-1875 without the episode dictionaries: its scores are the
     total_points play_games_batched reports for the same seeded games, and the checkpoint round-trips."""
