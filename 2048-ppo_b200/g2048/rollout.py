@@ -193,13 +193,15 @@ _GAMES_PLAYED = itertools.count()
 _CHUNK = 256
 
 
-def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, device) -> list[dict]:
+def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, device, game_state_on_device: bool = False) -> list[dict]:
     """Device records -> list[EpisodeData] exactly as train.py:299-345 builds them (host-side slow path)."""
     cat = lambda name: torch.cat([getattr(b, name) for b in bufs], dim=0)
     boards, flags = cat("boards"), cat("flags")
     T, B = flags.shape
     _check_overflow(flags)
     game_state = env.encode(boards.reshape(-1)).reshape(T, B, 48)
+    if not game_state_on_device:
+        game_state = game_state.cpu()
     ex = env.expand4(boards.reshape(-1))
     pts_possible = ex["points"].reshape(T, B, 4).cpu().numpy()
     pre_spawn = torch.gather(ex["succ"], 1, cat("actions").reshape(-1, 1).long()).reshape(-1)
@@ -251,8 +253,16 @@ def _episode_dicts(bufs: list[RolloutBuffers], final_boards: torch.Tensor, devic
 
 
 @torch.no_grad()
-def play_games_batched(model, num_games: int, max_steps: int | None = None, device=None, *, seed: int | None = None):
-    """Play `num_games` games to the end (or `max_steps` moves each) -> list[EpisodeData]."""
+def play_games_batched(model, num_games: int, max_steps: int | None = None, device=None, *, seed: int | None = None,
+                       game_state_on_device: bool = False):
+    """Play `num_games` games to the end (or `max_steps` moves each) -> list[EpisodeData].
+
+    `game_state` tensors are returned on the HOST by default: the reference's symmetry augmentation builds the
+    `game_state` of its copies with `Game2048(...).to_model_format()` on the CPU (train.py:840, 869) and `collate_fn` stacks
+    both kinds in one minibatch (train.py:396) before `model_optimize_step` moves the batch to the device (train.py:468-474),
+    so device tensors here would make the unmodified `train.py --gpu --upsample-ratio 0.25` fail in `torch.stack`
+    (play_game_for_episode's own device tensors, train.py:257-258, 303, hit exactly that).  game_state_on_device=True keeps
+    them on `device`."""
     if device is None or torch.device(device).type != "cuda":
         raise RuntimeError("play_games_batched runs on a CUDA device only (no CPU fallback); pass --gpu / device='cuda'")
     dev = env.init(device)
@@ -272,7 +282,7 @@ def play_games_batched(model, num_games: int, max_steps: int | None = None, devi
         played += T
         if not bool(alive.any()):
             break
-    return _episode_dicts(bufs, boards, dev)
+    return _episode_dicts(bufs, boards, dev, game_state_on_device)
 
 
 @torch.no_grad()

@@ -175,7 +175,7 @@ def test_play_games_batched_drop_in_schema(golden):
         assert ep["total_points"] == sum(m["points_earned"] for m in moves)
         assert not env.Game2048.state_has_next_step(ep["final_state"])
         for i, m in enumerate(moves):
-            assert m["game_state"].shape == (48,) and m["game_state"].is_cuda
+            assert m["game_state"].shape == (48,) and not m["game_state"].is_cuda      # host tensors: see play_games_batched
             assert len(m["policy_logprobs"]) == 4 and len(m["action_mask"]) == 4
             assert {"adjacency_delta", "chain_delta", "topological_delta", "smoothness_delta", "corner_delta"} <= set(m)
             assert not m["action_mask"][m["selected_direction"]]
@@ -190,8 +190,9 @@ def test_play_games_batched_drop_in_schema(golden):
         cells = lambda x: np.array(O.unpack_board(x)).reshape(-1)
         diff = cells(pre) != np.array(moves[0]["result_state"]).reshape(-1)
         assert diff.sum() == 1
-    capped = batched_rollout.play_games_batched(model, num_games=3, max_steps=10, device="cuda:0", seed=3)
+    capped = batched_rollout.play_games_batched(model, num_games=3, max_steps=10, device="cuda:0", seed=3, game_state_on_device=True)
     assert all(len(ep["moves"]) == 10 and ep["total_steps"] == 10 for ep in capped)
+    assert all(m["game_state"].is_cuda for ep in capped for m in ep["moves"])
     with pytest.raises(RuntimeError):
         batched_rollout.play_games_batched(model, num_games=1, device=None)
 
