@@ -36,9 +36,9 @@ MOVES = 4
 N_TRANS = N_BOARDS * MOVES
 BYTES_PER_TRANSITION = 30      # 8 board in + 1 action + 8 board out + 4 points + 1 flags + 8 shaping
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel_dense launch on this workload, from the
-# committed `ncu --set full` capture (profiles/r01_step_dense_ncu.txt: 38.0 MB read + 32.5 MB written; the rest of
+# committed `ncu --set full` capture (profiles/r02_step_dense_ncu.txt: 38.0 MB read + 32.8 MB written; the rest of
 # the 88 MB of outputs is still dirty in the 126 MB L2 when the kernel ends)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 70.5e6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 70.8e6
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 WORKLOAD = ("c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step "
@@ -135,14 +135,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.002 if len(self.samples) < 200 else 0.05)     # dense over the timed step region, sparse over the later sections
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
         med = int(np.median(self.samples)) if self.samples else None
+        busy = [c for c in self.samples if self.max_mhz is None or c >= 0.5 * self.max_mhz]     # idle gaps between sections clock down
+        med = int(np.median(busy)) if busy else med
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "sm_mhz_min": int(min(self.samples)) if self.samples else None}
 
 
 def cpu_baseline(min_seconds: float = 10.0):
@@ -393,7 +395,6 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -490,6 +491,7 @@ def run_ours(args):
     if not args.no_rollout:
         ro = rollout_section(args, dev, world, rank, barrier)
 
+    clocks = sampler.stop()      # sampled from the timed step region to the end of the GPU sections (the K timed launches alone last ~1.5 ms)
     if rank == 0:
         finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING, expand)
     if world > 1:
