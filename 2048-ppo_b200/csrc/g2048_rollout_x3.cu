@@ -81,7 +81,10 @@ struct Smem {
 static_assert(sizeof(Smem<208>) + 1024 <= 232448, "x3 rollout kernel exceeds the 227 KB shared memory limit");
 static_assert(Smem<208>::RING >= 4, "weight ring too short to cover the L2 latency");
 
-__device__ __forceinline__ void env_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ENV_THREADS) : "memory"); }
+// The four threads of an env row sit in the four warps of one lane quarter (warps q, q + 4, q + 8, q + 12), and everything they
+// exchange is per row: one named barrier per quarter (128 threads) instead of one over all 512 env threads, so that a slow
+// quarter does not hold up the other three.
+__device__ __forceinline__ void row_sync(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory"); }
 
 // one warp's arrival on a round barrier: every lane's operand bytes visible to the async proxy first
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
@@ -200,7 +203,7 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
     S.red[0][c.part][c.row] = sum2.x + sum2.y;
     S.red[1][c.part][c.row] = sq2.x + sq2.y;
     tc::fence_before_sync();          // every thread's reads of D are complete before the next GEMM may overwrite it
-    env_sync();
+    row_sync(c.row >> 5);
     const float inv_h = 1.0f / float(h);
     const float tsum = (S.red[0][0][c.row] + S.red[0][1][c.row]) + (S.red[0][2][c.row] + S.red[0][3][c.row]);
     const float tsq = (S.red[1][0][c.row] + S.red[1][1][c.row]) + (S.red[1][2][c.row] + S.red[1][3][c.row]);
@@ -314,7 +317,7 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
 #pragma unroll
             for (int q = 0; q < 5; ++q) S.headp[c.part - 1][c.row][q] = o[q];
         }
-        env_sync();
+        row_sync(c.row >> 5);
         if (c.part == 0) {
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                 }
                 float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                 if (L == 0) {                                        // no MMA shadow to hide in: play the moves up front
-                    env_sync();
+                    row_sync(quarter);
                     precompute_moves<HP>(S, p, lut, row, uint32_t(half), env, ctr);
                 }
                 // ---- stages: s = 0 stem, s = 1..L residual blocks
