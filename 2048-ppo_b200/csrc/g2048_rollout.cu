@@ -510,6 +510,8 @@ int g2048_rollout_mlp(const G2048Rollout* r, void* stream) {
     p.rec_shaping = r->rec_shaping;
     p.rec_flags = r->rec_flags;
     p.rec_entropy = r->rec_entropy;
+    p.sched = static_cast<int32_t*>(r->sched_workspace);
+    p.segs = 1;
     cudaStream_t st = cudaStream_t(stream);
     if (r->tensor_cores) {
         G2048_REQUIRE((reinterpret_cast<uintptr_t>(r->packed_weights) & 255u) == 0,

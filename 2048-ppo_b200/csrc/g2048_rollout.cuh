@@ -32,6 +32,8 @@ struct RolloutParams {
     uint64_t* rec_shaping;
     uint8_t* rec_flags;
     float* rec_entropy;            // or NULL
+    int32_t* sched;                // [ceil(B/128)] hand-off flags of the horizon segments (x3 kernel), zeroed before the launch; or NULL
+    int32_t segs;                  // horizon segments per tile (1 = a CTA plays a tile's whole horizon)
 };
 
 // packed weight layout (floats), HP = padded hidden

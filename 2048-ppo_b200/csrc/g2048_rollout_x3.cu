@@ -435,8 +435,20 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
     SM& S = *reinterpret_cast<SM*>(smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.layers, h = p.hidden;
+    // Work units: (tile, horizon segment).  With one segment per tile a CTA plays a tile's whole horizon and C3's 512 tiles are
+    // 3.46 waves on 148 SMs: every SM waits for the 68 that play a fourth tile.  With H segments the units are dealt round-robin
+    // (unit u = segment u / ntiles of tile u % ntiles -> CTA u % grid), a tile's board state passes from one segment to the next
+    // through p.boards / p.alive in global memory behind a per-tile flag, and the makespan is ceil(512 H / 148) / H horizons
+    // (3.5 at H = 2).  The unit a segment waits for always sits at an earlier position of some CTA's list: no cycle.
     const int64_t ntiles = (p.B + 127) / 128;
-    const int64_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int H = p.segs > 0 ? p.segs : 1;
+    const int64_t units = ntiles * H;
+    const int64_t my_units = units > blockIdx.x ? (units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint32_t my_steps = 0;
+    for (int64_t k = 0; k < my_units; ++k) {
+        const int seg = int((int64_t(blockIdx.x) + k * gridDim.x) / ntiles);
+        my_steps += uint32_t(int64_t(p.T) * (seg + 1) / H - int64_t(p.T) * seg / H);
+    }
     const uint8_t* img = reinterpret_cast<const uint8_t*>(p.packed + pk_x3_base(HP, L));
 
     // ---- one-time setup
@@ -470,9 +482,9 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
     const uint32_t tmem_base = S.tmem_base;
 
     if (warp == ENV_THREADS / 32) {
-        issuer<HP>(S, p, tmem_base, uint32_t(my_tiles) * uint32_t(p.T));
+        issuer<HP>(S, p, tmem_base, my_steps);
     } else if (warp == ENV_THREADS / 32 + 1) {
-        producer<HP>(S, p, uint32_t(my_tiles) * uint32_t(p.T), img);
+        producer<HP>(S, p, my_steps, img);
     } else {
         // ---------------- row = env in tile = TMEM lane; four threads (column parts) per row
         const LutGlobal lut{p.lut};
@@ -487,16 +499,28 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
         c.sw = uint32_t(c.row >> 2) & 1u;
         const int row = c.row;
         uint32_t mma_par = 0;                       // parity of the mma_done phase the next stage waits for
-        for (int64_t tl = 0; tl < my_tiles; ++tl) {
-            const int64_t env = (int64_t(blockIdx.x) + tl * gridDim.x) * 128 + row;
+        for (int64_t k = 0; k < my_units; ++k) {
+            const int64_t u = int64_t(blockIdx.x) + k * gridDim.x, tile = u % ntiles;
+            const int seg = int(u / ntiles);
+            const int t_begin = int(int64_t(p.T) * seg / H), t_end = int(int64_t(p.T) * (seg + 1) / H);
+            const int64_t env = tile * 128 + row;
             const bool owner = half == 0 && env < p.B;
+            if (seg > 0) {                                       // the tile's previous segment has left its boards in p.boards
+                if (tid == 0) {
+                    int v;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.sched + tile) : "memory");
+                    } while (v < seg);
+                }
+                asm volatile("bar.sync 5, %0;" ::"n"(ENV_THREADS) : "memory");
+            }
             Board board = {0u, 0u};
             bool alive = false;
             if (owner) {
-                board = make_board(p.boards[env]);
-                alive = p.alive ? p.alive[env] != 0 : true;
+                board = make_board(seg > 0 ? __ldcg(p.boards + env) : p.boards[env]);
+                alive = p.alive ? (seg > 0 ? __ldcg(p.alive + env) : p.alive[env]) != 0 : true;
             }
-            for (int t = 0; t < p.T; ++t) {
+            for (int t = t_begin; t < t_end; ++t) {
                 const uint64_t ctr = p.ctr0 + uint64_t(t);
                 uint32_t lm = 0;
                 if (owner) lm = begin_step(p, env, ctr, board, alive);
@@ -565,6 +589,11 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                 p.boards[env] = pack_board(board);
                 if (p.alive) p.alive[env] = alive ? 1 : 0;
             }
+            if (H > 1) {                                         // publish the segment: boards first, then the flag
+                __threadfence();
+                asm volatile("bar.sync 5, %0;" ::"n"(ENV_THREADS) : "memory");
+                if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.sched + tile), "r"(seg + 1) : "memory");
+            }
         }
     }
     tc::fence_before_sync();
@@ -573,14 +602,30 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
 }
 
 template <int HP>
-static int launch(const RolloutParams& p, cudaStream_t st) {
+static int launch(const RolloutParams& p_in, cudaStream_t st) {
+    RolloutParams p = p_in;
     const int smem = int(sizeof(Smem<HP>)) + 1024;
     auto kern = rollout_mlp_x3_kernel<HP>;
     G2048_CHECK_CUDA(ensure_smem(kern, smem));
     const int64_t ntiles = (p.B + 127) / 128;
     const int grid = int(ntiles < num_sms() ? ntiles : num_sms());
-    const int64_t tiles_per_cta = (ntiles + grid - 1) / grid;
-    if (tiles_per_cta * p.T * (int64_t(p.layers) * (HP / 16) + 1) >= (int64_t(1) << 31))
+    // horizon segments (see the kernel): only where they shorten the makespan, where there is a place to hand the env state
+    // over (a game that ended must stay ended: without auto-reset that needs the caller's alive array) and a flag array
+    p.segs = 1;
+    if (p.sched && ntiles > grid && p.T >= 64 && (p.auto_reset || p.alive)) {
+        const double one = double((ntiles + grid - 1) / grid);
+        double best = one;
+        for (int hseg = 2; hseg <= 4; ++hseg) {
+            const double m = double((ntiles * hseg + grid - 1) / grid) / hseg;
+            if (m < best * 0.97) {
+                best = m;
+                p.segs = hseg;
+            }
+        }
+    }
+    if (p.segs > 1) G2048_CHECK_CUDA(cudaMemsetAsync(p.sched, 0, size_t(ntiles) * sizeof(int32_t), st));
+    const int64_t units_per_cta = (ntiles * p.segs + grid - 1) / grid;
+    if (units_per_cta * (p.T / p.segs + 1) * (int64_t(p.layers) * (HP / 16) + 1) >= (int64_t(1) << 31))
         return fail(G2048_ESHAPE, "g2048_rollout_mlp: B * T too large for one launch of the tensor-core kernel; split the horizon");
     kern<<<grid, THREADS, smem, st>>>(p);
     G2048_CHECK_LAUNCH("rollout_mlp_x3_kernel");

@@ -29,7 +29,7 @@ class _RolloutStruct(C.Structure):
         ("forced_actions", C.c_void_p), ("rec_boards", C.c_void_p), ("rec_actions", C.c_void_p),
         ("rec_legal", C.c_void_p), ("rec_logp", C.c_void_p), ("rec_value", C.c_void_p), ("rec_points", C.c_void_p),
         ("rec_shaping", C.c_void_p), ("rec_flags", C.c_void_p), ("rec_entropy", C.c_void_p),
-        ("tensor_cores", C.c_int32), ("reserved_", C.c_int32),
+        ("tensor_cores", C.c_int32), ("reserved_", C.c_int32), ("sched_workspace", C.c_void_p),
     ]
 
 
@@ -139,6 +139,20 @@ class RolloutBuffers:
         return tuple(self.flags.shape)
 
 
+_SCHED: dict[int, torch.Tensor] = {}
+
+
+def _sched_workspace(dev, B: int) -> torch.Tensor:
+    """Per-device scratch for the x3 kernel's horizon segments (include/g2048.h G2048Rollout.sched_workspace); launches on
+    one device are stream-ordered, so one buffer per device serves them all."""
+    n = (B + 127) // 128
+    t = _SCHED.get(dev.index)
+    if t is None or t.numel() < n:
+        t = torch.zeros(max(n, 1024), dtype=torch.int32, device=dev)
+        _SCHED[dev.index] = t
+    return t
+
+
 def resolve_precision(precision: str, B: int, layers: int) -> str:
     """What "auto" means for B envs per GPU: the fp32-grade tensor-core kernel at large env batch, else fp32 FFMA."""
     if precision != "auto":
@@ -172,7 +186,7 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
                            _dp(policy.weights), _dp(env.lut(dev)), _dp(boards), _dp(alive), _dp(forced_actions),
                            _dp(buf.boards), _dp(buf.actions), _dp(buf.legal), _dp(buf.logp), _dp(buf.value),
                            _dp(buf.points), _dp(buf.shaping), _dp(buf.flags), _dp(buf.entropy),
-                           _PRECISION[resolve_precision(precision, B, policy.layers)], 0)
+                           _PRECISION[resolve_precision(precision, B, policy.layers)], 0, _dp(_sched_workspace(dev, B)))
         if policy.kind == "urm":
             _lib.call("g2048_rollout_urm", C.byref(s), policy.loops, _stream())
         else:

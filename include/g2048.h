@@ -212,6 +212,10 @@ typedef struct G2048Rollout {
                                   products per k-step, fp32 accumulation): fp32-grade, log-probs / values within
                                   2e-5 of the torch fp32 policy (game.py:1192-1203, train.py:256-274); <= 4 blocks */
     int32_t reserved_;
+    void* sched_workspace;  /* optional: 4 * ceil(B / 128) bytes of device scratch.  With it the X3 kernel cuts the horizon of a tile
+                               into segments dealt round-robin over the SMs (a tile's boards pass from segment to segment through
+                               `boards` / `alive`), which fills the last, partial wave of tiles: C3's 512 tiles are 3.46 waves on
+                               148 SMs.  Results do not depend on it.  NULL (or a zero-filled tail of the struct): off. */
 } G2048Rollout;
 
 int g2048_rollout_mlp(const G2048Rollout* params, void* stream);

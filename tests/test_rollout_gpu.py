@@ -350,6 +350,34 @@ def test_c3_horizon_rollout_replayed_through_the_oracle():
     torch.testing.assert_close(buf.entropy.reshape(-1), ent, rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_horizon_segments_give_identical_rollouts(auto_reset):
+    """More tiles than SMs and a horizon of >= 64 steps: the x3 kernel cuts each tile's horizon into segments dealt round-robin
+    over the SMs (board state handed over through global memory behind a flag).  Every record -- floats included -- must equal
+    the rollout of the same envs launched in two halves that fit the SMs (no segmentation), with and without auto-reset."""
+    from g2048 import env, rollout
+    model = random_model(196, 2, seed=23)
+    pol = rollout.pack_policy(model)
+    B, T, seed = 20000, 72, 77                      # 157 tiles on 148 SMs
+    names = ("boards", "actions", "legal", "points", "shaping", "flags", "logp", "value", "entropy")
+
+    def run(lo, hi):
+        boards = env.reset(hi - lo, device=0, seed=seed, env0=lo, ctr=0)
+        alive = None if auto_reset else torch.ones(hi - lo, dtype=torch.uint8, device="cuda")
+        buf = rollout.rollout(pol, boards, T, seed=seed, env0=lo, ctr0=1, auto_reset=auto_reset, alive=alive, precision="x3")
+        return buf, boards, alive
+
+    whole, wb, wa = run(0, B)
+    left, lb, la = run(0, B // 2)
+    right, rb, ra = run(B // 2, B)
+    for name in names:
+        assert torch.equal(getattr(whole, name), torch.cat([getattr(left, name), getattr(right, name)], dim=1)), name
+    assert torch.equal(wb, torch.cat([lb, rb]))
+    if not auto_reset:
+        assert torch.equal(wa, torch.cat([la, ra]))
+    assert bool((whole.flags & 0x80).any())
+
+
 def test_evaluate_reports_the_reference_metrics(golden, tmp_path):
     """rollout.evaluate = the eval block of train.py:1840-1875 without the episode dictionaries: its scores are the
     total_points play_games_batched reports for the same seeded games, and the checkpoint round-trips."""
