@@ -16,32 +16,11 @@
 // round 1 used bf16, 8 bits, and sat 0.10 / 0.08 off the fp32 model after the 8 block applications), everything else
 // fp32; tests compare against a torch emulation of exactly this arithmetic and against the reference's fp32 outputs.
 #include <cuda_fp16.h>
-#include "g2048_rollout.cuh"
+#include "g2048_urm.cuh"
 #include "g2048_tc.cuh"
 
 namespace g2048 {
 namespace urm {
-
-constexpr int H = 64, SEQ = 16, NHEAD = 4, HD = 16, INTER = 120, QKV = 3 * H, GU = 2 * INTER;
-constexpr int MAX_LAYERS = 2;
-constexpr int THREADS = 128;
-
-// packed parameter buffer: fp32 section, then (128-byte aligned) fp16 images per layer
-constexpr int F_STEM_W = 0;                       // [64][3]
-constexpr int F_STEM_G = F_STEM_W + H * 3;        // [64]
-constexpr int F_STEM_B = F_STEM_G + H;            // [64]
-constexpr int F_INIT = F_STEM_B + H;              // [16][64]
-constexpr int F_HEADW = F_INIT + SEQ * H;         // [5][64]
-constexpr int F_HEADB = F_HEADW + 5 * H;          // [8]
-constexpr int F_CONV = F_HEADB + 8;               // per layer: w0[128], w1[128], b[128]
-constexpr int F_CONV_STRIDE = 3 * 128;
-__host__ __device__ constexpr int f_total(int L) { return (F_CONV + L * F_CONV_STRIDE + 31) / 32 * 32; }
-constexpr int IMG_QKV = 0;                                   // [192 rows][128 B]
-constexpr int IMG_O = IMG_QKV + QKV * 128;                   // [64 rows][128 B]
-constexpr int IMG_GU = IMG_O + H * 128;                      // [240 rows][128 B]
-constexpr int IMG_D = IMG_GU + GU * 128;                     // 2 blocks x [64 rows][128 B] (K = 120 -> 128)
-constexpr int IMG_LAYER = IMG_D + 2 * H * 128;               // 79 872 B
-__host__ __device__ constexpr int64_t total_floats(int L) { return f_total(L) + int64_t(L) * IMG_LAYER / 4; }
 
 struct Smem {
     alignas(1024) uint8_t W[MAX_LAYERS * IMG_LAYER];
@@ -55,16 +34,6 @@ struct Smem {
     alignas(16) float conv[MAX_LAYERS][3][128];
     uint64_t a_ready, mma_done, w_full;
     uint32_t tmem_base;
-};
-
-struct PackSrc {
-    const float *stem_w, *stem_g, *stem_b, *init_hidden, *act_w, *act_b, *val_w, *val_b;
-    const float* qkv[MAX_LAYERS];
-    const float* o[MAX_LAYERS];
-    const float* gu[MAX_LAYERS];
-    const float* conv_w[MAX_LAYERS];
-    const float* conv_b[MAX_LAYERS];
-    const float* down[MAX_LAYERS];
 };
 
 __global__ void pack_kernel(PackSrc s, int L, float* __restrict__ out) {
@@ -442,7 +411,7 @@ extern "C" {
 
 int64_t g2048_urm_packed_floats(int32_t hidden, int32_t layers, int32_t heads, int32_t inter) {
     if (hidden != urm::H || heads != urm::NHEAD || inter != urm::INTER || layers < 1 || layers > urm::MAX_LAYERS) return -1;
-    return urm::total_floats(layers);
+    return urm::total_floats_all(layers);
 }
 
 int g2048_urm_pack(int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
@@ -464,7 +433,7 @@ int g2048_urm_pack(int32_t layers, const float* stem_w, const float* stem_ln_w, 
     }
     urm::pack_kernel<<<256, 256, 0, cudaStream_t(stream)>>>(s, layers, packed);
     G2048_CHECK_LAUNCH("urm::pack_kernel");
-    return G2048_OK;
+    return urm::launch_urm_x3_pack(s, layers, packed, cudaStream_t(stream));
 }
 
 int g2048_rollout_urm(const G2048Rollout* r, int32_t loops, void* stream) {
@@ -476,7 +445,7 @@ int g2048_rollout_urm(const G2048Rollout* r, int32_t loops, void* stream) {
     G2048_REQUIRE(r->packed_weights && r->lut && r->boards && r->rec_boards && r->rec_actions && r->rec_legal &&
                       r->rec_logp && r->rec_value && r->rec_points && r->rec_shaping && r->rec_flags,
                   "g2048_rollout_urm: NULL pointer argument");
-    G2048_REQUIRE((reinterpret_cast<uintptr_t>(r->packed_weights) & 127u) == 0, "g2048_rollout_urm: packed_weights must be 128-byte aligned");
+    G2048_REQUIRE((reinterpret_cast<uintptr_t>(r->packed_weights) & 255u) == 0, "g2048_rollout_urm: packed_weights must be 256-byte aligned");
     RolloutParams p{};
     p.B = r->B; p.T = r->T; p.hidden = r->hidden; p.layers = r->layers; p.auto_reset = r->auto_reset;
     p.seed = r->seed; p.env0 = r->env0; p.ctr0 = r->ctr0;
@@ -485,6 +454,8 @@ int g2048_rollout_urm(const G2048Rollout* r, int32_t loops, void* stream) {
     p.rec_boards = r->rec_boards; p.rec_actions = r->rec_actions; p.rec_legal = r->rec_legal; p.rec_logp = r->rec_logp;
     p.rec_value = r->rec_value; p.rec_points = r->rec_points; p.rec_shaping = r->rec_shaping; p.rec_flags = r->rec_flags;
     p.rec_entropy = r->rec_entropy;
+    // fp32 grade (split-fp16 operands) unless the caller asks for the single-fp16-operand variant by name
+    if (r->tensor_cores != G2048_ROLLOUT_BF16) return urm::launch_rollout_urm_x3(p, loops, cudaStream_t(stream));
     const int smem = int(sizeof(urm::Smem)) + 1024;
     G2048_CHECK_CUDA(ensure_smem(urm::rollout_urm_kernel, smem));
     const int64_t ntiles = (p.B + 7) / 8;

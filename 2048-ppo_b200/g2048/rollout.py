@@ -169,8 +169,15 @@ def rollout(policy: PackedPolicy, boards: torch.Tensor, T: int, *, seed: int, en
     products, fp32 accumulation: fp32-grade like "fp32", log-probs / values within 2e-5 of the torch fp32 policy),
     "bf16" = tcgen05 GEMMs on bf16-rounded operands (log-probs ~1e-2 off the fp32 policy: a labelled variant, never
     chosen automatically), "auto" = "x3" from TC_MIN_ENVS envs up (tensor cores only at large env batch)."""
-    if precision not in ("auto", "fp32", "bf16", "x3"):
-        raise ValueError(f"precision must be auto, fp32, x3 or bf16, got {precision!r}")
+    if precision not in ("auto", "fp32", "bf16", "fp16", "x3"):
+        raise ValueError(f"precision must be auto, fp32, x3 or bf16 (GameURM: auto, x3 or fp16), got {precision!r}")
+    if policy.kind == "urm":
+        # GameURM: the fp32-grade split-fp16 kernel unless the single-fp16-operand variant (1e-2 off the fp32 model) is asked for by name
+        if precision == "fp32":
+            raise ValueError("GameURM has no FFMA rollout kernel: precision is auto / x3 (fp32 grade) or fp16 (a labelled variant)")
+        precision = "bf16" if precision in ("bf16", "fp16") else "x3"
+    elif precision == "fp16":
+        raise ValueError("precision fp16 names the GameURM variant; GameMLP takes auto, fp32, x3 or bf16")
     boards = env._req(boards, torch.int64, "boards")
     B = boards.numel()
     dev = env.init(boards.device)

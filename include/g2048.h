@@ -221,12 +221,17 @@ typedef struct G2048Rollout {
 int g2048_rollout_mlp(const G2048Rollout* params, void* stream);
 
 /* GameURM policy (game.py:1223-1458, default GameURMConfig game.py:31-42: hidden 64, 4 heads,
- * inter 120, conv kernel 2; 1..2 layers) -- BASELINE config #5.  Same G2048Rollout records; the
- * projections run on tcgen05 (bf16 operands, fp32 accumulate), attention / norms / conv on CUDA
- * cores.  `loops` = GameURMConfig.num_loops.  Pointer arrays hold `layers` device pointers:
+ * inter 120, conv kernel 2; 1..2 layers) -- BASELINE config #5.  Same G2048Rollout records.
+ * `tensor_cores` = G2048_ROLLOUT_X3 (or _FP32: there is no FFMA variant): the four projections of a block
+ * on tcgen05 with split-fp16 operands (x = hi + lo, three products per k-step, fp32 accumulation in tensor
+ * memory), K / V, attention, norms, SiLUs and the depthwise conv in fp32 on CUDA cores: fp32 grade against the
+ * reference's forward.  G2048_ROLLOUT_BF16: the round-1 kernel with single fp16 operands and fp16 K / V
+ * (log-probs 1e-2 off the fp32 model): a labelled variant.  `loops` = GameURMConfig.num_loops.  Pointer
+ * arrays hold `layers` device pointers:
  * layers.{l}.attn.qkv_proj.weight [192,64], attn.o_proj.weight [64,64], mlp.gate_up_proj.weight
  * [240,64], mlp.dwconv.weight [120,1,2], mlp.dwconv.bias [120], mlp.down_proj.weight [64,120];
- * stem.0.weight [64,3], stem.1.{weight,bias} [64], init_hidden [1,16,64], heads as for the MLP. */
+ * stem.0.weight [64,3], stem.1.{weight,bias} [64], init_hidden [1,16,64], heads as for the MLP.
+ * `packed` (g2048_urm_packed_floats floats, 256-byte aligned) holds both kernels' images. */
 int64_t g2048_urm_packed_floats(int32_t hidden, int32_t layers, int32_t heads, int32_t inter);
 int g2048_urm_pack(int32_t layers, const float* stem_w, const float* stem_ln_w, const float* stem_ln_b,
                    const float* init_hidden, const float* const* qkv_w, const float* const* o_w,
