@@ -17,13 +17,13 @@
 // each block is used by both tiles before its slot is refilled (half the L2 traffic per tile); the issuer alternates between
 // the tiles stage by stage, so that one tile's MMAs run under the other's epilogue.
 // Per tile: 64 KiB of shared memory X that is, in turn, the hi | lo operand of the next projection (two 32 KiB regions) and the
-// fp32 K | V buffer of the attention; 256 TMEM columns = accumulator [0,192) + fp32 residual [192,256).
+// fp32 K | V buffer of the attention; 256 TMEM columns = accumulator [0,240), whose last 64 columns hold the fp32 residual
+// while the attention runs (its accumulator is 192 wide; through the SwiGLU half the residual stays in registers).
 // Stages of one block application (A operand -> accumulator columns):
 //   QKV  hn (R0)            -> q | k | v  [0,192)      then K | V -> X (fp32), attention on CUDA cores, o -> R0
 //   O    o  (R0)            -> [0,64)                  hidden = rms_norm(residual + .)          game.py:1345-1346
-//   GU1  hn (R0), N = 128   -> gate | up of channels 0..63     silu(gate) * up, conv, silu -> R1 (k-blocks 0..3 of D)
-//   GU2  hn (R0), N = 112   -> gate | up of channels 64..119   same -> R0 (k-blocks 4..7 of D)  game.py:1264-1276
-//   D    x  (R1 | R0)       -> [0,64)                  hidden = rms_norm(residual + .)          game.py:1349-1350
+//   GU   hn (R0), N = 240   -> gate | up  [0,240)      silu(gate) * up, conv, silu -> R1 | R0 (k-blocks 0..3 | 4..7 of D)
+//   D    x  (R1 | R0)       -> [0,64)                  hidden = rms_norm(residual + .)          game.py:1264-1276, 1349-1350
 #include <cuda_fp16.h>
 #include "g2048_urm.cuh"
 #include "g2048_tc.cuh"
@@ -35,11 +35,11 @@ namespace x3 {
 constexpr int TILES = 2;
 constexpr int ROW_THREADS = TILES * 128;
 constexpr int XTHREADS = ROW_THREADS + 64;        // + issuer warp, producer warp
-constexpr int RING = 7;
-constexpr uint32_t SLOT = 12288;                  // the largest unit: one QKV k-block (192 rows x 64 B)
+constexpr int RING = 6;
+constexpr uint32_t SLOT = 15360;                  // the largest unit: one gate | up k-block (240 rows x 64 B)
 constexpr uint32_t REGION = 32768;                // one hi | lo operand region of X: [hi: 4 k-blocks x 4096 B | lo: same]
 constexpr uint32_t LO_OFF = 16384;
-constexpr int UNITS = 18;                         // ring units per layer: QKV 4, O 2, GU1 4, GU2 4, D 4
+constexpr int UNITS = 14;                         // ring units per layer: QKV 4, O 2, GU 4, D 4
 constexpr uint32_t T_RES = 192;                   // TMEM column of the fp32 residual inside a tile's 256 columns
 
 struct Smem {
@@ -52,8 +52,8 @@ struct Smem {
 };
 static_assert(sizeof(Smem) + 1024 <= 232448, "URM x3 kernel exceeds the 227 KB shared memory limit");
 
-// size of ring unit u (0..17) of a layer's weight stream
-__device__ __forceinline__ uint32_t unit_bytes(uint32_t u) { return u < 4u ? 12288u : (u >= 10u && u < 14u ? 7168u : 8192u); }
+// size of ring unit u (0..13) of a layer's weight stream
+__device__ __forceinline__ uint32_t unit_bytes(uint32_t u) { return u < 4u ? 12288u : (u >= 6u && u < 10u ? 15360u : 8192u); }
 
 // ---------------------------------------------------------------------------------------------------------------- pack
 __device__ __forceinline__ void put_split(uint8_t* kblock, int rows, int n, int k, float v) {
@@ -67,9 +67,9 @@ __device__ __forceinline__ void put_split(uint8_t* kblock, int rows, int n, int 
 __global__ void pack_x3_kernel(PackSrc s, int L, float* __restrict__ out) {
     float* emb = out + x3_base(L);
     uint8_t* img = reinterpret_cast<uint8_t*>(emb + X3_EMB_FLOATS);
-    // elements per layer: QKV 192 x 64, O 64 x 64, GU1 128 x 64, GU2 112 x 64, D 64 x 128
-    constexpr int E_QKV = QKV * H, E_O = H * H, E_GU1 = 128 * H, E_GU2 = 112 * H, E_D = H * 128;
-    constexpr int E_LAYER = E_QKV + E_O + E_GU1 + E_GU2 + E_D;
+    // elements per layer: QKV 192 x 64, O 64 x 64, GU 240 x 64, D 64 x 128
+    constexpr int E_QKV = QKV * H, E_O = H * H, E_GU = GU * H, E_D = H * 128;
+    constexpr int E_LAYER = E_QKV + E_O + E_GU + E_D;
     const int64_t total = int64_t(16 * SEQ) + int64_t(L) * E_LAYER;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
         if (i < 16 * SEQ) {
@@ -104,16 +104,11 @@ __global__ void pack_x3_kernel(PackSrc s, int L, float* __restrict__ out) {
         } else if ((e -= E_QKV) < E_O) {
             const int n = int(e) / H, k = int(e) % H;
             put_split(base + X3_O + (k >> 4) * (H * 64), H, n, k, s.o[l][n * H + k]);
-        } else if ((e -= E_O) < E_GU1) {
-            const int n = int(e) / H, k = int(e) % H;                      // rows: gate 0..63 | up 0..63
-            const int src = n < 64 ? n : INTER + (n - 64);
-            put_split(base + X3_GU1 + (k >> 4) * (128 * 64), 128, n, k, s.gu[l][src * H + k]);
-        } else if ((e -= E_GU1) < E_GU2) {
-            const int n = int(e) / H, k = int(e) % H;                      // rows: gate 64..119 | up 64..119
-            const int src = n < 56 ? 64 + n : INTER + 64 + (n - 56);
-            put_split(base + X3_GU2 + (k >> 4) * (112 * 64), 112, n, k, s.gu[l][src * H + k]);
+        } else if ((e -= E_O) < E_GU) {
+            const int n = int(e) / H, k = int(e) % H;                      // rows: gate 0..119 | up 0..119
+            put_split(base + X3_GU + (k >> 4) * (GU * 64), GU, n, k, s.gu[l][n * H + k]);
         } else {
-            e -= E_GU2;
+            e -= E_GU;
             const int n = int(e) / 128, k = int(e) % 128;                  // K = 120 -> 128, zero padded
             put_split(base + X3_D + (k >> 4) * (H * 64), H, n, k, k < INTER ? s.down[l][n * INTER + k] : 0.f);
         }
@@ -170,16 +165,22 @@ struct TileSync {
     }
 };
 
-// hidden = rms_norm(residual + accumulator[0,64))   game.py:1223-1229, 1345-1350
+// hidden = rms_norm(residual + accumulator[0,64)); the residual comes from TMEM (TRES) or is h itself   game.py:1223-1229, 1345-1350
+template <bool TRES>
 __device__ __forceinline__ void residual_norm(uint32_t tl, float (&h)[H]) {
     float sq = 0.f;
 #pragma unroll
-    for (int c = 0; c < H; c += 8) {
-        float d[8], r[8];
-        tc::tmem_ld8x2(tl + uint32_t(c), d, tl + T_RES + uint32_t(c), r);
+    for (int c = 0; c < H; c += 16) {
+        float d[16], r[16];
+        if (TRES) {
+            tc::tmem_ld8x2(tl + uint32_t(c), d, tl + T_RES + uint32_t(c), r);
+            tc::tmem_ld8x2(tl + uint32_t(c + 8), d + 8, tl + T_RES + uint32_t(c + 8), r + 8);
+        } else {
+            tc::tmem_ld16p(tl + uint32_t(c), d);
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            h[c + j] = r[j] + d[j];
+        for (int j = 0; j < 16; ++j) {
+            h[c + j] = (TRES ? r[j] : h[c + j]) + d[j];
             sq = fmaf(h[c + j], h[c + j], sq);
         }
     }
@@ -188,15 +189,18 @@ __device__ __forceinline__ void residual_norm(uint32_t tl, float (&h)[H]) {
     for (int n = 0; n < H; ++n) h[n] *= rs;
 }
 
-// the hidden state as the operand of the next projection (R0) and as the fp32 residual (TMEM)
+// the hidden state as the operand of the next projection (R0) and, RES, as the fp32 residual in TMEM
+template <bool RES>
 __device__ __forceinline__ void publish_hidden(uint32_t x_row, uint32_t sw, uint32_t tl, const float (&h)[H]) {
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
         store_kblock(x_row + uint32_t(kb) * 4096u, sw, &h[16 * kb]);
-        tc::tmem_st8(tl + T_RES + uint32_t(16 * kb), &h[16 * kb]);
-        tc::tmem_st8(tl + T_RES + uint32_t(16 * kb + 8), &h[16 * kb + 8]);
+        if (RES) {
+            tc::tmem_st8(tl + T_RES + uint32_t(16 * kb), &h[16 * kb]);
+            tc::tmem_st8(tl + T_RES + uint32_t(16 * kb + 8), &h[16 * kb + 8]);
+        }
     }
-    tc::tmem_st_wait();
+    if (RES) tc::tmem_st_wait();
 }
 
 // silu(gate) * up -> depthwise conv over the tokens (k = 2, pad 1, trimmed: out[t] = w0 x[t-1] + w1 x[t] + b) -> silu, for the 16
@@ -306,8 +310,7 @@ __device__ __forceinline__ void issuer(Smem& S, uint32_t tmem_base, uint32_t sta
     for (uint32_t k = stage_sets * uint32_t(L); k > 0; --k) {
         stage(4, 1, QKV, 0u, 0u);                 // q | k | v
         stage(2, 2, H, 0u, 0u);                   // o projection
-        stage(4, 1, 128, 0u, 0u);                 // gate | up, channels 0..63
-        stage(4, 1, 112, 0u, 0u);                 // gate | up, channels 64..119
+        stage(4, 1, GU, 0u, 0u);                  // gate | up
         stage(4, 2, H, REGION, 0u);               // down projection: k-blocks 0..3 in R1, 4..7 in R0
     }
 }
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                     }
                     for (int l = 0; l < L; ++l) {
                         // ---------------- attention   game.py:1296-1317
-                        publish_hidden(x_row, sw, tl, h);
+                        publish_hidden<true>(x_row, sw, tl, h);
                         ts.signal();
                         ts.wait();                                               // q | k | v in the accumulator
                         // K | V -> shared memory, fp32, chunk-major: chunk c (4 floats) of token m at c * 2048 + slot(m) * 16
@@ -459,29 +462,21 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                         for (int kb = 0; kb < 4; ++kb) store_kblock(x_row + uint32_t(kb) * 4096u, sw, &o[16 * kb]);
                         ts.signal();
                         ts.wait();                                               // o projection in [0,64)
-                        residual_norm(tl, h);
-                        // ---------------- ConvSwiGLU   game.py:1264-1276
-                        publish_hidden(x_row, sw, tl, h);
+                        residual_norm<true>(tl, h);
+                        // ---------------- ConvSwiGLU   game.py:1264-1276   (h stays in registers as the residual)
+                        publish_hidden<false>(x_row, sw, tl, h);
                         ts.signal();
                         const float* cw = &S.conv[l][0][0];
-                        ts.wait();                                               // gate | up of channels 0..63 in [0,128)
+                        ts.wait();                                               // gate | up in [0,240)
 #pragma unroll 1
-                        for (int kb = 0; kb < 4; ++kb) {
+                        for (int kb = 0; kb < 8; ++kb) {
                             float x[16];
-                            swiglu_block(tl, uint32_t(16 * kb), uint32_t(64 + 16 * kb), cw, 16 * kb, cell == 0, 16, x);
-                            store_kblock(x_row + REGION + uint32_t(kb) * 4096u, sw, x);
-                        }
-                        ts.signal();
-                        ts.wait();                                               // gate | up of channels 64..119 in [0,112)
-#pragma unroll 1
-                        for (int kb = 0; kb < 4; ++kb) {
-                            float x[16];
-                            swiglu_block(tl, uint32_t(16 * kb), uint32_t(56 + 16 * kb), cw, 64 + 16 * kb, cell == 0, kb < 3 ? 16 : 8, x);
-                            store_kblock(x_row + uint32_t(kb) * 4096u, sw, x);
+                            swiglu_block(tl, uint32_t(16 * kb), uint32_t(INTER + 16 * kb), cw, 16 * kb, cell == 0, kb < 7 ? 16 : 8, x);
+                            store_kblock(x_row + (kb < 4 ? REGION + uint32_t(kb) * 4096u : uint32_t(kb - 4) * 4096u), sw, x);
                         }
                         ts.signal();
                         ts.wait();                                               // down projection in [0,64)
-                        residual_norm(tl, h);
+                        residual_norm<false>(tl, h);
                     }
                 }
                 // ---- mean-pool over the 16 tokens + heads   game.py:1451-1456

@@ -34,14 +34,12 @@ __host__ __device__ constexpr int64_t total_floats(int L) { return f_total(L) + 
 //               (exponent, cell) pair -- the stem sees nothing else -- computed once at pack time;
 //   weight stream per layer, split-fp16 (w = hi + lo) k-blocks of 16 input features in the 32-byte-swizzled K-major layout of
 //               g2048_tc.cuh, each k-block [hi: N rows x 32 B | lo: N rows x 32 B], in the order the kernel consumes them:
-//               QKV (N = 192, 4 k-blocks), O (N = 64, 4), GU1 = gate | up of channels 0..63 (N = 128, 4), GU2 = gate | up of channels
-//               64..119 (N = 112, 4), D (N = 64, K = 120 -> 128: 8 k-blocks).
+//               QKV (N = 192, 4 k-blocks), O (N = 64, 4), GU = gate | up (N = 240, 4), D (N = 64, K = 120 -> 128: 8 k-blocks).
 constexpr int X3_EMB_FLOATS = 16 * SEQ * H;
 constexpr int X3_QKV = 0;                                    // 4 x 12 288 B
 constexpr int X3_O = X3_QKV + 4 * QKV * 64;                  // 4 x 4 096 B
-constexpr int X3_GU1 = X3_O + 4 * H * 64;                    // 4 x 8 192 B
-constexpr int X3_GU2 = X3_GU1 + 4 * 128 * 64;                // 4 x 7 168 B
-constexpr int X3_D = X3_GU2 + 4 * 112 * 64;                  // 8 x 4 096 B
+constexpr int X3_GU = X3_O + 4 * H * 64;                     // 4 x 15 360 B
+constexpr int X3_D = X3_GU + 4 * GU * 64;                    // 8 x 4 096 B
 constexpr int X3_LAYER = X3_D + 8 * H * 64;                  // 159 744 B
 __host__ __device__ constexpr int64_t x3_base(int L) { return (total_floats(L) + 63) / 64 * 64; }   // floats
 __host__ __device__ constexpr int64_t total_floats_all(int L) { return x3_base(L) + X3_EMB_FLOATS + int64_t(L) * X3_LAYER / 4; }
