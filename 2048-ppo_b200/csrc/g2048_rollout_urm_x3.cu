@@ -47,6 +47,7 @@ struct Smem {
     alignas(1024) uint8_t W[RING][SLOT];
     alignas(16) float conv[MAX_LAYERS][3][128];
     alignas(16) float headw[5 * H + 8];
+    alignas(16) float zeros[128];
     uint64_t ready[TILES], done[TILES], w_full[RING], w_empty[RING];
     uint32_t tmem_base;
 };
@@ -116,9 +117,6 @@ __global__ void pack_x3_kernel(PackSrc s, int L, float* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------- device helpers
-// x * sigmoid(x) with the hardware ex2 / rcp approximations (~1e-6 relative)
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -203,33 +201,42 @@ __device__ __forceinline__ void publish_hidden(uint32_t x_row, uint32_t sw, uint
     if (RES) tc::tmem_st_wait();
 }
 
-// silu(gate) * up -> depthwise conv over the tokens (k = 2, pad 1, trimmed: out[t] = w0 x[t-1] + w1 x[t] + b) -> silu, for the 16
-// channels ch0.. of one k-block of the down projection; gate at accumulator column g0, up at u0.   game.py:1264-1276
-__device__ __forceinline__ void swiglu_block(uint32_t tl, uint32_t g0, uint32_t u0, const float* __restrict__ cw, int ch0, bool first_cell,
-                                             int valid, float* x) {
+// x * sigmoid(x), two at once on packed fp32 math, with the hardware ex2 / rcp approximations (~1e-6 relative)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float2 silu2(float2 x) {
+    const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+    const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+    return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+}
+
+// silu(gate) * up -> depthwise conv over the tokens (k = 2, pad 1, trimmed: out[t] = w0 x[t-1] + w1 x[t] + b) -> silu, for the 8
+// channels ch0.. (gate / up already in registers); `cw0` = the w0 row, or a row of zeros for the first token of an env (no x[t-1]).
+// game.py:1264-1276
+__device__ __forceinline__ void swiglu8(const float* g, const float* u, const float* __restrict__ cw0, const float* __restrict__ cw, int ch0,
+                                        float* x) {
+    const float4* w0 = reinterpret_cast<const float4*>(cw0 + ch0);
+    const float4* w1 = reinterpret_cast<const float4*>(cw + 128 + ch0);
+    const float4* bb = reinterpret_cast<const float4*>(cw + 256 + ch0);
+    const float4 wa = w0[0], wb = w0[1], va = w1[0], vb = w1[1], ba = bb[0], bc = bb[1];
+    const float2 k0[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y), make_float2(wb.z, wb.w)};
+    const float2 k1[4] = {make_float2(va.x, va.y), make_float2(va.z, va.w), make_float2(vb.x, vb.y), make_float2(vb.z, vb.w)};
+    const float2 kb[4] = {make_float2(ba.x, ba.y), make_float2(ba.z, ba.w), make_float2(bc.x, bc.y), make_float2(bc.z, bc.w)};
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        if (8 * hh < valid) {
-            float g[8], u[8];
-            tc::tmem_ld8x2(tl + g0 + uint32_t(8 * hh), g, tl + u0 + uint32_t(8 * hh), u);
-            const float4* w0 = reinterpret_cast<const float4*>(cw + ch0 + 8 * hh);
-            const float4* w1 = reinterpret_cast<const float4*>(cw + 128 + ch0 + 8 * hh);
-            const float4* bb = reinterpret_cast<const float4*>(cw + 256 + ch0 + 8 * hh);
-            const float4 wa = w0[0], wb = w0[1], va = w1[0], vb = w1[1], ba = bb[0], bc = bb[1];
-            const float k0[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-            const float k1[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-            const float kb[8] = {ba.x, ba.y, ba.z, ba.w, bc.x, bc.y, bc.z, bc.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float cur = silu(g[j]) * u[j];
-                float prev = __shfl_up_sync(0xffffffffu, cur, 1);           // token t-1 of the same env
-                prev = first_cell ? 0.f : prev;
-                x[8 * hh + j] = silu(fmaf(k0[j], prev, fmaf(k1[j], cur, kb[j])));
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[8 * hh + j] = 0.f;                // K padding 120..127
-        }
+    for (int j = 0; j < 4; ++j) {
+        const float2 cur = __fmul2_rn(silu2(make_float2(g[2 * j], g[2 * j + 1])), make_float2(u[2 * j], u[2 * j + 1]));
+        const float2 prev = make_float2(__shfl_up_sync(0xffffffffu, cur.x, 1), __shfl_up_sync(0xffffffffu, cur.y, 1));   // token t-1
+        const float2 y = silu2(__ffma2_rn(k0[j], prev, __ffma2_rn(k1[j], cur, kb[j])));
+        x[2 * j] = y.x;
+        x[2 * j + 1] = y.y;
     }
 }
 
@@ -342,6 +349,7 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
     }
     for (int i = tid; i < 5 * H + 8; i += XTHREADS) S.headw[i] = pk[F_HEADW + i];
     for (int i = tid; i < L * F_CONV_STRIDE; i += XTHREADS) (&S.conv[0][0][0])[i] = pk[F_CONV + i];
+    for (int i = tid; i < 128; i += XTHREADS) S.zeros[i] = 0.f;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -417,7 +425,8 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                             tc::tmem_ld16p(tl + uint32_t(hd * HD), q);
                             float2 q2[HD / 2];
 #pragma unroll
-                            for (int d = 0; d < HD / 2; ++d) q2[d] = make_float2(q[2 * d] * 0.25f, q[2 * d + 1] * 0.25f);   // 1/sqrt(head_dim)
+                            for (int d = 0; d < HD / 2; ++d)      // 1/sqrt(head_dim), and log2(e): the softmax below is in base 2
+                                q2[d] = make_float2(q[2 * d] * (0.25f * 1.4426950408889634f), q[2 * d + 1] * (0.25f * 1.4426950408889634f));
                             float sc[SEQ], mx = -INFINITY;
 #pragma unroll
                             for (int s = 0; s < SEQ; ++s) {
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                             float den = 0.f;
 #pragma unroll
                             for (int s = 0; s < SEQ; ++s) {
-                                sc[s] = __expf(sc[s] - mx);
+                                sc[s] = ex2_approx(sc[s] - mx);
                                 den += sc[s];
                             }
                             const float inv = __fdividef(1.0f, den);
@@ -467,12 +476,39 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                         publish_hidden<false>(x_row, sw, tl, h);
                         ts.signal();
                         const float* cw = &S.conv[l][0][0];
+                        const float* cw0 = cell == 0 ? S.zeros : cw;
                         ts.wait();                                               // gate | up in [0,240)
+                        {
+                            // 15 groups of 8 channels; the gate / up columns of the next group are requested before this one is worked on
+                            uint32_t gr[8], ur[8];
+                            tc::tmem_ld8_issue(tl, gr);
+                            tc::tmem_ld8_issue(tl + uint32_t(INTER), ur);
 #pragma unroll 1
-                        for (int kb = 0; kb < 8; ++kb) {
-                            float x[16];
-                            swiglu_block(tl, uint32_t(16 * kb), uint32_t(INTER + 16 * kb), cw, 16 * kb, cell == 0, kb < 7 ? 16 : 8, x);
-                            store_kblock(x_row + (kb < 4 ? REGION + uint32_t(kb) * 4096u : uint32_t(kb - 4) * 4096u), sw, x);
+                            for (int kb = 0; kb < 8; ++kb) {
+                                float x[16];
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int grp = 2 * kb + hh;
+                                    if (grp < INTER / 8) {
+                                        float g[8], u[8];
+                                        tc::tmem_ld_wait_all();
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) {
+                                            g[j] = tc::tmem_ld_pin(gr[j]);
+                                            u[j] = tc::tmem_ld_pin(ur[j]);
+                                        }
+                                        if (grp + 1 < INTER / 8) {
+                                            tc::tmem_ld8_issue(tl + uint32_t(8 * (grp + 1)), gr);
+                                            tc::tmem_ld8_issue(tl + uint32_t(INTER + 8 * (grp + 1)), ur);
+                                        }
+                                        swiglu8(g, u, cw0, cw, 8 * grp, &x[8 * hh]);
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) x[8 * hh + j] = 0.f;                  // K padding 120..127
+                                    }
+                                }
+                                store_kblock(x_row + (kb < 4 ? REGION + uint32_t(kb) * 4096u : uint32_t(kb - 4) * 4096u), sw, x);
+                            }
                         }
                         ts.signal();
                         ts.wait();                                               // down projection in [0,64)

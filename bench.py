@@ -317,14 +317,26 @@ def rollout_section(args, dev, world, rank, barrier):
         ubuf = gro.RolloutBuffers.allocate(args.urm_steps, args.urm_envs, dev)
         ctr = [1]
 
+        prec = ["x3"]
+
         def urm_once():
-            gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=ctr[0], out=ubuf)
+            gro.rollout(upol, ub, args.urm_steps, seed=5, env0=rank * args.urm_envs, ctr0=ctr[0], out=ubuf, precision=prec[0])
             ctr[0] += args.urm_steps
         ums, _ = timed(urm_once, 2)
         ums = max_over_ranks(ums)
+        # projections: 2 * 16 tokens * (64*192 + 64*64 + 64*240 + 120*64) per block application, attention 2 * 2 * 4 heads * 16 * 16 * 16
+        urm_flops = um.config.num_loops * um.config.num_layers * (2 * 16 * (64 * 192 + 64 * 64 + 64 * 240 + 120 * 64) + 4 * 4 * 16 * 16 * 16)
+        rate = world * args.urm_envs * args.urm_steps / (ums * 1e-3)
         out["urm"] = {"workload": f"c5: GameURM (hidden 64, 2 layers, 4 heads, 4 loops) fused rollout, {args.urm_envs} envs x {args.urm_steps} steps per GPU",
-                      "env_steps_per_sec": world * args.urm_envs * args.urm_steps / (ums * 1e-3), "ms": ums,
-                      "kernel": "rollout_urm_kernel (bf16 tcgen05.mma projections, CUDA-core attention)"}
+                      "env_steps_per_sec": rate, "ms": ums, "model_flops_per_env_step": urm_flops,
+                      "model_tflops": rate * urm_flops / 1e12 / world, "mma_tflops": rate * 3 * (urm_flops - um.config.num_loops * um.config.num_layers * 4 * 4 * 16 * 16 * 16) / 1e12 / world,
+                      "kernel": "rollout_urm_x3_kernel (tcgen05.mma projections on split-fp16 operands, three products per k-step; fp32 K/V, attention, "
+                                "norms and SwiGLU on CUDA cores; log-probs / values within 2e-5 of the fp32 model)"}
+        prec[0] = "fp16"
+        vms, _ = timed(urm_once, 2)
+        vms = max_over_ranks(vms)
+        out["urm"]["fp16_variant"] = {"ms": vms, "env_steps_per_sec": world * args.urm_envs * args.urm_steps / (vms * 1e-3), "kernel": "rollout_urm_kernel",
+                                      "note": "single fp16 operands and fp16 K/V: log-probs ~1e-2 off the fp32 model -- NOT reference precision, never selected by default"}
         del ubuf, ub
     return out
 
