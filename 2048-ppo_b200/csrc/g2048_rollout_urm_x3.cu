@@ -22,8 +22,11 @@
 // Stages of one block application (A operand -> accumulator columns):
 //   QKV  hn (R0)            -> q | k | v  [0,192)      then K | V -> X (fp32), attention on CUDA cores, o -> R0
 //   O    o  (R0)            -> [0,64)                  hidden = rms_norm(residual + .)          game.py:1345-1346
-//   GU   hn (R0), N = 240   -> gate | up  [0,240)      silu(gate) * up, conv, silu -> R1 | R0 (k-blocks 0..3 | 4..7 of D)
-//   D    x  (R1 | R0)       -> [0,64)                  hidden = rms_norm(residual + .)          game.py:1264-1276, 1349-1350
+//   G1   hn (R0), N = 128   -> gate | up of channels 0..63 [0,128)      silu(gate) * up, conv, silu -> R1 (k-blocks 0..3 of D)
+//   G2   hn (R0), N = 112   -> gate | up of channels 64..119 [128,240)  same -> R0 (k-blocks 4..7 of D)   game.py:1264-1276
+//   D    x  (R1, then R0)   -> [0,64)                  hidden = rms_norm(residual + .)          game.py:1349-1350
+// G1 and G2 are issued back to back with a completion barrier each, and the down projection starts on k-blocks 0..3 as soon as
+// they are written, so that the second half of the SwiGLU work runs under MMAs of the same tile.
 #include <cuda_fp16.h>
 #include "g2048_urm.cuh"
 #include "g2048_tc.cuh"
@@ -36,11 +39,13 @@ constexpr int TILES = 2;
 constexpr int ROW_THREADS = TILES * 128;
 constexpr int XTHREADS = ROW_THREADS + 64;        // + issuer warp, producer warp
 constexpr int RING = 6;
-constexpr uint32_t SLOT = 15360;                  // the largest unit: one gate | up k-block (240 rows x 64 B)
+constexpr uint32_t SLOT = 15360;                  // the largest unit: one gate | up k-block (G1 128 rows + G2 112 rows, x 64 B)
+constexpr uint32_t G2_OFF = 8192;                 // G2's part of a gate | up unit
 constexpr uint32_t REGION = 32768;                // one hi | lo operand region of X: [hi: 4 k-blocks x 4096 B | lo: same]
 constexpr uint32_t LO_OFF = 16384;
 constexpr int UNITS = 14;                         // ring units per layer: QKV 4, O 2, GU 4, D 4
 constexpr uint32_t T_RES = 192;                   // TMEM column of the fp32 residual inside a tile's 256 columns
+constexpr uint32_t T_G2 = 128;                    // TMEM column of G2's accumulator
 
 struct Smem {
     alignas(1024) uint8_t X[TILES][65536];
@@ -48,7 +53,7 @@ struct Smem {
     alignas(16) float conv[MAX_LAYERS][3][128];
     alignas(16) float headw[5 * H + 8];
     alignas(16) float zeros[128];
-    uint64_t ready[TILES], done[TILES], w_full[RING], w_empty[RING];
+    uint64_t ready[TILES], rdy_d1[TILES], rdy_d2[TILES], done[TILES], done_g1[TILES], done_g2[TILES], w_full[RING], w_empty[RING];
     uint32_t tmem_base;
 };
 static_assert(sizeof(Smem) + 1024 <= 232448, "URM x3 kernel exceeds the 227 KB shared memory limit");
@@ -106,8 +111,12 @@ __global__ void pack_x3_kernel(PackSrc s, int L, float* __restrict__ out) {
             const int n = int(e) / H, k = int(e) % H;
             put_split(base + X3_O + (k >> 4) * (H * 64), H, n, k, s.o[l][n * H + k]);
         } else if ((e -= E_O) < E_GU) {
-            const int n = int(e) / H, k = int(e) % H;                      // rows: gate 0..119 | up 0..119
-            put_split(base + X3_GU + (k >> 4) * (GU * 64), GU, n, k, s.gu[l][n * H + k]);
+            // one 15 360-byte unit per k-block: G1 = gate | up of channels 0..63 (128 rows), then G2 = gate | up of channels 64..119 (112)
+            const int n = int(e) / H, k = int(e) % H;                      // n: gate 0..119 | up 0..119 (the reference's row order)
+            const int ch = n % INTER, up = n / INTER;
+            uint8_t* unit = base + X3_GU + (k >> 4) * (GU * 64);
+            if (ch < 64) put_split(unit, 128, up * 64 + ch, k, s.gu[l][n * H + k]);
+            else put_split(unit + G2_OFF, 112, up * 56 + (ch - 64), k, s.gu[l][n * H + k]);
         } else {
             e -= E_GU;
             const int n = int(e) / 128, k = int(e) % 128;                  // K = 120 -> 128, zero padded
@@ -124,11 +133,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
 }
 
 // 16 consecutive K-elements of this thread's operand row -> hi | lo fp16 terms in one k-block (128 rows x 32 B per part, 32-byte
@@ -150,15 +154,22 @@ struct TileSync {
     uint64_t *ready, *done;
     uint32_t done_par;
     int lane;
-    __device__ __forceinline__ void signal() {
+    __device__ __forceinline__ void signal_on(uint64_t* bar) {
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(ready);
+        if (lane == 0) tc::mbar_arrive(bar);
     }
+    __device__ __forceinline__ void signal() { signal_on(ready); }
     __device__ __forceinline__ void wait() {
         tc::mbar_wait(done, done_par);
         done_par ^= 1u;
+        tc::fence_after_sync();
+    }
+    // a completion barrier with one phase per block application (every waiter waits for every phase)
+    __device__ __forceinline__ void wait_on(uint64_t* bar, uint32_t& par) {
+        tc::mbar_wait(bar, par);
+        par ^= 1u;
         tc::fence_after_sync();
     }
 };
@@ -273,52 +284,125 @@ __device__ __forceinline__ void issuer(Smem& S, uint32_t tmem_base, uint32_t sta
     const uint64_t d0 = tc::make_desc_sw32(0, 16, 256);
     const uint32_t d_hi = uint32_t(d0 >> 32), d_lo0 = uint32_t(d0);
     auto desc = [&](uint32_t saddr) { return uint64_t(d_lo0 | ((saddr >> 4) & 0x3FFFu)) | uint64_t(d_hi) << 32; };
+    // the three products of one k-block: A at ah (hi; lo at + LO_OFF), B at bh (hi; lo at + wpart)
+    auto mma3 = [&](uint32_t d_tmem, uint32_t ah, uint32_t bh, uint32_t wpart, uint32_t idesc, bool acc) {
+        tc::mma_bf16_ss(d_tmem, desc(ah + LO_OFF), desc(bh), idesc, acc);
+        tc::mma_bf16_ss(d_tmem, desc(ah), desc(bh + wpart), idesc, true);
+        tc::mma_bf16_ss(d_tmem, desc(ah), desc(bh), idesc, true);
+    };
     const uint32_t xa[TILES] = {tc::smem_addr(S.X[0]), tc::smem_addr(S.X[1])};
     const uint32_t wa = tc::smem_addr(S.W[0]);
-    uint32_t slot = 0, full_par = 0;
-    uint32_t ready_par[TILES] = {0u, 0u};
-    // one stage for both tiles: `units` ring units of `kpu` k-blocks each, B = N rows; A k-block j of the stage sits at a_off[j]
-    auto stage = [&](int units, int kpu, int N, uint32_t a_first, uint32_t a_second) {
-        const uint32_t idesc = tc::make_idesc_f16(128, N);
-        const uint32_t wpart = uint32_t(N) * 32u;
+    const uint32_t i_qkv = tc::make_idesc_f16(128, QKV), i_h = tc::make_idesc_f16(128, H), i_g1 = tc::make_idesc_f16(128, 128),
+                   i_g2 = tc::make_idesc_f16(128, 112);
+    uint32_t slot = 0, full_par = 0;               // first ring slot of the current stage and the parity of its w_full phase
+    uint32_t ready_par = 0, d1_par = 0, d2_par = 0;  // both tiles' barriers advance together
+    auto next = [&](uint32_t& sl, uint32_t& fp) {
+        if (++sl == uint32_t(RING)) { sl = 0; fp ^= 1u; }
+    };
+    for (uint32_t k = stage_sets * uint32_t(L); k > 0; --k) {
         uint32_t sl = slot, fp = full_par;
+        // ---- q | k | v: 4 units of one k-block
 #pragma unroll
         for (int tile = 0; tile < TILES; ++tile) {
-            tc::mbar_wait(&S.ready[tile], ready_par[tile]);
-            ready_par[tile] ^= 1u;
+            tc::mbar_wait(&S.ready[tile], ready_par);
             tc::fence_after_sync();
-            sl = slot;
-            fp = full_par;
+            sl = slot; fp = full_par;
 #pragma unroll 1
-            for (int u = 0; u < units; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 if (tile == 0) tc::mbar_wait(&S.w_full[sl], fp);      // tile 1 reuses what tile 0 has waited for
                 if (elect_one()) {
-                    const uint32_t d_tmem = tmem_base + uint32_t(tile) * 256u;
-#pragma unroll 1
-                    for (int j = 0; j < kpu; ++j) {
-                        const int kb = u * kpu + j;
-                        const uint32_t ah = xa[tile] + (kb < 4 ? a_first + uint32_t(kb) * 4096u : a_second + uint32_t(kb - 4) * 4096u);
-                        const uint32_t bh = wa + sl * SLOT + uint32_t(j) * 2u * wpart;
-                        tc::mma_bf16_ss(d_tmem, desc(ah + LO_OFF), desc(bh), idesc, kb > 0);
-                        tc::mma_bf16_ss(d_tmem, desc(ah), desc(bh + wpart), idesc, true);
-                        tc::mma_bf16_ss(d_tmem, desc(ah), desc(bh), idesc, true);
-                    }
+                    mma3(tmem_base + uint32_t(tile) * 256u, xa[tile] + uint32_t(u) * 4096u, wa + sl * SLOT, QKV * 32u, i_qkv, u > 0);
                     tc::mma_commit(&S.w_empty[sl]);
                 }
                 __syncwarp();
-                if (++sl == uint32_t(RING)) { sl = 0; fp ^= 1u; }
+                next(sl, fp);
             }
             if (elect_one()) tc::mma_commit(&S.done[tile]);
             __syncwarp();
         }
-        slot = sl;
-        full_par = fp;
-    };
-    for (uint32_t k = stage_sets * uint32_t(L); k > 0; --k) {
-        stage(4, 1, QKV, 0u, 0u);                 // q | k | v
-        stage(2, 2, H, 0u, 0u);                   // o projection
-        stage(4, 1, GU, 0u, 0u);                  // gate | up
-        stage(4, 2, H, REGION, 0u);               // down projection: k-blocks 0..3 in R1, 4..7 in R0
+        slot = sl; full_par = fp;
+        ready_par ^= 1u;
+        // ---- o projection: 2 units of two k-blocks
+#pragma unroll
+        for (int tile = 0; tile < TILES; ++tile) {
+            tc::mbar_wait(&S.ready[tile], ready_par);
+            tc::fence_after_sync();
+            sl = slot; fp = full_par;
+#pragma unroll 1
+            for (int u = 0; u < 2; ++u) {
+                if (tile == 0) tc::mbar_wait(&S.w_full[sl], fp);
+                if (elect_one()) {
+                    mma3(tmem_base + uint32_t(tile) * 256u, xa[tile] + uint32_t(2 * u) * 4096u, wa + sl * SLOT, H * 32u, i_h, u > 0);
+                    mma3(tmem_base + uint32_t(tile) * 256u, xa[tile] + uint32_t(2 * u + 1) * 4096u, wa + sl * SLOT + H * 64u, H * 32u, i_h, true);
+                    tc::mma_commit(&S.w_empty[sl]);
+                }
+                __syncwarp();
+                next(sl, fp);
+            }
+            if (elect_one()) tc::mma_commit(&S.done[tile]);
+            __syncwarp();
+        }
+        slot = sl; full_par = fp;
+        ready_par ^= 1u;
+        // ---- gate | up: 4 units [G1 | G2] of one k-block; all of G1 first (its own completion barrier), then G2
+#pragma unroll
+        for (int tile = 0; tile < TILES; ++tile) {
+            tc::mbar_wait(&S.ready[tile], ready_par);
+            tc::fence_after_sync();
+            sl = slot; fp = full_par;
+#pragma unroll 1
+            for (int u = 0; u < 4; ++u) {
+                if (tile == 0) tc::mbar_wait(&S.w_full[sl], fp);
+                if (elect_one()) mma3(tmem_base + uint32_t(tile) * 256u, xa[tile] + uint32_t(u) * 4096u, wa + sl * SLOT, 128u * 32u, i_g1, u > 0);
+                __syncwarp();
+                next(sl, fp);
+            }
+            if (elect_one()) tc::mma_commit(&S.done_g1[tile]);
+            __syncwarp();
+            sl = slot; fp = full_par;
+#pragma unroll 1
+            for (int u = 0; u < 4; ++u) {
+                if (elect_one()) {
+                    mma3(tmem_base + uint32_t(tile) * 256u + T_G2, xa[tile] + uint32_t(u) * 4096u, wa + sl * SLOT + G2_OFF, 112u * 32u, i_g2, u > 0);
+                    tc::mma_commit(&S.w_empty[sl]);
+                }
+                __syncwarp();
+                next(sl, fp);
+            }
+            if (elect_one()) tc::mma_commit(&S.done_g2[tile]);
+            __syncwarp();
+        }
+        slot = sl; full_par = fp;
+        ready_par ^= 1u;
+        // ---- down projection: 4 units of two k-blocks; k-blocks 0..3 (R1) once half 0 has written them, 4..7 (R0) after half 1
+#pragma unroll
+        for (int tile = 0; tile < TILES; ++tile) {
+            sl = slot; fp = full_par;
+#pragma unroll 1
+            for (int u = 0; u < 4; ++u) {
+                if (u == 0) {
+                    tc::mbar_wait(&S.rdy_d1[tile], d1_par);
+                    tc::fence_after_sync();
+                } else if (u == 2) {
+                    tc::mbar_wait(&S.rdy_d2[tile], d2_par);
+                    tc::fence_after_sync();
+                }
+                if (tile == 0) tc::mbar_wait(&S.w_full[sl], fp);
+                if (elect_one()) {
+                    const uint32_t a0 = xa[tile] + (u < 2 ? REGION + uint32_t(2 * u) * 4096u : uint32_t(2 * u - 4) * 4096u);
+                    mma3(tmem_base + uint32_t(tile) * 256u, a0, wa + sl * SLOT, H * 32u, i_h, u > 0);
+                    mma3(tmem_base + uint32_t(tile) * 256u, a0 + 4096u, wa + sl * SLOT + H * 64u, H * 32u, i_h, true);
+                    tc::mma_commit(&S.w_empty[sl]);
+                }
+                __syncwarp();
+                next(sl, fp);
+            }
+            if (elect_one()) tc::mma_commit(&S.done[tile]);
+            __syncwarp();
+        }
+        slot = sl; full_par = fp;
+        d1_par ^= 1u;
+        d2_par ^= 1u;
     }
 }
 
@@ -339,7 +423,11 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
     if (tid == 0) {
         for (int t = 0; t < TILES; ++t) {
             tc::mbar_init(&S.ready[t], 4);
+            tc::mbar_init(&S.rdy_d1[t], 4);
+            tc::mbar_init(&S.rdy_d2[t], 4);
             tc::mbar_init(&S.done[t], 1);
+            tc::mbar_init(&S.done_g1[t], 1);
+            tc::mbar_init(&S.done_g2[t], 1);
         }
         for (int s = 0; s < RING; ++s) {
             tc::mbar_init(&S.w_full[s], 1);
@@ -365,10 +453,12 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
         const uint32_t xb = tc::smem_addr(S.X[tile]);
         const uint32_t x_row = xb + uint32_t(row) * 32u, sw = uint32_t(row >> 2) & 1u;
         const uint32_t kv_slot = xb + (uint32_t(row) ^ (uint32_t(row >> 4) & 1u)) * 16u;     // this token's 16-byte slot of a K | V chunk
-        const uint32_t kv_env = xb + uint32_t(row & ~15) * 16u;                              // the 16 slots of this env
+        // the 16 slots of this env; plain loads (not asm) so that the compiler can request a head's K or V rows well ahead of their use
+        const float4* const kv_env = reinterpret_cast<const float4*>(S.X[tile]) + (row & ~15);
         const int bar_id = 1 + tile;
         const LutGlobal lut{p.lut};
         TileSync ts{&S.ready[tile], &S.done[tile], 0u, lane};
+        uint32_t g1_par = 0, g2_par = 0;
         for (int64_t pr = 0; pr < my_pairs; ++pr) {
             const int64_t env = ((int64_t(blockIdx.x) + pr * gridDim.x) * TILES + tile) * 8 + (row >> 4);
             const bool owner = env < p.B && cell == 0;              // the env's leader thread owns the board
@@ -433,7 +523,7 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                                 float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
-                                    const float4 kk = lds128(kv_env + uint32_t(hd * 4 + c) * 2048u + uint32_t(s) * 16u);
+                                    const float4 kk = kv_env[(hd * 4 + c) * 128 + s];
                                     acc = __ffma2_rn(q2[2 * c], make_float2(kk.x, kk.y), acc);
                                     acc = __ffma2_rn(q2[2 * c + 1], make_float2(kk.z, kk.w), acc);
                                 }
@@ -455,7 +545,7 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                                 const float2 pj = make_float2(sc[s], sc[s]);
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
-                                    const float4 vv = lds128(kv_env + uint32_t(16 + hd * 4 + c) * 2048u + uint32_t(s) * 16u);
+                                    const float4 vv = kv_env[(16 + hd * 4 + c) * 128 + s];
                                     o2[2 * c] = __ffma2_rn(pj, make_float2(vv.x, vv.y), o2[2 * c]);
                                     o2[2 * c + 1] = __ffma2_rn(pj, make_float2(vv.z, vv.w), o2[2 * c + 1]);
                                 }
@@ -477,19 +567,24 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                         ts.signal();
                         const float* cw = &S.conv[l][0][0];
                         const float* cw0 = cell == 0 ? S.zeros : cw;
-                        ts.wait();                                               // gate | up in [0,240)
-                        {
-                            // 15 groups of 8 channels; the gate / up columns of the next group are requested before this one is worked on
-                            uint32_t gr[8], ur[8];
-                            tc::tmem_ld8_issue(tl, gr);
-                            tc::tmem_ld8_issue(tl + uint32_t(INTER), ur);
+                        // channels 0..63 (G1, [0,128)) -> R1, then channels 64..119 (G2, [128,240)) -> R0; 8 channels at a time, the
+                        // gate / up columns of the next group requested before this one is worked on
 #pragma unroll 1
-                            for (int kb = 0; kb < 8; ++kb) {
+                        for (int part = 0; part < 2; ++part) {
+                            ts.wait_on(part == 0 ? &S.done_g1[tile] : &S.done_g2[tile], part == 0 ? g1_par : g2_par);
+                            const int ngrp = part == 0 ? 8 : 7, ch_base = 64 * part;
+                            const uint32_t g_col = part == 0 ? 0u : T_G2, u_col = part == 0 ? 64u : T_G2 + 56u;
+                            const uint32_t x_out = x_row + (part == 0 ? REGION : 0u);
+                            uint32_t gr[8], ur[8];
+                            tc::tmem_ld8_issue(tl + g_col, gr);
+                            tc::tmem_ld8_issue(tl + u_col, ur);
+#pragma unroll 1
+                            for (int kb = 0; kb < 4; ++kb) {
                                 float x[16];
 #pragma unroll
                                 for (int hh = 0; hh < 2; ++hh) {
                                     const int grp = 2 * kb + hh;
-                                    if (grp < INTER / 8) {
+                                    if (grp < ngrp) {
                                         float g[8], u[8];
                                         tc::tmem_ld_wait_all();
 #pragma unroll
@@ -497,20 +592,20 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                                             g[j] = tc::tmem_ld_pin(gr[j]);
                                             u[j] = tc::tmem_ld_pin(ur[j]);
                                         }
-                                        if (grp + 1 < INTER / 8) {
-                                            tc::tmem_ld8_issue(tl + uint32_t(8 * (grp + 1)), gr);
-                                            tc::tmem_ld8_issue(tl + uint32_t(INTER + 8 * (grp + 1)), ur);
+                                        if (grp + 1 < ngrp) {
+                                            tc::tmem_ld8_issue(tl + g_col + uint32_t(8 * (grp + 1)), gr);
+                                            tc::tmem_ld8_issue(tl + u_col + uint32_t(8 * (grp + 1)), ur);
                                         }
-                                        swiglu8(g, u, cw0, cw, 8 * grp, &x[8 * hh]);
+                                        swiglu8(g, u, cw0, cw, ch_base + 8 * grp, &x[8 * hh]);
                                     } else {
 #pragma unroll
                                         for (int j = 0; j < 8; ++j) x[8 * hh + j] = 0.f;                  // K padding 120..127
                                     }
                                 }
-                                store_kblock(x_row + (kb < 4 ? REGION + uint32_t(kb) * 4096u : uint32_t(kb - 4) * 4096u), sw, x);
+                                store_kblock(x_out + uint32_t(kb) * 4096u, sw, x);
                             }
+                            ts.signal_on(part == 0 ? &S.rdy_d1[tile] : &S.rdy_d2[tile]);
                         }
-                        ts.signal();
                         ts.wait();                                               // down projection in [0,64)
                         residual_norm<false>(tl, h);
                     }

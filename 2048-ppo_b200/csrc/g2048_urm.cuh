@@ -34,7 +34,8 @@ __host__ __device__ constexpr int64_t total_floats(int L) { return f_total(L) + 
 //               (exponent, cell) pair -- the stem sees nothing else -- computed once at pack time;
 //   weight stream per layer, split-fp16 (w = hi + lo) k-blocks of 16 input features in the 32-byte-swizzled K-major layout of
 //               g2048_tc.cuh, each k-block [hi: N rows x 32 B | lo: N rows x 32 B], in the order the kernel consumes them:
-//               QKV (N = 192, 4 k-blocks), O (N = 64, 4), GU = gate | up (N = 240, 4), D (N = 64, K = 120 -> 128: 8 k-blocks).
+//               QKV (N = 192, 4 k-blocks), O (N = 64, 4), GU (4 k-blocks, each [G1 = gate | up of channels 0..63, 128 rows][G2 = gate | up
+//               of channels 64..119, 112 rows]), D (N = 64, K = 120 -> 128: 8 k-blocks).
 constexpr int X3_EMB_FLOATS = 16 * SEQ * H;
 constexpr int X3_QKV = 0;                                    // 4 x 12 288 B
 constexpr int X3_O = X3_QKV + 4 * QKV * 64;                  // 4 x 4 096 B
