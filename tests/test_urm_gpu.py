@@ -91,7 +91,7 @@ def test_urm_rollout_first_step_matches_reference_fixture(golden, precision):
 
 
 @pytest.mark.parametrize("precision", ["x3", "fp16"])
-@pytest.mark.parametrize("B,T,layers", [(100, 6, 2), (8, 3, 1), (1000, 2, 2), (2500, 3, 2)])
+@pytest.mark.parametrize("B,T,layers", [(100, 6, 2), (8, 3, 1), (1000, 2, 2), (2500, 3, 2), (20004, 2, 2)])
 def test_urm_rollout_env_path_bit_exact(B, T, layers, precision):
     from g2048 import env, policy, rollout
     torch.manual_seed(B)
