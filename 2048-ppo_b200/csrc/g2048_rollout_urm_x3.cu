@@ -223,10 +223,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// (one rcp for the pair: 1/a = b / (ab), 1/b = a / (ab); the exponents are capped so that a and b stay finite -- a product that
+// overflows then gives sigmoid = 0 * finite = 0, which is what it rounds to -- the SwiGLU phase is bound by the XU pipe)
 __device__ __forceinline__ float2 silu2(float2 x) {
     const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-    const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
-    return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+    const float2 d = __fadd2_rn(make_float2(ex2_approx(fminf(t.x, 126.0f)), ex2_approx(fminf(t.y, 126.0f))), make_float2(1.0f, 1.0f));
+    const float r = rcp_approx(d.x * d.y);
+    return __fmul2_rn(x, __fmul2_rn(make_float2(r, r), make_float2(d.y, d.x)));
 }
 
 // silu(gate) * up -> depthwise conv over the tokens (k = 2, pad 1, trimmed: out[t] = w0 x[t-1] + w1 x[t] + b) -> silu, for the 8
@@ -508,57 +511,85 @@ __global__ void __launch_bounds__(XTHREADS, 1) rollout_urm_x3_kernel(RolloutPara
                                        __float_as_uint(kv[4 * q + 2]), __float_as_uint(kv[4 * q + 3]));
                         }
                         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                        float o[H];
+                        // Every 128-bit K / V load serves the two envs of the warp only: the attention is bound by shared-memory
+                        // wavefronts.  So a thread works on TWO queries per K / V row -- its own token's and its lane neighbour's
+                        // (lane ^ 1, same env) -- for two of the four heads (even lanes heads 0, 1; odd lanes heads 2, 3): half the
+                        // loads, the queries of the other two heads and the finished outputs cross by shuffles.
+                        const int odd = lane & 1;
+                        float om[2 * HD], ox[2 * HD];                             // outputs of my two heads: my token, the neighbour's
 #pragma unroll
-                        for (int hd = 0; hd < NHEAD; ++hd) {
-                            float q[HD];
-                            tc::tmem_ld16p(tl + uint32_t(hd * HD), q);
-                            float2 q2[HD / 2];
+                        for (int j = 0; j < 2; ++j) {
+                            const int hd = 2 * odd + j;                           // my head; 2 * (1 - odd) + j goes to the neighbour
+                            float qlo[HD], qhi[HD];                               // (TMEM addresses are warp-uniform: both heads, then select)
+                            tc::tmem_ld16p(tl + uint32_t(j * HD), qlo);
+                            tc::tmem_ld16p(tl + uint32_t((2 + j) * HD), qhi);
+                            float2 qa[HD / 2], qb[HD / 2];                        // my token's query, the neighbour's
 #pragma unroll
-                            for (int d = 0; d < HD / 2; ++d)      // 1/sqrt(head_dim), and log2(e): the softmax below is in base 2
-                                q2[d] = make_float2(q[2 * d] * (0.25f * 1.4426950408889634f), q[2 * d + 1] * (0.25f * 1.4426950408889634f));
-                            float sc[SEQ], mx = -INFINITY;
+                            for (int d = 0; d < HD / 2; ++d) {    // 1/sqrt(head_dim), and log2(e): the softmax below is in base 2
+                                const float sc0 = 0.25f * 1.4426950408889634f;
+                                const float m0 = odd ? qhi[2 * d] : qlo[2 * d], m1 = odd ? qhi[2 * d + 1] : qlo[2 * d + 1];
+                                const float s0 = odd ? qlo[2 * d] : qhi[2 * d], s1 = odd ? qlo[2 * d + 1] : qhi[2 * d + 1];
+                                qa[d] = make_float2(m0 * sc0, m1 * sc0);
+                                qb[d] = make_float2(__shfl_xor_sync(0xffffffffu, s0, 1) * sc0, __shfl_xor_sync(0xffffffffu, s1, 1) * sc0);
+                            }
+                            const float4* const kp = kv_env + hd * 4 * 128;
+                            float sa[SEQ], sb[SEQ], mxa = -INFINITY, mxb = -INFINITY;
 #pragma unroll
-                            for (int s = 0; s < SEQ; ++s) {
-                                float2 acc = make_float2(0.f, 0.f);
+                            for (int s2 = 0; s2 < SEQ; ++s2) {
+                                float2 aa = make_float2(0.f, 0.f), ab = make_float2(0.f, 0.f);
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
-                                    const float4 kk = kv_env[(hd * 4 + c) * 128 + s];
-                                    acc = __ffma2_rn(q2[2 * c], make_float2(kk.x, kk.y), acc);
-                                    acc = __ffma2_rn(q2[2 * c + 1], make_float2(kk.z, kk.w), acc);
+                                    const float4 kk = kp[c * 128 + s2];
+                                    aa = __ffma2_rn(qa[2 * c], make_float2(kk.x, kk.y), aa);
+                                    aa = __ffma2_rn(qa[2 * c + 1], make_float2(kk.z, kk.w), aa);
+                                    ab = __ffma2_rn(qb[2 * c], make_float2(kk.x, kk.y), ab);
+                                    ab = __ffma2_rn(qb[2 * c + 1], make_float2(kk.z, kk.w), ab);
                                 }
-                                sc[s] = acc.x + acc.y;
-                                mx = fmaxf(mx, sc[s]);
+                                sa[s2] = aa.x + aa.y;
+                                sb[s2] = ab.x + ab.y;
+                                mxa = fmaxf(mxa, sa[s2]);
+                                mxb = fmaxf(mxb, sb[s2]);
                             }
-                            float den = 0.f;
+                            float dena = 0.f, denb = 0.f;
 #pragma unroll
-                            for (int s = 0; s < SEQ; ++s) {
-                                sc[s] = ex2_approx(sc[s] - mx);
-                                den += sc[s];
+                            for (int s2 = 0; s2 < SEQ; ++s2) {
+                                sa[s2] = ex2_approx(sa[s2] - mxa);
+                                sb[s2] = ex2_approx(sb[s2] - mxb);
+                                dena += sa[s2];
+                                denb += sb[s2];
                             }
-                            const float inv = __fdividef(1.0f, den);
-                            float2 o2[HD / 2];
+                            const float inva = __fdividef(1.0f, dena), invb = __fdividef(1.0f, denb);
+                            float2 oa[HD / 2], ob[HD / 2];
 #pragma unroll
-                            for (int d = 0; d < HD / 2; ++d) o2[d] = make_float2(0.f, 0.f);
+                            for (int d = 0; d < HD / 2; ++d) oa[d] = ob[d] = make_float2(0.f, 0.f);
 #pragma unroll
-                            for (int s = 0; s < SEQ; ++s) {
-                                const float2 pj = make_float2(sc[s], sc[s]);
+                            for (int s2 = 0; s2 < SEQ; ++s2) {
+                                const float2 pa = make_float2(sa[s2], sa[s2]), pb = make_float2(sb[s2], sb[s2]);
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
-                                    const float4 vv = kv_env[(16 + hd * 4 + c) * 128 + s];
-                                    o2[2 * c] = __ffma2_rn(pj, make_float2(vv.x, vv.y), o2[2 * c]);
-                                    o2[2 * c + 1] = __ffma2_rn(pj, make_float2(vv.z, vv.w), o2[2 * c + 1]);
+                                    const float4 vv = kp[(16 * 128) + c * 128 + s2];
+                                    oa[2 * c] = __ffma2_rn(pa, make_float2(vv.x, vv.y), oa[2 * c]);
+                                    oa[2 * c + 1] = __ffma2_rn(pa, make_float2(vv.z, vv.w), oa[2 * c + 1]);
+                                    ob[2 * c] = __ffma2_rn(pb, make_float2(vv.x, vv.y), ob[2 * c]);
+                                    ob[2 * c + 1] = __ffma2_rn(pb, make_float2(vv.z, vv.w), ob[2 * c + 1]);
                                 }
                             }
 #pragma unroll
                             for (int d = 0; d < HD / 2; ++d) {
-                                o[hd * HD + 2 * d] = o2[d].x * inv;
-                                o[hd * HD + 2 * d + 1] = o2[d].y * inv;
+                                om[j * HD + 2 * d] = oa[d].x * inva;
+                                om[j * HD + 2 * d + 1] = oa[d].y * inva;
+                                ox[j * HD + 2 * d] = ob[d].x * invb;
+                                ox[j * HD + 2 * d + 1] = ob[d].y * invb;
                             }
                         }
+#pragma unroll
+                        for (int d = 0; d < 2 * HD; ++d) ox[d] = __shfl_xor_sync(0xffffffffu, ox[d], 1);   // now: my token, the other two heads
                         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // every token of the tile has read K | V
 #pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) store_kblock(x_row + uint32_t(kb) * 4096u, sw, &o[16 * kb]);
+                        for (int j = 0; j < 2; ++j) {                                     // k-block = head
+                            store_kblock(x_row + uint32_t(2 * odd + j) * 4096u, sw, &om[16 * j]);
+                            store_kblock(x_row + uint32_t(2 * (1 - odd) + j) * 4096u, sw, &ox[16 * j]);
+                        }
                         ts.signal();
                         ts.wait();                                               // o projection in [0,64)
                         residual_norm<true>(tl, h);
