@@ -45,9 +45,9 @@ WORKLOAD = ("c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step tra
             "(move+merge points+shaping+Philox spawn+legal/done)")
 
 
-def python_reference(seconds: float = 2.0):
-    """BASELINE.md section 3 B1-B3 on the UNMODIFIED Python reference staged under baseline/_ref (own process: its worker
-    pool must not fork a CUDA context).  None when the reference is not staged."""
+def python_reference(seconds: float = 2.0, train_steps: int = 12):
+    """BASELINE.md section 3 B1-B5 on the UNMODIFIED Python reference staged under baseline/_ref (own process: its worker
+    pool must not fork a CUDA context; B5 = `train_steps` steps of the config #1 command on CPU).  None when the reference is not staged."""
     import subprocess
     script = os.path.join(ROOT, "baseline", "time_reference.py")
     if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "game.py")):
@@ -56,7 +56,8 @@ def python_reference(seconds: float = 2.0):
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):     # torchrun exports OMP_NUM_THREADS=1
         env.pop(k, None)
     try:
-        out = subprocess.run([sys.executable, script, "--seconds", str(seconds)], capture_output=True, text=True, timeout=240, env=env)
+        out = subprocess.run([sys.executable, script, "--seconds", str(seconds), "--train-steps", str(train_steps)], capture_output=True,
+                             text=True, timeout=420, env=env)
         return json.loads(out.stdout.strip().splitlines()[-1])
     except Exception as e:          # a baseline that cannot run is reported, not fatal
         return {"unavailable": f"{type(e).__name__}: {e}"}
