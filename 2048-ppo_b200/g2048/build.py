@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "csrc")
 LIB = os.environ.get("G2048_LIB", os.path.join(HERE, "libg2048.so"))
-SOURCES = ["g2048_host.cu", "g2048_env.cu", "g2048_train.cu", "g2048_rollout.cu", "g2048_rollout_tc.cu", "g2048_rollout_x3.cu", "g2048_rollout_urm.cu", "g2048_rollout_urm_x3.cu", "g2048_tc.cu",
+SOURCES = ["g2048_host.cu", "g2048_env.cu", "g2048_train.cu", "g2048_rollout.cu", "g2048_rollout_tc.cu", "g2048_rollout_x3.cu", "g2048_rollout_urm.cu", "g2048_rollout_urm_x3.cu", "g2048_urm_train.cu", "g2048_tc.cu",
            "g2048_update.cu", "g2048_linear.cu", "g2048_update_x3.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import dp, env, fused, ppo, rollout, update
+from . import dp, env, fused, ppo, rollout, update, urm_ops
 from .policy import GameMLP, GameURM, GameURMConfig, MLPConfig
 
 
@@ -24,6 +24,9 @@ class TrainConfig:
                                    # no_grad as in game.py:1400-1413) with the fused PPO-loss kernel -- SURVEY 8(f) N4, host half
     urm: GameURMConfig = field(default_factory=lambda: GameURMConfig(dropout=0.0))
     urm_chunk: int = 1 << 15       # samples per autograd chunk of the URM update (~0.4 MB of saved activations per sample)
+    urm_update: str = "ops"        # "ops": every block op of the URM update on this library's kernels, forward and backward
+                                   # (g2048/urm_ops.py: tcgen05 projections + hand-written attention / ConvSwiGLU / norm kernels);
+                                   # "autograd": the torch mirror's own forward (ATen / cuBLAS) -- the comparator of the tests
     hidden_dim: int = 196
     num_layers: int = 2
     envs: int = 65536              # global env count (sharded over ranks)
@@ -115,6 +118,8 @@ class Trainer:
         self.rank, self.world = dp.world()
         self.lo, self.hi = dp.shard_range(cfg.envs, self.rank, self.world)
         torch.manual_seed(cfg.seed)   # identical initial weights on every rank
+        if cfg.urm_update not in ("ops", "autograd"):
+            raise ValueError(f"urm_update must be 'ops' or 'autograd', got {cfg.urm_update!r}")
         if cfg.model_type not in ("mlp", "urm"):
             raise ValueError(f"model_type must be 'mlp' or 'urm', got {cfg.model_type!r}")
         if model is not None:
@@ -224,6 +229,8 @@ class Trainer:
                     if self.is_mlp:
                         logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
                                                       matmul="x3" if c.update_matmul in ("x3", "fused") else "cublas")
+                    elif c.urm_update == "ops":
+                        logits, v = urm_ops.forward(self.model, env.encode(boards[sl]))
                     else:
                         logits, v = self.model(env.encode(boards[sl]))
                     loss, stats = ppo.ppo_loss(logits, v, logp[sl], actions[sl], legal[sl], a[sl], g[sl], flags=flags[sl],

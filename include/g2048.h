@@ -240,6 +240,27 @@ int g2048_urm_pack(int32_t layers, const float* stem_w, const float* stem_ln_w, 
                    const float* value_b, float* packed, void* stream);
 int g2048_rollout_urm(const G2048Rollout* params, int32_t loops, void* stream);
 
+/* ---- GameURM update: the block ops that are not projections, forward and hand-written backward ----------
+ * Replaces, inside a GameURM update step, torch's scaled_dot_product_attention (game.py:1296-1317), the inner chain of
+ * GameConvSwiGLU (silu(gate) * up -> depthwise Conv1d(kernel 2, padding 1, trimmed) -> silu, game.py:1264-1276) and
+ * rms_norm(hidden + branch) (game.py:1223-1229, 1345-1350) with their autograd backward; the projections run on
+ * g2048_x3_gemm / g2048_x3_wgrad.  Default GameURMConfig shapes only: 16 tokens, 4 heads x head_dim 16, hidden 64, inter 120.
+ * All tensors row-major fp32 device memory; B = boards (envs), rows = B * 16 tokens.
+ *   attention  qkv [B,16,192] = per token [q | k | v], head h at columns 16h..16h+15 of each third; out / dout [B,16,64]
+ *   swiglu     gate, up, y, dy, dgate, dup [B,16,120]; conv_w [120,2] (= dwconv.weight [120,1,2]), conv_b [120];
+ *              dconv_w / dconv_b are overwritten with the batch sums (fixed-order reduction); workspace of
+ *              g2048_urm_swiglu_workspace_floats() floats
+ *   norm       y = s * rsqrt(mean(s^2) + eps), s = x + r, rows of 64; rs [rows] keeps the row factor for the backward, which
+ *              returns ds (the gradient of both x and r) from y, rs and dy */
+int g2048_urm_attn_fwd(const float* qkv, float* out, int64_t B, void* stream);
+int g2048_urm_attn_bwd(const float* qkv, const float* dout, float* dqkv, int64_t B, void* stream);
+int g2048_urm_swiglu_fwd(const float* gate, const float* up, const float* conv_w, const float* conv_b, float* y, int64_t B, void* stream);
+int64_t g2048_urm_swiglu_workspace_floats(void);
+int g2048_urm_swiglu_bwd(const float* gate, const float* up, const float* conv_w, const float* conv_b, const float* dy, float* dgate,
+                         float* dup, float* dconv_w, float* dconv_b, float* workspace, int64_t B, void* stream);
+int g2048_urm_norm_fwd(const float* x, const float* r, float* y, float* rs, int64_t rows, float eps, void* stream);
+int g2048_urm_norm_bwd(const float* y, const float* rs, const float* dy, float* ds, int64_t rows, void* stream);
+
 /* ---- policy update: fused y = res + ReLU(LayerNorm(z)) and its backward ---------------------
  * The elementwise chain of a GameMLP block (game.py:1038-1046; stem: game.py:1069-1073, res = NULL)
  * in eval/p=0 dropout form.  Row-major [n,h] fp32, h a multiple of 4 up to 256, eps = 1e-5 in the
