@@ -174,6 +174,9 @@ class Trainer:
                 self.model.eval()
                 if self.is_mlp and update.supported(self.model):
                     _, v = update.forward(self.model, self.boards)
+                elif not self.is_mlp and c.urm_update == "ops" and urm_ops.supported(self.model):
+                    v = torch.cat([urm_ops.forward(self.model, env.encode(self.boards[i:i + c.urm_chunk]))[1]
+                                   for i in range(0, self.boards.numel(), c.urm_chunk)])
                 else:
                     _, v = self.model(env.encode(self.boards))
                 boot = v.reshape(-1).float() * (sd + 1e-8) + mu_c        # the critic predicts the NORMALISED return (train.py:760-772)

@@ -339,6 +339,24 @@ def rollout_section(args, dev, world, rank, barrier):
         out["urm"]["fp16_variant"] = {"ms": vms, "env_steps_per_sec": world * args.urm_envs * args.urm_steps / (vms * 1e-3), "kernel": "rollout_urm_kernel",
                                       "note": "single fp16 operands and fp16 K/V: log-probs ~1e-2 off the fp32 model -- NOT reference precision, never selected by default"}
         del ubuf, ub
+        # GameURM train step: fused rollout + advantage + update on this library's kernels (g2048/urm_ops.py),
+        # with the torch mirror's own forward / backward (ATen + cuBLAS) timed beside it
+        if args.urm_train_envs > 0:
+            utr = {}
+            for mode in ("ops", "autograd"):
+                ucfg = tr.TrainConfig(model_type="urm", envs=args.urm_train_envs * world, horizon=args.urm_train_steps, zero_heads=False,
+                                      warmup_steps=0, seed=5, urm_update=mode)
+                ut = tr.Trainer(ucfg, dev)
+                ms, _ = timed(ut.train_step, 2 if mode == "ops" else 1)
+                ms = max_over_ranks(ms)
+                utr[mode] = {"train_step_ms": ms, "update_ms_rank0": ut.times.update_ms, "rollout_ms_rank0": ut.times.rollout_ms,
+                             "rollout_update_steps_per_sec": world * args.urm_train_envs * args.urm_train_steps / (ms * 1e-3)}
+                del ut
+            out["urm"]["train_step"] = {
+                "workload": f"GameURM rollout + advantage + update, {args.urm_train_envs} envs x {args.urm_train_steps} steps per GPU, Muon+AdamW",
+                "update": "projections on x3_gemm_kernel / x3_wgrad_kernel (tcgen05), attention / ConvSwiGLU / RMS-norm forward and backward on "
+                          "g2048_urm_train.cu kernels; torch autograd only as the tape",
+                **utr["ops"], "aten_autograd_variant": utr["autograd"]}
     return out
 
 
@@ -630,6 +648,8 @@ def main():
     ap.add_argument("--update-variants", action="store_true", help="also time the autograd update variants (cuBLAS fp32 / TF32, x3 GEMMs)")
     ap.add_argument("--urm-envs", type=int, default=262144, help="config #5 env count per GPU (0 = skip)")
     ap.add_argument("--urm-steps", type=int, default=64)
+    ap.add_argument("--urm-train-envs", type=int, default=65536, help="GameURM train step: envs per GPU (0 = skip)")
+    ap.add_argument("--urm-train-steps", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
