@@ -15,7 +15,8 @@ namespace urmt {
 
 constexpr int SEQ = 16, NHEAD = 4, HD = 16, H = 64, INTER = 120;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// hardware ex2 / rcp approximations (~1e-6 relative): the IEEE divide and expf were most of the ConvSwiGLU kernels' instructions
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
 // d silu(x) / dx = s (1 + x (1 - s)), s = sigmoid(x)
 __device__ __forceinline__ float dsiluf_(float x) {
@@ -215,19 +216,22 @@ __global__ void __launch_bounds__(SW_THREADS) swiglu_bwd_kernel(const float* __r
 }
 
 // fixed-order sum of the per-block partials into dcw [120, 2], dcb [120]
+// (block k = which sum; four independent accumulators keep loads in flight, combined in a fixed order)
 __global__ void conv_reduce_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ dcw, float* __restrict__ dcb) {
-    const int c = threadIdx.x;
+    const int c = threadIdx.x, k = blockIdx.x;
     if (c >= INTER) return;
-    float a0 = 0.f, a1 = 0.f, ab = 0.f;
-    for (int i = 0; i < nblocks; ++i) {
-        const float* pp = partials + size_t(i) * 3 * SW_THREADS;
-        a0 += pp[c];
-        a1 += pp[SW_THREADS + c];
-        ab += pp[2 * SW_THREADS + c];
+    const float* pp = partials + k * SW_THREADS + c;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    int i = 0;
+    for (; i + 4 <= nblocks; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] += __ldg(pp + size_t(i + u) * 3 * SW_THREADS);
     }
-    dcw[2 * c] = a0;
-    dcw[2 * c + 1] = a1;
-    dcb[c] = ab;
+    for (; i < nblocks; ++i) a[0] += __ldg(pp + size_t(i) * 3 * SW_THREADS);
+    const float sum = (a[0] + a[1]) + (a[2] + a[3]);
+    if (k == 0) dcw[2 * c] = sum;
+    else if (k == 1) dcw[2 * c + 1] = sum;
+    else dcb[c] = sum;
 }
 
 // ---------------------------------------------------------------------------------------------------------------- RMS norm + residual
@@ -313,7 +317,7 @@ int g2048_urm_swiglu_bwd(const float* gate, const float* up, const float* conv_w
     const int grid = B == 0 ? 1 : urmt::grid_for(B, 8);
     urmt::swiglu_bwd_kernel<<<grid, urmt::SW_THREADS, 0, cudaStream_t(stream)>>>(gate, up, conv_w, conv_b, dy, dgate, dup, workspace, B);
     G2048_CHECK_LAUNCH("urmt::swiglu_bwd_kernel");
-    urmt::conv_reduce_kernel<<<1, urmt::SW_THREADS, 0, cudaStream_t(stream)>>>(workspace, grid, dconv_w, dconv_b);
+    urmt::conv_reduce_kernel<<<3, urmt::SW_THREADS, 0, cudaStream_t(stream)>>>(workspace, grid, dconv_w, dconv_b);
     G2048_CHECK_LAUNCH("urmt::conv_reduce_kernel");
     return G2048_OK;
 }
