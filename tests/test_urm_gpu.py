@@ -172,3 +172,20 @@ def test_trainer_urm_train_steps_match_autograd_on_the_same_batch():
     assert any(not torch.equal(a, p.detach()) for a, p in zip(before, t.model.parameters()))
     s2 = t.train_step()
     assert all(np.isfinite(s2[k]) for k in ("loss", "policy_loss", "value_loss", "entropy", "grad_norm"))
+
+
+def test_urm_precision_names():
+    """GameURM has the fp32-grade kernel (auto / x3) and the labelled fp16 variant; there is no FFMA kernel to fall back to."""
+    from g2048 import env, policy, rollout
+    model = policy.GameURM(policy.GameURMConfig(dropout=0.0)).cuda().eval()
+    pol = rollout.pack_policy(model)
+    boards = env.reset(16, device=0, seed=1, env0=0, ctr=0)
+    with pytest.raises(ValueError):
+        rollout.rollout(pol, boards.clone(), 1, seed=1, precision="fp32")
+    a = rollout.rollout(pol, boards.clone(), 2, seed=1, precision="auto")
+    b = rollout.rollout(pol, boards.clone(), 2, seed=1, precision="x3")
+    torch.cuda.synchronize()
+    assert torch.equal(a.logp, b.logp) and torch.equal(a.boards, b.boards)
+    mlp = rollout.pack_policy(policy.GameMLP(policy.MLPConfig(hidden_dim=64, num_layers=1, dropout=0.0)).cuda().eval())
+    with pytest.raises(ValueError):
+        rollout.rollout(mlp, boards.clone(), 1, seed=1, precision="fp16")
