@@ -98,3 +98,24 @@ def test_reference_advantage_and_optimize_step_consume_our_episodes(ref, episode
     assert all(np.isfinite(stats[k]) for k in ("loss", "policy_loss", "value_loss", "entropy", "kl_average"))
     # the rollout policy IS this model: the recorded log-probs are its own, so the first-epoch KL is ~0
     assert abs(stats["kl_average"]) < 1e-4
+
+
+def test_reference_timing_script_runs_b1_to_b5():
+    """baseline/time_reference.py (bench.py's `cpu_baseline.python_reference`): every leg of BASELINE.md section 3 on the staged,
+    unmodified reference, with tiny budgets -- the script itself is what is checked here, not the numbers."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "baseline", "_ref", "game.py")):
+        pytest.skip("baseline/_ref is not staged (baseline/stage_reference.sh needs /root/reference)")
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+    out = subprocess.run([sys.executable, os.path.join(root, "baseline", "time_reference.py"), "--seconds", "0.5", "--train-steps", "2"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("simulate_move_transitions_per_sec", "step_env_steps_per_sec", "play_game_for_episode_env_steps_per_sec"):
+        assert d[k] > 0, k
+    b4, b5 = d["advantage_and_update"], d["config1_train_cli"]
+    assert b4["samples"] > 0 and b4["model_optimize_step_batch4_samples_per_sec"] > 0 and b4["model_optimize_step_one_batch_samples_per_sec"] > 0
+    assert "unavailable" not in b5 and b5["train_steps"] == 2 and b5["env_steps_per_sec"] > 0
