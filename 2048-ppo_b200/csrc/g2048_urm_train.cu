@@ -95,8 +95,8 @@ struct AttnBwdTile {
     float dS[NHEAD][SEQ][SEQ + 1];
 };
 
-__global__ void __launch_bounds__(64) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
-                                                      float* __restrict__ dqkv, int64_t B) {
+__global__ void __launch_bounds__(64, 8) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                         float* __restrict__ dqkv, int64_t B) {
     __shared__ __align__(16) AttnBwdTile T;
     const int tid = threadIdx.x, h = tid >> 4, i = tid & 15;
     for (int64_t env = blockIdx.x; env < B; env += gridDim.x) {
@@ -104,24 +104,45 @@ __global__ void __launch_bounds__(64) attn_bwd_kernel(const float* __restrict__ 
         load_env_rows(&T.t.qkv[0][0], 3 * H + 4, qkv + env * SEQ * 3 * H, 3 * H, tid, 64);
         load_env_rows(&T.dout[0][0], H + 4, dout + env * SEQ * H, H, tid, 64);
         __syncthreads();
-        float p[SEQ], dp[SEQ];
-        prob_row(T.t, h, i, p);
-        float delta = 0.f;
+        // row i of head h, key by key (the j loops are NOT unrolled: scores, probabilities and dP pass through this thread's own
+        // rows of the shared-memory P / dS arrays instead of 3 x 16 registers with every K / V load hoisted above them)
+        float q[HD], g[HD];
 #pragma unroll
-        for (int j = 0; j < SEQ; ++j) {
-            float s = 0.f;
-#pragma unroll
-            for (int d = 0; d < HD; ++d) s = fmaf(T.dout[i][h * HD + d], T.t.qkv[j][2 * H + h * HD + d], s);
-            dp[j] = s;
-            delta = fmaf(p[j], s, delta);
+        for (int d = 0; d < HD; ++d) {
+            q[d] = T.t.qkv[i][h * HD + d] * 0.25f;
+            g[d] = T.dout[i][h * HD + d];
         }
+        float mx = -INFINITY;
+#pragma unroll 2
+        for (int j = 0; j < SEQ; ++j) {
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) {
+                s = fmaf(q[d], T.t.qkv[j][H + h * HD + d], s);
+                dp = fmaf(g[d], T.t.qkv[j][2 * H + h * HD + d], dp);
+            }
+            T.P[h][i][j] = s;
+            T.dS[h][i][j] = dp;
+            mx = fmaxf(mx, s);
+        }
+        float den = 0.f, delta = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < SEQ; ++j) {
+            const float e = expf(T.P[h][i][j] - mx);
+            T.P[h][i][j] = e;
+            den += e;
+            delta = fmaf(e, T.dS[h][i][j], delta);
+        }
+        const float inv = 1.0f / den;
+        delta *= inv;
         float dq[HD];
 #pragma unroll
         for (int d = 0; d < HD; ++d) dq[d] = 0.f;
-#pragma unroll
+#pragma unroll 2
         for (int j = 0; j < SEQ; ++j) {
-            const float ds = p[j] * (dp[j] - delta);
-            T.P[h][i][j] = p[j];
+            const float pj = T.P[h][i][j] * inv;
+            const float ds = pj * (T.dS[h][i][j] - delta);
+            T.P[h][i][j] = pj;
             T.dS[h][i][j] = ds;
 #pragma unroll
             for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, T.t.qkv[j][H + h * HD + d], dq[d]);
@@ -135,7 +156,7 @@ __global__ void __launch_bounds__(64) attn_bwd_kernel(const float* __restrict__ 
         float dk[HD], dv[HD];
 #pragma unroll
         for (int d = 0; d < HD; ++d) dk[d] = dv[d] = 0.f;
-#pragma unroll
+#pragma unroll 2
         for (int r = 0; r < SEQ; ++r) {
             const float ds = T.dS[h][r][i], pr = T.P[h][r][i];
 #pragma unroll

@@ -13,7 +13,7 @@ from g2048 import trainer as tr  # noqa: E402
 envs = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 horizon = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 dev = torch.device("cuda:0")
-for mode in ("ops", "autograd", "autograd_tf32"):
+for mode in os.environ.get("URM_MODES", "ops,autograd,autograd_tf32").split(","):
     cfg = tr.TrainConfig(model_type="urm", envs=envs, horizon=horizon, zero_heads=False, warmup_steps=0,
                          urm_update="ops" if mode == "ops" else "autograd", update_matmul="tf32" if mode.endswith("tf32") else "fused")
     t = tr.Trainer(cfg, dev)
