@@ -138,7 +138,11 @@ __device__ __forceinline__ void step_loop(const uint32_t* slut, const uint32_t* 
 
 // Step (+ every shaping term when SHAPING) on the dense tables (M | S staged whole, 219 KiB; M alone without shaping):
 // persistent, one CTA per SM, one transition per thread and iteration.  Boards with a 4096+ tile take the general path through L2.
-template <bool SHAPING>
+// REPLAY = the caller passed replayed draws.  A template parameter, not a run-time test: with the (predicated-off) replay load in
+// the loop, the first constant load of the Philox round keys reused its destination register and had to wait on the scoreboard that
+// the load shares with the NEXT transition's board prefetch -- every iteration then waited out a full HBM latency (ncu source view,
+// round 2: 13 % of the kernel's stall samples on that one LDC).
+template <bool SHAPING, bool REPLAY>
 __global__ void __launch_bounds__(STEP_THREADS, 1)
 step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict__ in, const uint8_t* __restrict__ actions,
                   uint64_t* __restrict__ out, int32_t* __restrict__ points, uint8_t* __restrict__ flags,
@@ -167,7 +171,7 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
             next_action = __ldg(actions + nx);
         }
         uint32_t u0, u1;
-        if (replay) {
+        if (REPLAY) {
             const uint2 r = __ldg(reinterpret_cast<const uint2*>(replay) + i);
             u0 = r.x;
             u1 = r.y;
@@ -545,7 +549,8 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
     const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
     cudaStream_t st = cudaStream_t(stream);
     if (n >= STAGED_MIN_UNITS) {
-        auto kern = shaping ? step_kernel_dense<true> : step_kernel_dense<false>;
+        auto kern = shaping ? (replay ? step_kernel_dense<true, true> : step_kernel_dense<true, false>)
+                            : (replay ? step_kernel_dense<false, true> : step_kernel_dense<false, false>);
         G2048_CHECK_CUDA(ensure_smem(kern, DENSE_BYTES));
         constexpr int64_t SPLIT = int64_t(1) << 30;               // the kernel indexes with 32 bits
         for (int64_t o = 0; o < n; o += SPLIT) {

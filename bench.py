@@ -444,7 +444,7 @@ def run_ours(args):
     barrier()
     ns_ms = ev0.elapsed_time(ev1) / args.steps
     no_shaping = {"ms_per_launch": ns_ms, "bytes_per_transition": 22, "env_steps_per_sec": world * N_TRANS / (ns_ms * 1e-3),
-                  "achieved_gbs": 22 * N_TRANS / (ns_ms * 1e-3) / 1e9, "kernel": "step_kernel_dense<false>"}
+                  "achieved_gbs": 22 * N_TRANS / (ns_ms * 1e-3) / 1e9, "kernel": "step_kernel_dense<false, false>"}
 
     # ---- C2 in its 4-move expansion form (g2048_expand4: all four pre-spawn successors per board)
     ex_sets = [dict(succ=torch.empty((N_BOARDS, 4), dtype=torch.int64, device=dev),
