@@ -36,9 +36,9 @@ MOVES = 4
 N_TRANS = N_BOARDS * MOVES
 BYTES_PER_TRANSITION = 30      # 8 board in + 1 action + 8 board out + 4 points + 1 flags + 8 shaping
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel_dense launch on this workload, from the
-# committed `ncu --set full` capture (profiles/r02_step_dense_ncu.txt: 38.0 MB read + 32.8 MB written; the rest of
+# committed `ncu --set full` capture (profiles/r02_step_dense_ncu.txt: 38.0 MB read + 33.2 MB written; the rest of
 # the 88 MB of outputs is still dirty in the 126 MB L2 when the kernel ends)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 70.8e6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 71.2e6
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 WORKLOAD = ("c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step "
