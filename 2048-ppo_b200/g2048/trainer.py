@@ -23,7 +23,8 @@ class TrainConfig:
                                    # fused URM kernel, update through torch autograd on the policy mirror (truncated loops under
                                    # no_grad as in game.py:1400-1413) with the fused PPO-loss kernel -- SURVEY 8(f) N4, host half
     urm: GameURMConfig = field(default_factory=lambda: GameURMConfig(dropout=0.0))
-    urm_chunk: int = 1 << 15       # samples per autograd chunk of the URM update (~0.4 MB of saved activations per sample)
+    urm_chunk: int = 1 << 17       # samples per autograd chunk of the URM update (~0.4 MB of saved activations per sample: 50 GB;
+                                   # a chunk is ~300 small launches, so short chunks leave the GPU waiting for the host)
     urm_update: str = "ops"        # "ops": every block op of the URM update on this library's kernels, forward and backward
                                    # (g2048/urm_ops.py: tcgen05 projections + hand-written attention / ConvSwiGLU / norm kernels);
                                    # "autograd": the torch mirror's own forward (ATen / cuBLAS) -- the comparator of the tests

@@ -345,7 +345,7 @@ def rollout_section(args, dev, world, rank, barrier):
             utr = {}
             for mode in ("ops", "autograd"):
                 ucfg = tr.TrainConfig(model_type="urm", envs=args.urm_train_envs * world, horizon=args.urm_train_steps, zero_heads=False,
-                                      warmup_steps=0, seed=5, urm_update=mode)
+                                      warmup_steps=0, seed=5, urm_update=mode, urm_chunk=(1 << 17) if mode == "ops" else (1 << 15))
                 ut = tr.Trainer(ucfg, dev)
                 ms, _ = timed(ut.train_step, 2 if mode == "ops" else 1)
                 ms = max_over_ranks(ms)
