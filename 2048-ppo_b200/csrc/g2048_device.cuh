@@ -677,6 +677,94 @@ __device__ __forceinline__ StepOut env_step_dense(Board b, uint32_t mx_b, uint32
     return o;
 }
 
+// ------------------------------------------------------------------ the four moves of one board on the dense tables (C2 form)
+// What the four transitions of a board share: its transpose, its largest exponent, the corner rules and the count of empty cells
+// before the move, and the across-the-move line potentials before the move (the rows of the board for UP / DOWN, its columns for
+// LEFT / RIGHT).  env_step_dense_m<.., ACTION> is env_step_dense with the direction as a template parameter (no run-time
+// selects, no conditional row reversal) on top of these; same results, bit for bit.
+struct Step4Shared {
+    Board b, bt;
+    uint32_t mx_b, empt_b;
+    uint32_t s_rows, s_cols;       // s_sum(b), s_sum(bt): potentials of the board's rows / columns (SHAPING only)
+    bool fc_b, ic_b;
+};
+template <bool SHAPING>
+__device__ __forceinline__ Step4Shared step4_shared(Board b, uint32_t mx_b, const DenseSmem& tab) {
+    Step4Shared sh;
+    sh.b = b;
+    sh.bt = transpose(b);
+    sh.mx_b = mx_b;
+    sh.empt_b = sh.s_rows = sh.s_cols = 0u;
+    sh.fc_b = sh.ic_b = false;
+    if constexpr (SHAPING) {
+        sh.s_rows = s_sum(b, tab);
+        sh.s_cols = s_sum(sh.bt, tab);
+        corner_rules(b, mx_b, sh.fc_b, sh.ic_b);
+        sh.empt_b = 16u - __popc(nz_flags8(b.lo)) - __popc(nz_flags8(b.hi));
+    }
+    return sh;
+}
+template <bool SHAPING, int ACTION>
+__device__ __forceinline__ StepOut env_step_dense_m(const Step4Shared& sh, uint32_t u0, uint32_t u1, const DenseSmem& tab) {
+    constexpr bool horiz = (ACTION & 2) != 0, rev = (ACTION & 1) != 0;
+    StepOut o;
+    const Board along = horiz ? sh.b : sh.bt;
+    const Board canon = rev ? rev_rows(along) : along;
+    const uint32_t ia = dense2<12, DENSE_M_STRIDE>(canon.lo), ib = dense2<12, DENSE_M_STRIDE>(canon.hi);
+    uint2 m0, m1, m2, m3;
+    if constexpr (SHAPING) {
+        m0 = tab.M((ia << 3) & 0x7FFF8u), m1 = tab.M((ia >> 13) & 0x7FFF8u);
+        m2 = tab.M((ib << 3) & 0x7FFF8u), m3 = tab.M((ib >> 13) & 0x7FFF8u);
+    } else {
+        m0 = make_uint2(tab.Mlo((ia << 3) & 0x7FFF8u), 0u), m1 = make_uint2(tab.Mlo((ia >> 13) & 0x7FFF8u), 0u);
+        m2 = make_uint2(tab.Mlo((ib << 3) & 0x7FFF8u), 0u), m3 = make_uint2(tab.Mlo((ib >> 13) & 0x7FFF8u), 0u);
+    }
+    const Board moved_c = {__byte_perm(m0.x, m1.x, 0x5410), __byte_perm(m2.x, m3.x, 0x5410)};
+    const bool valid = !same(moved_c, canon);                      // game.py:959
+    const uint32_t pt = (__byte_perm(m0.x, m1.x, 0x7632) & 0x0FFF0FFFu) + (__byte_perm(m2.x, m3.x, 0x7632) & 0x0FFF0FFFu);
+    const uint32_t points = ((pt & 0xFFFFu) + (pt >> 16)) << 2;
+    const uint32_t created = max(max(m0.x, m1.x), max(m2.x, m3.x)) >> 28;
+    const Board un = rev ? rev_rows(moved_c) : moved_c;
+    const Board unt = transpose(un);
+    const Board moved = horiz ? un : unt;
+    uint32_t shape_lo = 0u, shape_hi = 0u;
+    if constexpr (SHAPING) {
+        const uint32_t ca = s_sum(unt, tab), cb = horiz ? sh.s_cols : sh.s_rows;
+        const uint32_t al = m0.y + m1.y + m2.y + m3.y;                 // lines along the move axis: lane 0 before, lane 1 after
+        const uint32_t cr = ca * 65536u + cb;                          // lines across it
+        const uint32_t pairs = __vmaxu2(al & 0x000F000Fu, (al >> 4) & 0x000F000Fu) +
+                               __vmaxu2(cr & 0x000F000Fu, (cr >> 4) & 0x000F000Fu);
+        const uint32_t smooth = ((al >> 8) & 0x00FF00FFu) + ((cr >> 8) & 0x00FF00FFu);
+        const uint32_t mx_a = max(sh.mx_b, created);
+        bool fc_a, ic_a;
+        corner_rules(moved, mx_a, fc_a, ic_a);
+        const uint32_t dbl = pairs + pairs, hlf = (pairs >> 1) & 0x000F000Fu;            // game.py:755-758
+        const uint32_t mono_b = (sh.fc_b ? dbl : hlf) & 0x3Fu, mono_a = (fc_a ? dbl : hlf) >> 16;
+        const uint32_t smooth_b = smooth & 0xFFFFu, smooth_a = smooth >> 16;
+        shape_lo = mono_b | mono_a << 6 | sh.empt_b << 12 | created << 22 | sh.mx_b << 27 | uint32_t(sh.ic_b) << 31;
+        shape_hi = mx_a | uint32_t(ic_a) << 4 | smooth_b << 5 | smooth_a << 14;
+    }
+    // spawn (game.py:923-940, as spawn_tile) -- its count of empty cells is emptiness_after
+    const uint32_t zl = z_flags8(moved.lo) >> 3, zh = z_flags8(moved.hi) >> 3;
+    const uint32_t pl = zl * 0x11111111u;
+    const uint32_t nl = pl >> 28, empt_a = nl + __popc(zh);
+    const uint32_t k = __umulhi(u0, empt_a);
+    const bool in_lo = k < nl;
+    const uint32_t z = in_lo ? zl : zh;
+    const uint32_t p = in_lo ? pl : zh * 0x11111111u;
+    const uint32_t t = in_lo ? k + 1u : k + 1u - nl;
+    const uint32_t hit = z_flags8(p ^ (t * 0x11111111u)) & (z << 3);
+    const uint32_t tile = (hit >> 3) * (u1 >= 3865470567u ? 2u : 1u);
+    const Board spawned = {moved.lo | (in_lo ? tile : 0u), moved.hi | (in_lo ? 0u : tile)};
+    o.shape_lo = (SHAPING && valid) ? (shape_lo | empt_a << 17) : 0u;
+    o.shape_hi = (SHAPING && valid) ? shape_hi : 0u;
+    o.board = valid ? spawned : sh.b;
+    o.points = valid ? int(points) : 0;
+    const uint32_t lm = legal_mask(o.board);                       // game.py:1006 / 963
+    o.flags = lm | (lm == 0u ? FLAG_DONE : 0u) | (valid ? 0u : FLAG_INVALID);
+    return o;
+}
+
 // ------------------------------------------------------------------ model input
 // game.py:92-101: 16 x [exponent, row/3, col/3]
 __device__ __forceinline__ float pos_feature(int i) { return float(i) / 3.0f; }

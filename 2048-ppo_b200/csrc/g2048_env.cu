@@ -191,6 +191,96 @@ step_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict_
     }
 }
 
+// The C2 form of the step (BASELINE config 2: "1M random boards x 4 moves"): one thread plays all four moves of a board, each with
+// its own spawn -- transition (b, m) = move m (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT) on board b with the draws of env id env0 + 4 b + m,
+// i.e. exactly what g2048_step returns for the 4 n (board, action) pairs -- and the four transitions share the board's transpose,
+// largest exponent, before-move potentials, corner rules and empty count (env_step_dense_m).  Outputs are [n, 4]: one board's four
+// records are 32 / 16 / 4 / 32 contiguous bytes, written with 128-bit stores.
+#ifndef G2048_STEP4_THREADS
+#define G2048_STEP4_THREADS 512
+#endif
+constexpr int STEP4_THREADS = G2048_STEP4_THREADS;      // 512: 128 registers per thread (four transitions' outputs are live at once)
+
+template <bool SHAPING, bool REPLAY>
+__global__ void __launch_bounds__(STEP4_THREADS, 1)
+step4_kernel_dense(const uint32_t* __restrict__ glut, const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                   int32_t* __restrict__ points, uint8_t* __restrict__ flags, uint64_t* __restrict__ shaping, int64_t n,
+                   const uint32_t* __restrict__ replay, const PhiloxKeys seed, uint64_t env0, uint64_t ctr) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    const uint32_t stride = gridDim.x * blockDim.x, n32 = uint32_t(n);      // (the host splits launches at 2^28 boards)
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    stage_lut_issue<uint32_t(SHAPING ? DENSE_BYTES : DENSE_M_BYTES)>(
+        reinterpret_cast<uint32_t*>(smem_raw), reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(glut) + DENSE_OFFSET_BYTES), &bar);
+    pdl_wait();
+    uint64_t next_board = i < n32 ? __ldg(in + i) : 0ull;
+    stage_lut_wait(&bar);
+    const DenseSmem tab{smem_u32(smem_raw), smem_u32(smem_raw) + uint32_t(DENSE_M_BYTES)};
+    for (; i < n32; i += stride) {
+        const Board b = make_board(next_board);
+        const uint32_t nx = i + stride;
+        if (nx < n32) next_board = __ldg(in + nx);
+        uint32_t u0[4], u1[4];
+        if (REPLAY) {
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(replay) + 2 * size_t(i)), r1 = __ldg(reinterpret_cast<const uint4*>(replay) + 2 * size_t(i) + 1);
+            u0[0] = r0.x; u1[0] = r0.y; u0[1] = r0.z; u1[1] = r0.w; u0[2] = r1.x; u1[2] = r1.y; u0[3] = r1.z; u1[3] = r1.w;
+        } else {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const U4 d = env_draws(seed, env0 + 4ull * uint64_t(i) + uint64_t(m), ctr);
+                u0[m] = d.x;
+                u1[m] = d.y;
+            }
+        }
+        StepOut o[4];
+        const uint32_t mx = max_nibble(b);
+        if (mx <= 11u) {
+            const Step4Shared sh = step4_shared<SHAPING>(b, mx, tab);
+            o[0] = env_step_dense_m<SHAPING, 0>(sh, u0[0], u1[0], tab);
+            o[1] = env_step_dense_m<SHAPING, 1>(sh, u0[1], u1[1], tab);
+            o[2] = env_step_dense_m<SHAPING, 2>(sh, u0[2], u1[2], tab);
+            o[3] = env_step_dense_m<SHAPING, 3>(sh, u0[3], u1[3], tab);
+        } else {                                                       // rare: a 4096+ tile on the board
+#pragma unroll                                                         // (unrolled: o[] must stay in registers)
+            for (int m = 0; m < 4; ++m) o[m] = env_step<SHAPING>(b, uint32_t(m), u0[m], u1[m], LutGlobal{glut});
+        }
+        uint4* ob = reinterpret_cast<uint4*>(out + 4 * size_t(i));
+        ob[0] = make_uint4(o[0].board.lo, o[0].board.hi, o[1].board.lo, o[1].board.hi);
+        ob[1] = make_uint4(o[2].board.lo, o[2].board.hi, o[3].board.lo, o[3].board.hi);
+        reinterpret_cast<int4*>(points)[i] = make_int4(o[0].points, o[1].points, o[2].points, o[3].points);
+        reinterpret_cast<uint32_t*>(flags)[i] = o[0].flags | o[1].flags << 8 | o[2].flags << 16 | o[3].flags << 24;
+        if (SHAPING) {
+            uint4* os = reinterpret_cast<uint4*>(shaping + 4 * size_t(i));
+            os[0] = make_uint4(o[0].shape_lo, o[0].shape_hi, o[1].shape_lo, o[1].shape_hi);
+            os[1] = make_uint4(o[2].shape_lo, o[2].shape_hi, o[3].shape_lo, o[3].shape_hi);
+        }
+    }
+}
+
+template <bool SHAPING>
+__global__ void __launch_bounds__(256)
+step4_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* in, uint64_t* out, int32_t* points, uint8_t* flags, uint64_t* shaping,
+                    int64_t n, const uint32_t* replay, const PhiloxKeys seed, uint64_t env0, uint64_t ctr) {
+    const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;      // one transition per thread
+    if (t >= 4 * n) return;
+    const Board b = make_board(in[t >> 2]);
+    uint32_t u0, u1;
+    if (replay) {
+        u0 = replay[2 * t];
+        u1 = replay[2 * t + 1];
+    } else {
+        const U4 d = env_draws(seed, env0 + uint64_t(t), ctr);
+        u0 = d.x;
+        u1 = d.y;
+    }
+    const StepOut o = env_step<SHAPING>(b, uint32_t(t & 3), u0, u1, LutGlobal{glut});
+    out[t] = pack_board(o.board);
+    points[t] = o.points;
+    flags[t] = uint8_t(o.flags);
+    if (SHAPING) shaping[t] = uint64_t(o.shape_lo) | uint64_t(o.shape_hi) << 32;
+}
+
 template <bool SHAPING>
 __global__ void __launch_bounds__(256)
 step_kernel_direct(const uint32_t* __restrict__ glut, const uint64_t* in, const uint8_t* actions, uint64_t* out,
@@ -565,6 +655,37 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
         kern<<<unsigned((n + 255) / 256), 256, 0, st>>>(lut, boards_in, actions, boards_out, points, flags, shaping, n,
                                                         replay, philox_round_keys(seed), env0, ctr);
         G2048_CHECK_LAUNCH("step_kernel_direct");
+    }
+    return G2048_OK;
+}
+
+int g2048_step4(const void* d_lut, const uint64_t* boards_in, uint64_t* boards_out, int32_t* points, uint8_t* flags, uint64_t* shaping,
+                int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0, uint64_t ctr, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_step4: n < 0");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_lut && boards_in && boards_out && points && flags, "g2048_step4: NULL pointer argument");
+    G2048_REQUIRE(((reinterpret_cast<uintptr_t>(boards_out) | reinterpret_cast<uintptr_t>(points) | reinterpret_cast<uintptr_t>(shaping) |
+                    reinterpret_cast<uintptr_t>(replay)) & 15) == 0 && (reinterpret_cast<uintptr_t>(flags) & 3) == 0,
+                  "g2048_step4: the [n,4] outputs (and replay) must be 16-byte aligned, flags 4-byte aligned");
+    const uint32_t* lut = static_cast<const uint32_t*>(d_lut);
+    cudaStream_t st = cudaStream_t(stream);
+    if (4 * n >= STAGED_MIN_UNITS) {
+        auto kern = shaping ? (replay ? step4_kernel_dense<true, true> : step4_kernel_dense<true, false>)
+                            : (replay ? step4_kernel_dense<false, true> : step4_kernel_dense<false, false>);
+        G2048_CHECK_CUDA(ensure_smem(kern, DENSE_BYTES));
+        constexpr int64_t SPLIT = int64_t(1) << 28;               // the kernel indexes with 32 bits
+        for (int64_t o = 0; o < n; o += SPLIT) {
+            const int64_t m = n - o < SPLIT ? n - o : SPLIT;
+            G2048_CHECK_CUDA(launch_pdl(kern, num_sms(), STEP4_THREADS, DENSE_BYTES, st, lut, boards_in + o, boards_out + 4 * o, points + 4 * o,
+                                        flags + 4 * o, shaping ? shaping + 4 * o : static_cast<uint64_t*>(nullptr), m,
+                                        replay ? replay + 8 * o : static_cast<const uint32_t*>(nullptr), philox_round_keys(seed),
+                                        env0 + 4ull * uint64_t(o), ctr));
+        }
+    } else {
+        auto kern = shaping ? step4_kernel_direct<true> : step4_kernel_direct<false>;
+        kern<<<unsigned((4 * n + 255) / 256), 256, 0, st>>>(lut, boards_in, boards_out, points, flags, shaping, n, replay,
+                                                            philox_round_keys(seed), env0, ctr);
+        G2048_CHECK_LAUNCH("step4_kernel_direct");
     }
     return G2048_OK;
 }

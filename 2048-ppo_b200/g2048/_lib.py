@@ -23,6 +23,7 @@ _SIGNATURES = {
     "g2048_build_lut": [vp, vp],
     "g2048_reset": [vp, i64, vp, u64, u64, u64, vp],
     "g2048_step": [vp, vp, vp, vp, vp, vp, vp, i64, vp, u64, u64, u64, vp],
+    "g2048_step4": [vp, vp, vp, vp, vp, vp, i64, vp, u64, u64, u64, vp],
     "g2048_expand4": [vp, vp, vp, vp, vp, vp, i64, vp],
     "g2048_potentials": [vp, vp, vp, i64, vp],
     "g2048_encode": [vp, vp, i64, vp],

@@ -123,6 +123,30 @@ def step(boards: torch.Tensor, actions: torch.Tensor, *, seed: int = 0, env0: in
     return out
 
 
+def step4(boards: torch.Tensor, *, seed: int = 0, env0: int = 0, ctr: int = 0, replay: torch.Tensor | None = None,
+          shaping: bool = True, out: dict | None = None) -> dict:
+    """game.py:952-1030 for all four moves of every board, each with its own spawn (BASELINE config 2: boards x 4 moves).
+
+    Transition (b, m) = move m (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT) on board b with the draws of env id env0 + 4 b + m: the same results as
+    `step(boards.repeat_interleave(4), tensor([0, 1, 2, 3]).repeat(n), env0=env0, ...)`, from one thread per board that shares the
+    work the four moves have in common.  Returns dict(boards int64[n,4], points int32[n,4], flags uint8[n,4], shaping int64[n,4] | None)."""
+    boards = _req(boards, torch.int64, "boards")
+    n = boards.numel()
+    dev = init(boards.device)
+    with torch.cuda.device(dev):
+        table = lut(dev)
+        if out is None:
+            out = dict(boards=torch.empty((n, 4), dtype=torch.int64, device=dev), points=torch.empty((n, 4), dtype=torch.int32, device=dev),
+                       flags=torch.empty((n, 4), dtype=torch.uint8, device=dev),
+                       shaping=torch.empty((n, 4), dtype=torch.int64, device=dev) if shaping else None)
+        if replay is not None:
+            replay = _req(replay, torch.int32, "replay")
+            assert replay.numel() == 8 * n
+        _lib.call("g2048_step4", _ptr(table), _ptr(boards), _ptr(out["boards"]), _ptr(out["points"]), _ptr(out["flags"]),
+                  _ptr(out.get("shaping")), n, _ptr(replay), seed, env0, ctr, _stream())
+    return out
+
+
 def bind_host_thread_to_gpu(device=None):
     """Pin the calling thread to the CPUs NVML reports as local to `device` (its NUMA node / PCIe root), so that
     pinned host buffers allocated afterwards are first-touched next to the GPU and the copies do not cross the
@@ -192,6 +216,51 @@ class HostStepper:
                 _lib.call("g2048_step", _ptr(self.table), _ptr(sl["boards"]), _ptr(sl["actions"]), _ptr(sl["out_boards"]),
                           _ptr(sl["points"]), _ptr(sl["flags"]), _ptr(sl["shaping"]), m, None, seed, env0 + lo, ctr,
                           C.c_void_p(st.cuda_stream))
+                h_out["boards"][lo:hi].copy_(sl["out_boards"][:m], non_blocking=True)
+                h_out["points"][lo:hi].copy_(sl["points"][:m], non_blocking=True)
+                h_out["flags"][lo:hi].copy_(sl["flags"][:m], non_blocking=True)
+                if self.shaping:
+                    h_out["shaping"][lo:hi].copy_(sl["shaping"][:m], non_blocking=True)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return h_out
+
+
+class HostStepper4:
+    """`step4` for HOST (pinned) arrays, chunked over a ring of CUDA streams like HostStepper: h_boards int64[n] in,
+    dict(boards [n,4], points [n,4], flags [n,4][, shaping [n,4]]) out."""
+
+    def __init__(self, n: int, *, device=None, chunk: int = 1 << 18, streams: int = 2, shaping: bool = True):
+        self.n, self.chunk, self.shaping = n, min(chunk, max(n, 1)), shaping
+        self.dev = init(device)
+        self.table = lut(self.dev)
+        with torch.cuda.device(self.dev):
+            self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(streams)]
+            c = self.chunk
+            self.slots = [dict(boards=torch.empty(c, dtype=torch.int64, device=self.dev),
+                               out_boards=torch.empty((c, 4), dtype=torch.int64, device=self.dev),
+                               points=torch.empty((c, 4), dtype=torch.int32, device=self.dev),
+                               flags=torch.empty((c, 4), dtype=torch.uint8, device=self.dev),
+                               shaping=torch.empty((c, 4), dtype=torch.int64, device=self.dev) if shaping else None)
+                          for _ in range(streams)]
+
+    def step(self, h_boards, h_out: dict, *, seed: int = 0, env0: int = 0, ctr: int = 0) -> dict:
+        for t in (h_boards, *[v for v in h_out.values() if v is not None]):
+            if t.is_cuda or not t.is_pinned():
+                raise ValueError("HostStepper4 works on pinned host tensors")
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            st.wait_stream(cur)
+        k = 0
+        for lo in range(0, self.n, self.chunk):
+            hi = min(self.n, lo + self.chunk)
+            m = hi - lo
+            st, sl = self.streams[k % len(self.streams)], self.slots[k % len(self.slots)]
+            k += 1
+            with torch.cuda.stream(st):
+                sl["boards"][:m].copy_(h_boards[lo:hi], non_blocking=True)
+                _lib.call("g2048_step4", _ptr(self.table), _ptr(sl["boards"]), _ptr(sl["out_boards"]), _ptr(sl["points"]), _ptr(sl["flags"]),
+                          _ptr(sl["shaping"]), m, None, seed, env0 + 4 * lo, ctr, C.c_void_p(st.cuda_stream))
                 h_out["boards"][lo:hi].copy_(sl["out_boards"][:m], non_blocking=True)
                 h_out["points"][lo:hi].copy_(sl["points"][:m], non_blocking=True)
                 h_out["flags"][lo:hi].copy_(sl["flags"][:m], non_blocking=True)

@@ -34,11 +34,14 @@ import numpy as np  # noqa: E402
 N_BOARDS = 1 << 20
 MOVES = 4
 N_TRANS = N_BOARDS * MOVES
-BYTES_PER_TRANSITION = 30      # 8 board in + 1 action + 8 board out + 4 points + 1 flags + 8 shaping
+BYTES_PER_TRANSITION = 30      # g2048_step on (board, action) pairs: 8 board in + 1 action + 8 board out + 4 points + 1 flags + 8 shaping
+BYTES_PER_BOARD4 = 92          # g2048_step4 (the C2 form, one board -> its four transitions): 8 board in + 4 x (8 + 4 + 1 + 8) out = 23 B / transition
 # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel_dense launch on this workload, from the
 # committed `ncu --set full` capture (profiles/r02_step_dense_ncu.txt: 38.0 MB read + 33.2 MB written; the rest of
 # the 88 MB of outputs is still dirty in the 126 MB L2 when the kernel ends)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 71.2e6
+# the same for one step4_kernel_dense launch (profiles/r02_step4_ncu.txt)
+NCU_TRAFFIC_BYTES_PER_LAUNCH_STEP4 = 37.5e6     # 8.7 MB read + 28.9 MB written (of 96 MB algorithmic: the outputs are still dirty in L2)
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 WORKLOAD = ("c2_env_step: 2^20 boards x 4 moves = 4194304 full Game2048.step transitions per GPU per step "
@@ -430,8 +433,39 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    pairs_ms_per_step = ms / args.steps           # g2048_step on the 4 Mi (board, action) pairs
+    pairs_value = world * N_TRANS * args.steps / (ms * 1e-3)
+
+    # ---- the headline: the same 4 194 304 transitions in C2's own form, g2048_step4 (one thread plays the four moves of a board
+    # and shares their common work; bit for bit the transitions g2048_step returns for the pairs -- tests/test_env_gpu.py).  The
+    # [n,4] outputs reuse the pair buffers.
+    s4_in = [s["boards"][:N_BOARDS] for s in sets]
+    s4_out = [{k: v.view(N_BOARDS, 4) for k, v in s["out"].items()} for s in sets]
+
+    def one_step4(k):
+        env.step4(s4_in[k % RING], seed=2048, env0=env0, ctr=1 + k, shaping=True, out=s4_out[k % RING])
+
+    for w in range(max(args.warmup, 3)):
+        one_step4(w)
+    barrier()
+    s4_graph = capture(one_step4, args.steps)
+    barrier()
+    ev0.record()
+    s4_graph.replay()                 # exactly args.steps launches of g2048_step4
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     ms_per_step = ms / args.steps
     value = world * N_TRANS * args.steps / (ms * 1e-3)
+    global PAIRS_FORM
+    PAIRS_FORM = {"ms_per_launch": pairs_ms_per_step, "env_steps_per_sec": pairs_value, "bytes_per_transition": BYTES_PER_TRANSITION,
+                  "achieved_gbs": BYTES_PER_TRANSITION * N_TRANS / (pairs_ms_per_step * 1e-3) / 1e9, "kernel": "step_kernel_dense<true, false>",
+                  "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                  "note": "g2048_step on 4 194 304 independent (board, action) pairs: the general form of the same transitions"}
 
     # ---- the same step without the shaping record (shaping == NULL: 22 B / transition)
     ns_out = [dict(boards=s["out"]["boards"], points=s["out"]["points"], flags=s["out"]["flags"]) for s in sets]
@@ -512,7 +546,7 @@ def run_ours(args):
 
     e2e_value = e2e_ms = None
     e2e_steps = 0
-    h2d = N_TRANS * (8 + 1)
+    h2d = N_BOARDS * 8
     d2h = N_TRANS * (8 + 4 + 1 + 8)
     if not args.no_e2e:
         e2e_value, e2e_ms, e2e_steps = e2e_section(args, dev, world, rank, barrier, sets, env0)
@@ -530,9 +564,10 @@ def run_ours(args):
 
 
 def e2e_section(args, dev, world, rank, barrier, sets, env0):
-    """Same metric through the public host-buffer API (g2048.env.HostStepper) with HOST pinned buffers:
-    every step copies the inputs host->device, runs g2048_step and copies every output device->host
-    (2^20-transition chunks on 2 streams so the two PCIe directions and the kernel overlap; tools/time_e2e.py: the device->host direction saturates at ~46 GB/s for every chunking)."""
+    """Same metric through the public host-buffer API (g2048.env.HostStepper4, and HostStepper for the pairs form) with HOST pinned
+    buffers: every step copies the inputs host->device, runs g2048_step4 and copies every output device->host (2^20-transition
+    chunks on 2 streams so the two PCIe directions and the kernel overlap; tools/pcie_bw.py / tools/time_e2e.py: the device->host
+    direction is the ceiling for every chunking)."""
     import torch
     import torch.distributed as dist
 
@@ -548,25 +583,36 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
                  flags=torch.empty(N_TRANS, dtype=torch.uint8).pin_memory(),
                  shaping=torch.empty(N_TRANS, dtype=torch.int64).pin_memory())
     stepper = env.HostStepper(N_TRANS, device=dev)
+    stepper4 = env.HostStepper4(N_BOARDS, device=dev)
+    h_boards4 = torch.from_numpy(hb[:N_BOARDS].copy()).pin_memory()
+    h_out4 = {k: v.view(N_BOARDS, 4) for k, v in h_out.items()}
 
     def e2e_step(k):
+        stepper4.step(h_boards4, h_out4, seed=2048, env0=env0, ctr=1000 + k)
+
+    def e2e_step_pairs(k):
         stepper.step(h_boards, h_actions, h_out, seed=2048, env0=env0, ctr=1000 + k)
 
     e2e_steps = max(3, min(args.steps, 20))
-    for w in range(3):
-        e2e_step(w)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    for k in range(e2e_steps):
-        e2e_step(k)
-    ev1.record()
-    barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+
+    def run(fn):
+        for w in range(3):
+            fn(w)
+        barrier()
+        ev0.record()
+        for k in range(e2e_steps):
+            fn(k)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    pairs_ms = run(e2e_step_pairs)
+    e2e_ms = run(e2e_step)
     e2e_value = world * N_TRANS * e2e_steps / (e2e_ms * 1e-3)
     # information only: the same call without the shaping record (13 B instead of 21 B per transition device->host) -- the
     # device->host direction is what bounds this leg
@@ -586,8 +632,11 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ns_ms = float(t.item())
     global E2E_EXTRA
-    E2E_EXTRA = {"pcie_d2h_gbs_per_gpu": N_TRANS * 21 * e2e_steps / (e2e_ms * 1e-3) / 1e9,
-                 "pcie_h2d_gbs_per_gpu": N_TRANS * 9 * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+    E2E_EXTRA = {"api": "g2048.env.HostStepper4.step (g2048_step4 on pinned host buffers, 2^18-board chunks on 2 streams)",
+                 "pcie_d2h_gbs_per_gpu": N_TRANS * 21 * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                 "pcie_h2d_gbs_per_gpu": N_BOARDS * 8 * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                 "pairs_form": {"value": world * N_TRANS * e2e_steps / (pairs_ms * 1e-3), "h2d_bytes_per_step": N_TRANS * 9, "d2h_bytes_per_step": N_TRANS * 21,
+                                "api": "g2048.env.HostStepper.step (g2048_step on (board, action) pairs)"},
                  "without_shaping_record": {"value": world * N_TRANS * e2e_steps / (ns_ms * 1e-3), "d2h_bytes_per_step": N_TRANS * 13,
                                             "pcie_d2h_gbs_per_gpu": N_TRANS * 13 * e2e_steps / (ns_ms * 1e-3) / 1e9,
                                             "note": "information only: the headline e2e returns every output of the step"}}
@@ -597,6 +646,7 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
 
 
 E2E_EXTRA = {}
+PAIRS_FORM = {}
 
 
 def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps, h2d, d2h, ro, RING, expand):
@@ -606,22 +656,26 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
         no_shaping = expand.pop("no_shaping_step")
         no_shaping["frac_of_hbm_peak"] = no_shaping["achieved_gbs"] / peak
         expand["large_batch"]["frac_of_hbm_peak"] = expand["large_batch"]["achieved_gbs"] / peak
-        achieved = BYTES_PER_TRANSITION * N_TRANS / (ms_per_step * 1e-3) / 1e9
+        achieved = BYTES_PER_BOARD4 * N_BOARDS / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "boards": N_BOARDS, "moves": MOVES, "kernel_launches_per_step": 1, "l2": f"ring of {RING} distinct 120 MiB buffer sets (> 126 MB L2) used round-robin",
+            "config": {"workload": WORKLOAD, "boards": N_BOARDS, "moves": MOVES, "kernel_launches_per_step": 1,
+                       "entry_point": "g2048_step4: the four moves of every board from one thread, each transition with its own Philox spawn (env id 4 b + m)", "l2": f"ring of {RING} distinct 120 MiB buffer sets (> 126 MB L2) used round-robin",
                        "spawn": "philox4x32-10", "launch": "the K timed launches are one replay of a CUDA graph (after one untimed replay that uploads it)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": (e2e_ms / e2e_steps) if e2e_steps else None, **E2E_EXTRA},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "algorithmic_bytes_per_launch": BYTES_PER_TRANSITION * N_TRANS,
-                         "peak_source": which, "kernel": "step_kernel_dense",
-                         "bytes_per_unit": BYTES_PER_TRANSITION, "units_per_launch": N_TRANS},
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH_STEP4 or None, "algorithmic_bytes_per_launch": BYTES_PER_BOARD4 * N_BOARDS,
+                         "peak_source": which, "kernel": "step4_kernel_dense<true, false>",
+                         "bytes_per_unit": BYTES_PER_BOARD4 / MOVES, "units_per_launch": N_TRANS},
         }
+        if PAIRS_FORM:
+            PAIRS_FORM["frac_of_hbm_peak"] = PAIRS_FORM["achieved_gbs"] / peak
+            line["step_pairs_form"] = PAIRS_FORM
         line["step_without_shaping"] = no_shaping
         line["expand4"] = expand
         if ro is not None:

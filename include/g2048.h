@@ -87,6 +87,15 @@ int g2048_step(const void* d_lut, const uint64_t* boards_in, const uint8_t* acti
                int32_t* points, uint8_t* flags, uint64_t* shaping, int64_t n, const uint32_t* replay,
                uint64_t seed, uint64_t env0, uint64_t ctr, void* stream);
 
+/* The same step in the form of BASELINE config 2 ("1M random boards x 4 moves"): all four moves of every board, each with its
+ * own spawn.  Transition (b, m) plays move m (0 UP, 1 DOWN, 2 LEFT, 3 RIGHT) on boards_in[b] with the draws of env id
+ * env0 + 4 b + m -- bit for bit what g2048_step returns for the 4 n pairs (boards_in[b], m) -- and the outputs are [n,4] arrays
+ * (16-byte aligned; flags 4-byte aligned).  One thread plays a board's four moves and shares what they have in common (transpose,
+ * largest exponent, before-move potentials and corner rules, empty count): game.py:952-1030 four times per board at ~0.7 of the
+ * instructions.  shaping may be NULL; replay: u32[n,4,2] or NULL. */
+int g2048_step4(const void* d_lut, const uint64_t* boards_in, uint64_t* boards_out, int32_t* points, uint8_t* flags, uint64_t* shaping,
+                int64_t n, const uint32_t* replay, uint64_t seed, uint64_t env0, uint64_t ctr, void* stream);
+
 /* All four moves of every board without spawning: game.py:121-160 simulate_move,
  * game.py:167-184 preview_move_rewards, game.py:295-299 current_valid_directions.
  * succ[n,4] (== board where illegal), points[n,4] (0 where illegal), legal[n] (bit d),

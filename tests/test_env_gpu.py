@@ -455,3 +455,53 @@ def test_c2_full_size_step_matches_oracle_and_the_direct_kernel(env):
         for k in ("boards", "points", "flags", "shaping"):
             assert torch.equal(q[k], r[k][lo:lo + chunk]), (k, lo)
     assert int(r["points"].sum()) == int(want["points"].sum())
+
+
+@pytest.mark.parametrize("n,shaping", [(1, True), (1000, True), (1000, False), (40000, True), (70001, True), (70001, False), (1 << 20, True)])
+def test_step4_equals_step_on_every_board_and_move(n, shaping):
+    """g2048_step4 (the C2 form: one thread plays the four moves of a board and shares their common work) against g2048_step on
+    the 4 n (board, move) pairs with the same env ids -- every output bit for bit -- and, on a subset, against the oracle; both
+    the direct (small n) and the dense-table kernel (4 n >= 2^17), boards with 4096+ tiles (the L2 path) included."""
+    from g2048 import env
+    rng = np.random.default_rng(n)
+    e = rng.integers(1, 12, (n, 16))
+    e[rng.random((n, 16)) < 0.3] = 0
+    big = rng.random(n) < 0.05                                   # a few boards with a 4096..16384 tile
+    e[big, rng.integers(0, 16, int(big.sum()))] = rng.integers(12, 15, int(big.sum()))
+    b = (e.astype(np.uint64) << (np.arange(16, dtype=np.uint64) * np.uint64(4))).sum(axis=1).astype(np.uint64)
+    boards = torch.from_numpy(b.view(np.int64)).cuda()
+    got = env.step4(boards, seed=77, env0=1000, ctr=3, shaping=shaping)
+    want = env.step(boards.repeat_interleave(4), torch.arange(4, dtype=torch.uint8, device="cuda").repeat(n), seed=77, env0=1000, ctr=3,
+                    shaping=shaping)
+    torch.cuda.synchronize()
+    for k in ("boards", "points", "flags") + (("shaping",) if shaping else ()):
+        assert torch.equal(got[k].reshape(-1), want[k]), k
+    m = min(n, 3000)
+    ob, info = O.step_batch(np.repeat(b[:m], 4), np.tile(np.arange(4, dtype=np.uint8), m), seed=77, env0=1000, ctr=3)
+    np.testing.assert_array_equal(got["boards"][:m].reshape(-1).cpu().numpy().view(np.uint64), ob)
+    np.testing.assert_array_equal(got["points"][:m].reshape(-1).cpu().numpy(), info["points"])
+
+
+def test_step4_replay_and_host_stepper():
+    from g2048 import env
+    n = 50000
+    rng = np.random.default_rng(5)
+    e = rng.integers(1, 12, (n, 16))
+    e[rng.random((n, 16)) < 0.3] = 0
+    b = (e.astype(np.uint64) << (np.arange(16, dtype=np.uint64) * np.uint64(4))).sum(axis=1).astype(np.uint64)
+    boards = torch.from_numpy(b.view(np.int64)).cuda()
+    draws = torch.from_numpy(rng.integers(0, 2**32, (n, 4, 2), dtype=np.uint64).astype(np.uint32).view(np.int32)).cuda()
+    got = env.step4(boards, replay=draws)
+    want = env.step(boards.repeat_interleave(4), torch.arange(4, dtype=torch.uint8, device="cuda").repeat(n), replay=draws.reshape(-1, 2))
+    torch.cuda.synchronize()
+    for k in ("boards", "points", "flags", "shaping"):
+        assert torch.equal(got[k].reshape(-1), want[k]), k
+    hs = env.HostStepper4(n, device=0, chunk=1 << 14)
+    h_in = boards.cpu().pin_memory()
+    h_out = dict(boards=torch.empty((n, 4), dtype=torch.int64).pin_memory(), points=torch.empty((n, 4), dtype=torch.int32).pin_memory(),
+                 flags=torch.empty((n, 4), dtype=torch.uint8).pin_memory(), shaping=torch.empty((n, 4), dtype=torch.int64).pin_memory())
+    hs.step(h_in, h_out, seed=9, env0=64, ctr=2)
+    torch.cuda.synchronize()
+    ref = env.step4(boards, seed=9, env0=64, ctr=2)
+    for k in ("boards", "points", "flags", "shaping"):
+        assert torch.equal(h_out[k], ref[k].cpu()), k
