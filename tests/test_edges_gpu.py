@@ -21,6 +21,8 @@ def test_empty_batches_are_no_ops():
     r = env.step(e64, e8)
     assert r["boards"].numel() == 0 and r["shaping"].numel() == 0
     assert env.expand4(e64)["succ"].shape == (0, 4)
+    r4 = env.step4(e64)
+    assert r4["boards"].shape == (0, 4) and r4["shaping"].shape == (0, 4)
     assert env.potentials(e64).shape == (0, 6) and env.encode(e64).shape == (0, 48)
     assert env.potentials_ext(e64, e64).shape == (0, 7)
     a = env.augment(e64, e64, e8, e8, torch.empty((0, 4), device=dev), e8)
@@ -35,9 +37,21 @@ def test_empty_batches_are_no_ops():
     assert float(loss) == 0.0 and stats.tolist() == [0.0] * 4
     assert fused.ln_relu_res(z, torch.ones(8, device=dev), torch.zeros(8, device=dev)).shape == (0, 8)
     pol = rollout.pack_policy(GameMLP(MLPConfig(hidden_dim=64, num_layers=1)).to(dev))
-    for prec in ("fp32", "bf16"):
+    for prec in ("fp32", "bf16", "x3"):
         assert rollout.rollout(pol, e64, 3, seed=1, precision=prec).shape == (3, 0)
         assert rollout.rollout(pol, env.reset(5, device=dev), 0, seed=1, precision=prec).shape == (0, 5)
+    # GameURM: rollout kernels and the update ops
+    from g2048 import urm_ops
+    from g2048.policy import GameURM, GameURMConfig
+    um = GameURM(GameURMConfig(dropout=0.0)).to(dev)
+    upol = rollout.pack_policy(um.eval())
+    for prec in ("x3", "fp16"):
+        assert rollout.rollout(upol, e64, 2, seed=1, precision=prec).shape == (2, 0)
+    assert urm_ops.attention(torch.empty((0, 16, 192), device=dev)).shape == (0, 16, 64)
+    assert urm_ops.residual_norm(torch.empty((0, 64), device=dev), torch.empty((0, 64), device=dev), 1e-5).shape == (0, 64)
+    y = urm_ops.conv_swiglu(torch.empty((0, 16, 120), device=dev), torch.empty((0, 16, 120), device=dev), um.layers[0].mlp.dwconv.weight.detach(),
+                            um.layers[0].mlp.dwconv.bias.detach())
+    assert y.shape == (0, 16, 120)
 
 
 @pytest.mark.parametrize("n", [(1 << 17) - 1, 1 << 17, (1 << 17) + 1, 148 * 1024 + 1, 148 * 2048 - 1])
@@ -72,6 +86,13 @@ def test_bad_arguments_are_reported_not_crashes():
     assert rc == -1 and b"NULL" in lib.g2048_last_error()
     rc = lib.g2048_step(None, None, None, None, None, None, None, -1, None, 0, 0, 0, None)
     assert rc == -1 and b"n < 0" in lib.g2048_last_error()
+    rc = lib.g2048_step4(None, None, None, None, None, None, 5, None, 0, 0, 0, None)
+    assert rc == -1 and b"NULL" in lib.g2048_last_error()
+    b = torch.zeros(8, dtype=torch.int64, device="cuda")
+    odd = torch.zeros(4 * 8 + 1, dtype=torch.uint8, device="cuda")[1:]            # flags not 4-byte aligned
+    with pytest.raises(_lib.G2048Error):
+        _lib.call("g2048_step4", env._ptr(env.lut(torch.device("cuda:0"))), env._ptr(b), env._ptr(torch.zeros((8, 4), dtype=torch.int64, device="cuda")),
+                  env._ptr(torch.zeros((8, 4), dtype=torch.int32, device="cuda")), env._ptr(odd), None, 8, None, 0, 0, 0, None)
     with pytest.raises(ValueError):
         rollout.pack_policy(GameMLP(MLPConfig(hidden_dim=512, num_layers=1)).cuda())
     with pytest.raises(_lib.G2048Error):
