@@ -223,11 +223,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// (one rcp for the pair: 1/a = b / (ab), 1/b = a / (ab); the exponents are capped so that a and b stay finite -- a product that
-// overflows then gives sigmoid = 0 * finite = 0, which is what it rounds to -- the SwiGLU phase is bound by the XU pipe)
+// (one rcp for the pair: 1/a = b / (ab), 1/b = a / (ab) -- the SwiGLU phase is bound by the XU pipe.  The exponents are capped at 63
+// so that the product ab <= 2^126 can neither overflow nor push its reciprocal below the normal range (where .ftz would flush it
+// and zero BOTH sigmoids): beyond x < -43.7 the sigmoid is then 2^-63 instead of something smaller, an error below 1e-17 in
+// x * sigmoid(x).)
 __device__ __forceinline__ float2 silu2(float2 x) {
     const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
-    const float2 d = __fadd2_rn(make_float2(ex2_approx(fminf(t.x, 126.0f)), ex2_approx(fminf(t.y, 126.0f))), make_float2(1.0f, 1.0f));
+    const float2 d = __fadd2_rn(make_float2(ex2_approx(fminf(t.x, 63.0f)), ex2_approx(fminf(t.y, 63.0f))), make_float2(1.0f, 1.0f));
     const float r = rcp_approx(d.x * d.y);
     return __fmul2_rn(x, __fmul2_rn(make_float2(r, r), make_float2(d.y, d.x)));
 }

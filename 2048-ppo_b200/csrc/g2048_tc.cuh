@@ -198,18 +198,20 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 // two fp32 values -> packed fp16 hi terms and packed fp16 lo terms (a in the low half).  SASS: F2FP, 2 x FHFMA
-// (fp32 += fp16 * fp16, sm_100+), F2FP.
+// (fp32 += fp16 * fp16, sm_100+), F2FP.  The conversions saturate (F2FP.SATFINITE, same cost): a value beyond the fp16 range
+// becomes +-65504 (+ a saturated lo term: hi + lo reaches +-131008) instead of an infinity that turns the whole MMA row into NaN --
+// out of range the result is then merely inaccurate, like the fp32 reference's own ill-conditioned regime, not poisoned.
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
     float ra, rb;
     asm("{\n\t.reg .f16 l, u, m;\n\t"
-        "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
+        "cvt.rn.satfinite.f16x2.f32 %0, %4, %3;\n\t"
         "mov.b32 {l, u}, %0;\n\t"
         "mov.b16 m, 0xBC00;\n\t"                 // -1.0
         "fma.rn.f32.f16 %1, l, m, %3;\n\t"
         "fma.rn.f32.f16 %2, u, m, %4;\n\t}"
         : "=&r"(hi), "=f"(ra), "=f"(rb)
         : "f"(a), "f"(b));
-    asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(ra), "f"(rb));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(ra), "f"(rb));
 }
 __device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"

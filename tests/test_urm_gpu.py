@@ -189,3 +189,30 @@ def test_urm_precision_names():
     mlp = rollout.pack_policy(policy.GameMLP(policy.MLPConfig(hidden_dim=64, num_layers=1, dropout=0.0)).cuda().eval())
     with pytest.raises(ValueError):
         rollout.rollout(mlp, boards.clone(), 1, seed=1, precision="fp16")
+
+
+@pytest.mark.parametrize("scale", [4.0, 16.0, 40.0])
+def test_urm_rollout_stays_finite_on_ill_conditioned_weights(scale):
+    """Weights scaled until the fp32 reference itself is ill conditioned (torch fp32 and fp64 differ by 1e-3 at x4, 0.3 at x16) and
+    activations leave the fp16 range of the split operands: the kernel must stay finite (saturating split, capped SiLU exponents) with
+    the reference's pattern of legal actions, and at x4 stay within a small multiple of the reference's own fp32 noise."""
+    from g2048 import env, policy, rollout
+    torch.manual_seed(1)
+    model = policy.GameURM(policy.GameURMConfig(dropout=0.0)).cuda().eval()
+    with torch.no_grad():
+        for layer in model.layers:
+            layer.mlp.gate_up_proj.weight.mul_(scale)
+            layer.mlp.dwconv.weight.mul_(scale)
+            layer.attn.qkv_proj.weight.mul_(scale ** 0.5)
+    boards = env.reset(2000, device=0, seed=3)
+    buf = rollout.rollout(rollout.pack_policy(model), boards, 3, seed=3, precision="x3")
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        logits, v = model(env.encode(buf.boards.reshape(-1)))
+    want = masked_lp(logits, buf.legal)
+    got = buf.logp.reshape(-1, 4)
+    assert not torch.isnan(got).any() and torch.isfinite(buf.value).all()
+    assert torch.equal(torch.isfinite(got), torch.isfinite(want))
+    if scale == 4.0:
+        fin = torch.isfinite(want)
+        assert float((got[fin] - want[fin]).abs().max()) < 2e-2 and float((buf.value.reshape(-1) - v.squeeze(1)).abs().max()) < 2e-2
