@@ -648,6 +648,7 @@ __device__ __forceinline__ void storer(Smem<HP>& S, const Params& p, uint32_t my
     const int L = p.L;
     const size_t tile_bytes = size_t(HP) * 512;                           // 128 samples x HP x 4 B
     uint32_t par = 0;
+    const uint64_t stream_policy = tc::l2_policy_evict_first();
     for (uint32_t t = 0; t < my_tiles; ++t) {
         const size_t tile = size_t(blockIdx.x) + size_t(t) * gridDim.x;
         for (int k = 0; k < 2 * (L + 1); ++k) {                          // h_0 .. h_L, dz_L .. dz_0
@@ -657,8 +658,8 @@ __device__ __forceinline__ void storer(Smem<HP>& S, const Params& p, uint32_t my
             tc::mbar_wait(&S.img_ready, par);
             par ^= 1u;
             if (elect_one()) {
-                tc::bulk_s2g(dst, S.A[0], SM::PART);
-                tc::bulk_s2g(dst + SM::PART, S.A[1], SM::PART);
+                tc::bulk_s2g_hint(dst, S.A[0], SM::PART, stream_policy);       // evict-first: the images are read by the weight-gradient
+                tc::bulk_s2g_hint(dst + SM::PART, S.A[1], SM::PART, stream_policy);   // kernels later, the z scratch by this kernel soon
                 tc::bulk_commit();
                 tc::bulk_wait_read0();
                 tc::mbar_arrive(&S.a_free);
