@@ -490,6 +490,35 @@ def gen_augment(rng):
     print("augment:", out.shape)
 
 
+def gen_onnx():
+    """The reference's shipped browser model (docs/data/model.onnx, written by train.export_model_to_onnx, train.py:33-78):
+    its structure without the weights -> tests/golden/onnx_structure.json, and the outputs of tests/onnx_mini.py's numpy
+    evaluator on it for the inputs of model_best.npz -> tests/golden/onnx_reference.npz.  Checked here, where torch can run the same weights: evaluator == torch forward."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import onnx_mini
+
+    m = onnx_mini.load(os.path.join(REF, "docs", "data", "model.onnx"))
+    json.dump(onnx_mini.structure(m), open(os.path.join(OUT, "onnx_structure.json"), "w"), indent=1)
+    cfg = json.load(open(os.path.join(REF, "docs", "data", "model_config.json")))
+    model = G.GameMLP(G.MLPConfig(**cfg)).eval()
+    init = m["initializers"]
+    mm = iter(sorted(k for k in init if k.startswith("onnx::MatMul_")))
+    sd = {}
+    for k in model.state_dict():
+        sd[k] = torch.from_numpy(init[k].copy()) if k in init else torch.from_numpy(init[next(mm)].T.copy())
+    model.load_state_dict(sd)
+    x = np.load(os.path.join(OUT, "model_best.npz"))["inputs"]
+    out = onnx_mini.run(m, {"board_state": x})
+    with torch.no_grad():
+        lg, v = model(torch.from_numpy(x))
+    assert np.abs(out["action_logits"] - lg.numpy()).max() < 2e-5 and np.abs(out["value"] - v.numpy()).max() < 2e-5
+    best = np.load(os.path.join(OUT, "model_best.npz"))        # the shipped file holds best_model.pt's weights: not stored twice
+    assert all(np.array_equal(best["sd__" + k.replace(".", "__")], t.numpy()) for k, t in sd.items())
+    np.savez_compressed(os.path.join(OUT, "onnx_reference.npz"), action_logits=out["action_logits"], value=out["value"],
+                        config=json.dumps(cfg))
+    print("onnx:", len(m["nodes"]), "nodes,", len(init), "initializers; evaluator == torch forward")
+
+
 if __name__ == "__main__":
     if "--ext-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
@@ -497,6 +526,9 @@ if __name__ == "__main__":
     elif "--augment-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         gen_augment(np.random.default_rng(17))
+    elif "--onnx-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        gen_onnx()
     elif "--urm-only" in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         gen_urm(np.random.default_rng(13))
