@@ -155,6 +155,88 @@ ppo_loss_kernel(const float4* __restrict__ logits, const float* __restrict__ val
     block_reduce_store<4>(acc, partials);
 }
 
+// ------------------------------------------------------------------ KL(old || new) statistic (train.py:577-597, logged only)
+// Per sample: sum over the legal moves of p_old (log p_old - log p_new), both distributions the masked softmax of their logits.
+// partials: [gridDim.x][3] = {sum KL, count, max KL} over valid slots; the final kernel sums the first two in a fixed order
+// and takes the maximum of the third.
+__device__ __forceinline__ void masked_log_softmax4(const float (&l)[4], uint32_t legal, float (&lp)[4]) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (legal >> k & 1u) m = fmaxf(m, l[k]);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (legal >> k & 1u) s += expf(l[k] - m);
+    const float lse = m + logf(s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lp[k] = l[k] - lse;
+}
+__global__ void __launch_bounds__(256)
+masked_kl_kernel(const float4* __restrict__ old_logits, const float4* __restrict__ new_logits, const uint8_t* __restrict__ legal,
+                 const uint8_t* __restrict__ flags, int64_t n, float* __restrict__ kl_out, double* __restrict__ partials) {
+    double acc[2] = {0.0, 0.0};
+    double mx = -INFINITY;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t lg = legal[i] & 15u;
+        if ((flags && !(flags[i] & ROLL_VALID)) || lg == 0u) {
+            if (kl_out) kl_out[i] = 0.f;
+            continue;
+        }
+        const float4 o4 = old_logits[i], n4 = new_logits[i];
+        const float lo_in[4] = {o4.x, o4.y, o4.z, o4.w}, ln_in[4] = {n4.x, n4.y, n4.z, n4.w};
+        float lo[4], ln[4];
+        masked_log_softmax4(lo_in, lg, lo);
+        masked_log_softmax4(ln_in, lg, ln);
+        float kl = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (lg >> k & 1u) kl += expf(lo[k]) * (lo[k] - ln[k]);
+        if (kl_out) kl_out[i] = kl;
+        acc[0] += double(kl);
+        acc[1] += 1.0;
+        mx = fmax(mx, double(kl));
+    }
+    __shared__ double shm[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) shm[warp] = mx;
+    __syncthreads();
+    if (warp == 0) {
+        double x = lane < nwarps ? shm[lane] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+        if (lane == 0) partials[size_t(gridDim.x) * 2 + blockIdx.x] = x;
+    }
+    block_reduce_store<2>(acc, partials);
+}
+__global__ void final_reduce_kl_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+    __shared__ double sh[256];
+    for (int k = 0; k < 2; ++k) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += partials[size_t(i) * 2 + k];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+            if (int(threadIdx.x) < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[k] = sh[0];
+        __syncthreads();
+    }
+    double m = -INFINITY;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) m = fmax(m, partials[size_t(nblocks) * 2 + i]);
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (int(threadIdx.x) < o) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[2] = out[1] > 0.0 ? sh[0] : 0.0;
+}
+
 }  // namespace g2048
 
 using namespace g2048;
@@ -228,6 +310,31 @@ int g2048_ppo_loss(const float* logits, const float* value, const float* old_log
     G2048_CHECK_LAUNCH("ppo_loss_kernel");
     final_reduce_kernel<4><<<1, 256, 0, st>>>(partials, int(blocks), stats_out);
     G2048_CHECK_LAUNCH("final_reduce_kernel");
+    return G2048_OK;
+}
+
+int g2048_masked_kl(const float* old_logits, const float* new_logits, const uint8_t* legal, const uint8_t* flags, int64_t n,
+                    float* kl_out, double* stats_out, void* workspace, void* stream) {
+    G2048_REQUIRE(n >= 0, "g2048_masked_kl: n < 0");
+    G2048_REQUIRE(stats_out != nullptr, "g2048_masked_kl: stats_out is NULL");
+    cudaStream_t st = cudaStream_t(stream);
+    if (n == 0) {                 // empty batch: the data pointers may be NULL
+        G2048_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, 3 * sizeof(double), st));
+        return G2048_OK;
+    }
+    G2048_REQUIRE(old_logits && new_logits && legal && workspace, "g2048_masked_kl: NULL pointer argument");
+    G2048_REQUIRE(((reinterpret_cast<uintptr_t>(old_logits) | reinterpret_cast<uintptr_t>(new_logits)) & 15) == 0,
+                  "g2048_masked_kl: the [n,4] logits must be 16-byte aligned");
+    const int threads = 256;
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = int64_t(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    double* partials = static_cast<double*>(workspace);
+    masked_kl_kernel<<<unsigned(blocks), threads, 0, st>>>(reinterpret_cast<const float4*>(old_logits),
+                                                           reinterpret_cast<const float4*>(new_logits), legal, flags, n, kl_out, partials);
+    G2048_CHECK_LAUNCH("masked_kl_kernel");
+    final_reduce_kl_kernel<<<1, 256, 0, st>>>(partials, int(blocks), stats_out);
+    G2048_CHECK_LAUNCH("final_reduce_kl_kernel");
     return G2048_OK;
 }
 

@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import update
+from . import ppo, update
 
 
 def _epoch_order(n: int) -> torch.Tensor:
@@ -58,16 +58,6 @@ def episodes_to_batch(episodes, device) -> dict:
         logp=f32("policy_logprobs").reshape(n, 4).to(device))
 
 
-def _masked_kl(old_logits, new_logits, legal):
-    """sum_legal p_old (log p_old - log p_new) per sample (train.py:586-597)."""
-    bits = torch.arange(4, device=legal.device)
-    ok = ((legal.long()[:, None] >> bits) & 1) == 1
-    neg = torch.finfo(torch.float32).min
-    lo = torch.log_softmax(torch.where(ok, old_logits, torch.full_like(old_logits, neg)), dim=-1)
-    ln = torch.log_softmax(torch.where(ok, new_logits, torch.full_like(new_logits, neg)), dim=-1)
-    return torch.where(ok, lo.exp() * (lo - ln), torch.zeros_like(lo)).sum(-1)
-
-
 def optimize_batch(model, batch: dict, optimizer, lr_scheduler=None, kl_strength: float = 0.1, critic_strength: float = 1.0,
                    batch_size: int = 32, epochs: int = 1) -> dict:
     """model_optimize_step on an already collated dataset (see episodes_to_batch)."""
@@ -92,7 +82,7 @@ def optimize_batch(model, batch: dict, optimizer, lr_scheduler=None, kl_strength
             current_lr = lr_scheduler.get_last_lr()[0] if lr_scheduler is not None else 0.0
             with torch.no_grad():
                 new_logits, _ = update.forward(model, b["boards"])
-                kl = _masked_kl(old_logits, new_logits, b["legal"])
+                kl_sum, _, kl_max = ppo.masked_kl(old_logits, new_logits, b["legal"])[0].tolist()   # train.py:586-597
             s_ppo, s_vl, s_ent, _ = (float(v) for v in stats.tolist())
             tot["loss"] += -(s_ppo - critic_strength * s_vl + kl_strength * s_ent) / nb
             tot["policy_loss"] += -s_ppo / nb
@@ -100,9 +90,9 @@ def optimize_batch(model, batch: dict, optimizer, lr_scheduler=None, kl_strength
             tot["value_loss"] += critic_strength * s_vl / nb
             tot["grad_norm"] += float(grad_norm)
             tot["entropy"] += s_ent / nb
-            tot["kl_total"] += float(kl.sum())
-            tot["kl_average"] += float(kl.mean())
-            max_kl = max(max_kl, float(kl.max()))
+            tot["kl_total"] += kl_sum
+            tot["kl_average"] += kl_sum / nb
+            max_kl = max(max_kl, kl_max)
             num_batches += 1
     optimizer.scheduler_step()                                                   # train.py:625
     out = {k: v / num_batches for k, v in tot.items()}

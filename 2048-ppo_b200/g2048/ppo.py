@@ -21,6 +21,7 @@ _lib.register("g2048_rtg_advantage_bootstrap",
               [C.c_void_p] * 5 + [C.c_int32, C.c_int64] + [C.c_double] * 6 + [C.c_void_p] * 6 + [C.c_void_p])
 _lib.register("g2048_ppo_loss",
               [C.c_void_p] * 3 + [C.c_int32] + [C.c_void_p] * 5 + [C.c_int64] + [C.c_float] * 4 + [C.c_void_p] * 5)
+_lib.register("g2048_masked_kl", [C.c_void_p] * 4 + [C.c_int64] + [C.c_void_p] * 4)
 _lib.lib().g2048_reduce_workspace_bytes.restype = C.c_int64
 
 _WS: dict[int, torch.Tensor] = {}
@@ -126,6 +127,25 @@ def ppo_loss(logits, value, old_logp, actions, legal, adv, g_norm, *, flags=None
     global sample count when the batch is a shard or a chunk of a larger minibatch)."""
     return _PPOLoss.apply(logits, value, old_logp, actions, legal, flags, adv, g_norm, clip_eps,
                           critic_strength, entropy_strength, n_total)
+
+
+def masked_kl(old_logits, new_logits, legal, *, flags=None, want_per_sample: bool = False):
+    """The KL(old || new) statistic of model_optimize_step (train.py:577-597): per sample the sum over the legal moves of
+    p_old (log p_old - log p_new) with both distributions the masked softmax of their logits [n, 4].
+    Returns (stats, kl): stats = float64[3] device tensor {sum KL, count, max KL} over the valid slots (deterministic
+    reduction), kl = float32 [n] per-sample values or None."""
+    old_logits = _req(old_logits, torch.float32, "old_logits")
+    new_logits = _req(new_logits, torch.float32, "new_logits")
+    n = old_logits.shape[0]
+    assert old_logits.shape == (n, 4) and new_logits.shape == (n, 4)
+    dev = init(old_logits.device)
+    with torch.cuda.device(dev):
+        stats = torch.empty(3, dtype=torch.float64, device=dev)
+        kl = torch.empty(n, dtype=torch.float32, device=dev) if want_per_sample else None
+        _lib.call("g2048_masked_kl", _ptr(old_logits), _ptr(new_logits), _ptr(_req(legal, torch.uint8, "legal")),
+                  _ptr(None if flags is None else _req(flags, torch.uint8, "flags")), n, _ptr(kl), _ptr(stats),
+                  _ptr(_workspace(dev)), _stream())
+    return stats, kl
 
 
 def sample_augmentation(valid: torch.Tensor, upsample_ratio: float, generator: torch.Generator | None = None):

@@ -50,6 +50,8 @@ class TrainConfig:
     chunk: int = 1 << 22           # samples per forward/backward chunk (measured: 4M is 7.6 % faster than 1M; ~26 GB live)
     seed: int = 2048
     zero_heads: bool = True        # train.py:1559-1567
+    kl_stats: bool = False         # the KL(old || new) statistic the reference logs after every optimizer step (train.py:577-597):
+                                   # a second, forward-only pass over the minibatch with the updated weights (GameMLP, fused update)
     dropout: float = 0.0           # Dropout of the residual blocks in the update forward (the reference's MLPConfig default is 0.1)
     bootstrap: bool = True         # the envs persist across train steps (auto-reset), so a buffer usually ends in the middle of
                                    # a game: start the return-to-go scan of such a column from the critic's value of the
@@ -222,13 +224,16 @@ class Trainer:
                 use_fused = self.is_mlp and c.update_matmul == "fused" and update.supported(self.model)
                 packed = update.pack(self.model) if use_fused else None
                 chunk = c.chunk if self.is_mlp else c.urm_chunk
+                want_kl = use_fused and c.kl_stats
+                old_logits = torch.empty((m1 - m0, 4), dtype=torch.float32, device=self.device) if want_kl else None
                 for c0 in range(m0, m1, chunk):
                     sl = slice(c0, min(m1, c0 + chunk)) if order is None else order[c0:min(m1, c0 + chunk)]
                     if use_fused:
                         tot += update.loss_and_grads(self.model, boards[sl], actions[sl], legal[sl], logp[sl], a[sl], g[sl],
                                                      flags=flags[sl], clip_eps=c.clip_eps, critic_strength=c.critic_strength,
                                                      entropy_strength=c.entropy_strength, n_total=max(n_mb_global[m], 1), packed=packed,
-                                                     dropout_p=c.dropout, dropout_seed=self._dropout_seed())
+                                                     dropout_p=c.dropout, dropout_seed=self._dropout_seed(),
+                                                     logits_out=old_logits[c0 - m0:min(m1, c0 + chunk) - m0] if want_kl else None)
                         continue
                     if self.is_mlp:
                         logits, v = fused.mlp_forward(self.model, env.encode(boards[sl]),
@@ -248,12 +253,32 @@ class Trainer:
                 e_ar[1].record()
                 gn = self.bucket.clip_norm_(1.0)                                    # train.py:561
                 self.opt.step()
-                last = (tot, gn)
+                kl = None
+                if want_kl:                       # train.py:577-597: forward of the UPDATED model (train() mode: a fresh dropout mask)
+                    packed = update.pack(self.model)
+                    kl = torch.zeros(3, dtype=torch.float64, device=self.device)
+                    for c0 in range(m0, m1, chunk):
+                        c1 = min(m1, c0 + chunk)
+                        sl = slice(c0, c1) if order is None else order[c0:c1]
+                        new_logits, _ = update.forward(self.model, boards[sl], packed, dropout_p=c.dropout, dropout_seed=self._dropout_seed())
+                        ks, _ = ppo.masked_kl(old_logits[c0 - m0:c1 - m0], new_logits, legal[sl], flags=flags[sl])
+                        kl[:2] += ks[:2]
+                        kl[2] = torch.maximum(kl[2], ks[2])
+                last = (tot, gn, kl)
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
         self.opt.scheduler_step()                                                   # train.py:625
         tot = dp.allreduce_stats(last[0].clone())
         out = ppo.loss_stats(tot, c.critic_strength, c.entropy_strength)
         out["grad_norm"] = float(last[1])
+        if last[2] is not None:
+            kl = last[2]
+            if dp.world()[1] > 1 and dp.COLLECTIVES:
+                mx = kl[2:3].clone()
+                torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
+                dp.allreduce_stats(kl)
+                kl[2] = mx[0]
+            s_kl, n_kl, m_kl = kl.tolist()
+            out.update(kl_total=s_kl, kl_average=s_kl / max(n_kl, 1.0), kl_max=m_kl)
         return out
 
     def finish_moments(self, adv) -> None:

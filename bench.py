@@ -242,7 +242,8 @@ def rollout_section(args, dev, world, rank, barrier):
         return ev0.elapsed_time(ev1) / reps, r
 
     def measure(envs_total, horizon, reps, variants):
-        cfg = tr.TrainConfig(hidden_dim=196, num_layers=2, envs=envs_total, horizon=horizon, zero_heads=False, seed=2048)
+        # the model the reference builds (train.py:1522: MLPConfig default, Dropout(0.1) active in the update forward, train.py:483)
+        cfg = tr.TrainConfig(hidden_dim=196, num_layers=2, envs=envs_total, horizon=horizon, zero_heads=False, seed=2048, dropout=0.1)
         t = tr.Trainer(cfg, dev)
         n_global = envs_total * horizon
         res = {"envs_total": envs_total, "envs_per_gpu": t.B, "horizon": horizon, "timing_reps": reps}
@@ -275,6 +276,18 @@ def rollout_section(args, dev, world, rank, barrier):
         res["phase_ms_rank0"] = {"rollout": times.rollout_ms, "advantage": times.advantage_ms, "update": times.update_ms,
                                  "grad_allreduce_last_step": times.grad_allreduce_ms, "moments_allreduce": times.allreduce_ms}
         res["loss"] = stats["loss"]
+        res["update_dropout"] = cfg.dropout
+        if variants:
+            cfg.dropout = 0.0                     # information only: the same step on a model without dropout
+            ms0, _ = timed(t.train_step, reps)
+            res["train_step_ms_without_dropout"] = max_over_ranks(ms0)
+            res["update_ms_rank0_without_dropout"] = t.times.update_ms
+            cfg.dropout = 0.1
+            cfg.kl_stats = True                   # + the KL(old || new) statistic the reference logs (train.py:577-597): a second,
+            ms1, st1 = timed(t.train_step, reps)  # forward-only pass over the batch with the updated weights
+            res["train_step_ms_with_kl_statistic"] = max_over_ranks(ms1)
+            res["kl_average"] = st1.get("kl_average")
+            cfg.kl_stats = False
         if world > 1:
             # the same train step without the collectives: every rank alone on its shard
             dp.COLLECTIVES = False
@@ -298,7 +311,8 @@ def rollout_section(args, dev, world, rank, barrier):
 
     out = {"model_flops_per_env_step": flops,
            "update": "update_mlp_x3_kernel (one pipelined tcgen05 kernel: GameMLP forward + PPO loss + backward-data, split-fp16 GEMMs, "
-                     "three products per k-step in both directions) + x3_wgrad_kernel weight gradients on the fp16 operand images, Muon+AdamW"}
+                     "three products per k-step in both directions, Philox Dropout(0.1) masks as the reference's update forward has them) + "
+                     "x3_wgrad_kernel weight gradients on the fp16 operand images, Muon+AdamW"}
     if world == 1:
         c3 = measure(args.rollout_envs, args.rollout_steps, 10, True)
         c3["workload"] = (f"c3: GameMLP h=196 L=2 fused rollout, {args.rollout_envs} envs x {args.rollout_steps} steps on one GPU, "

@@ -170,6 +170,14 @@ int g2048_ppo_loss(const float* logits, const float* value, const float* old_log
                    const float* g_norm, int64_t n, float clip_eps, float c_v, float beta_ent, float inv_n,
                    float* dlogits, float* dvalue, double* stats_out, void* workspace, void* stream);
 
+/* train.py:577-597: the KL(old || new) statistic model_optimize_step logs after every optimizer step.  Per sample
+ * sum over the legal moves of p_old (log p_old - log p_new), both the masked softmax of their logits (f32[n,4], 16-byte
+ * aligned; old = the logits of the loss forward, new = a second forward with the updated weights).  kl_out: f32[n]
+ * per-sample values, may be NULL; flags may be NULL (= all valid); slots that are invalid or have no legal move count 0.
+ * stats_out: f64[3] = {sum KL, #valid, max KL}; fixed-order reduction (deterministic). */
+int g2048_masked_kl(const float* old_logits, const float* new_logits, const uint8_t* legal, const uint8_t* flags, int64_t n,
+                    float* kl_out, double* stats_out, void* workspace, void* stream);
+
 /* ---- fused actor-critic rollout ------------------------------------------------------------
  * Replaces the loop of train.py:213-345 (play_game_for_episode) for B environments at once and
  * is what batched_rollout.play_games_batched (the module train.py:30 imports) is built on.

@@ -227,3 +227,71 @@ def test_trainer_with_symmetry_augmentation():
     t0 = tr.Trainer(cfg0, torch.device("cuda:0"))
     t0.train_step()
     assert t0.n_update_samples == n
+
+
+def _ref_masked_kl(old_logits, new_logits, legal):
+    """train.py:586-597 in float64: sum over the legal moves of p_old (log p_old - log p_new)."""
+    ok = ((legal.long()[:, None] >> torch.arange(4)) & 1) == 1
+    lo = torch.masked_fill(old_logits.double(), ~ok, float("-inf")).log_softmax(-1)
+    ln = torch.masked_fill(new_logits.double(), ~ok, float("-inf")).log_softmax(-1)
+    return torch.where(ok, lo.exp() * (lo - ln), torch.zeros_like(lo)).sum(-1)
+
+
+@pytest.mark.parametrize("n", [1, 255, 100003])
+def test_masked_kl_matches_torch_restatement(n):
+    from g2048 import ppo
+    logits, _, _, _, legal, _, _ = _random_loss_inputs(n, n + 5)
+    g = torch.Generator().manual_seed(n)
+    new = logits + 0.3 * torch.randn((n, 4), generator=g)
+    flags = torch.full((n,), 0x80, dtype=torch.uint8)
+    flags[1::5] = 0
+    ref = _ref_masked_kl(logits, new, legal)
+    stats, kl = ppo.masked_kl(logits.cuda(), new.cuda(), legal.cuda(), want_per_sample=True)
+    np.testing.assert_allclose(kl.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=2e-6)
+    s = stats.tolist()
+    np.testing.assert_allclose(s[0], float(ref.sum()), rtol=1e-5, atol=1e-6 * n)
+    assert s[1] == n
+    np.testing.assert_allclose(s[2], float(ref.max()), rtol=1e-4, atol=2e-6)
+    # invalid slots count nothing
+    keep = flags != 0
+    stats_f, kl_f = ppo.masked_kl(logits.cuda(), new.cuda(), legal.cuda(), flags=flags.cuda(), want_per_sample=True)
+    assert float(kl_f.cpu()[~keep].abs().sum()) == 0.0 and stats_f[1].item() == int(keep.sum())
+    if int(keep.sum()):
+        np.testing.assert_allclose(stats_f[0].item(), float(ref[keep].sum()), rtol=1e-5, atol=1e-6 * n)
+        np.testing.assert_allclose(stats_f[2].item(), float(ref[keep].max()), rtol=1e-4, atol=2e-6)
+    # identical distributions: exactly zero; empty batch: zeros
+    z = ppo.masked_kl(logits.cuda(), logits.cuda(), legal.cuda())[0].tolist()
+    assert z[0] == 0.0 and z[2] == 0.0
+    e = ppo.masked_kl(torch.empty((0, 4), device="cuda"), torch.empty((0, 4), device="cuda"), torch.empty(0, dtype=torch.uint8, device="cuda"))
+    assert e[0].tolist() == [0.0, 0.0, 0.0]
+
+
+def test_trainer_kl_statistic():
+    """TrainConfig.kl_stats: the statistic of train.py:577-597 after every optimizer step, from a forward-only pass of the
+    fused kernel with the updated weights; it must not change the training itself."""
+    import copy
+    from g2048 import ppo, trainer as tr, update
+    dev = torch.device("cuda:0")
+    kw = dict(hidden_dim=64, num_layers=2, envs=512, horizon=16, zero_heads=False, minibatches=1, seed=5, warmup_steps=0)
+    t = tr.Trainer(tr.TrainConfig(kl_stats=True, **kw), dev)
+    before = copy.deepcopy(t.model)
+    buf = t.collect()
+    adv = t.advantages(buf)
+    s = t.update(buf, adv)
+    assert 0.0 <= s["kl_average"] <= s["kl_max"] and np.isfinite(s["kl_total"]) and s["kl_average"] > 0.0
+    # by hand: old logits from the weights before the step, new logits from the weights after it, on the recorded boards
+    boards, legal, flags = buf.boards.reshape(-1), buf.legal.reshape(-1), buf.flags.reshape(-1)
+    lo, _ = update.forward(before.eval(), boards)
+    ln, _ = update.forward(t.model.eval(), boards)
+    keep = (flags.cpu() & 0x80) != 0
+    ref = _ref_masked_kl(lo.cpu(), ln.cpu(), legal.cpu())[keep]
+    np.testing.assert_allclose(s["kl_total"], float(ref.sum()), rtol=1e-4)
+    np.testing.assert_allclose(s["kl_average"], float(ref.mean()), rtol=1e-4)
+    np.testing.assert_allclose(s["kl_max"], float(ref.max()), rtol=1e-4)
+    # the same step without the statistic: identical weights afterwards
+    t0 = tr.Trainer(tr.TrainConfig(**kw), dev)
+    b0 = t0.collect()
+    s0 = t0.update(b0, t0.advantages(b0))
+    assert "kl_average" not in s0 and s0["loss"] == s["loss"]
+    for (k, v), (_, v0) in zip(t.model.state_dict().items(), t0.model.state_dict().items()):
+        assert torch.equal(v, v0), k
