@@ -61,7 +61,8 @@ struct Params {
     float clip_eps, c_v, beta_ent, inv_n;
     uint32_t drop_thr;            // dropout (game.py:1042): an element is dropped iff its 16-bit Philox draw < drop_thr; 0 = off
     float drop_scale;             // 1 / (1 - p)
-    uint64_t drop_seed, sample0;  // Philox key; index of this call's first sample in the mask's counter space
+    uint64_t sample0;             // index of this call's first sample in the mask's counter space
+    PhiloxKeys drop_keys;         // the ten round keys of the call's dropout seed (constant-bank operands of the rounds)
     const float* pf;              // fp32 section of the pack
     const uint8_t* img;           // weight k-blocks in consumption order
     uint8_t* h_out;               // [L+1][ntiles] fp16 hi|lo operand images of 128 samples x HP, 4 B / value
@@ -172,13 +173,29 @@ __device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, float a0, 
 // Dropout mask of 8 consecutive columns of one sample in block l (game.py:1038-1046: x + Dropout(ReLU(LN(Linear x)))):
 // one Philox4x32-10 call, counter = (sample index, l, column group), key = the call's dropout seed; column j of the
 // group is KEPT iff the j-th 16-bit lane of the 128 random bits is >= drop_thr = round(p * 65536).  Bit j of the result.
-__device__ __noinline__ uint32_t dropout_keep8(const Params& p, int64_t sample, int l, int col) {
+__device__ __forceinline__ uint32_t dropout_keep8(const Params& p, int64_t sample, int l, int col) {
     const U4 r = philox4x32_10(uint32_t(sample), uint32_t(uint64_t(sample) >> 32), uint32_t(l), uint32_t(col >> 3),
-                               uint32_t(p.drop_seed), uint32_t(p.drop_seed >> 32));
+                               p.drop_keys);
     const uint32_t t2 = p.drop_thr * 0x00010001u;
     const uint32_t a = __vsetgeu2(r.x, t2), b = __vsetgeu2(r.y, t2), c = __vsetgeu2(r.z, t2), d = __vsetgeu2(r.w, t2);   // bits 0, 16
     return (a & 1u) | ((a >> 15) & 2u) | ((b & 1u) << 2) | ((b >> 13) & 8u) | ((c & 1u) << 4) | ((c >> 11) & 32u) | ((d & 1u) << 6) |
            ((d >> 9) & 128u);
+}
+
+// The masks of one thread's columns of block l (its NBF 16-column k-blocks and its quarter of the 4-column units), packed
+// as the epilogues read them: bits 16 i + 8 u + j = column 16 (4 i + part) + 8 u + j, bits 16 NBF + 4 r + j = column
+// 16 (4 NBF + r) + 4 part + j.  Called BEFORE the wait for the stage's MMAs, so that the Philox rounds run under them.
+template <int NBF, int NR>
+__device__ __forceinline__ uint64_t dropout_keep_row(const Params& p, int64_t sample, int l, int part) {
+    uint64_t kb = 0ull;                 // (one call site per kernel; unrolled: the calls are independent dependency chains)
+#pragma unroll
+    for (int i = 0; i < 2 * NBF; ++i) kb |= uint64_t(dropout_keep8(p, sample, l, 16 * (4 * (i >> 1) + part) + 8 * (i & 1))) << (8 * i);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int col = 16 * (4 * NBF + r) + 4 * part;
+        kb |= uint64_t((dropout_keep8(p, sample, l, col) >> (col & 7)) & 0xFu) << (16 * NBF + 4 * r);
+    }
+    return kb;
 }
 
 struct RowCtx {
@@ -230,7 +247,7 @@ __device__ __forceinline__ void store_quad(const RowCtx& c, int blk, const float
 // products (complete on part 0).  Thread columns: blocks 4i + part (16 each) and 4 columns of every remainder block.
 // One copy of the code serves the stem (l == 0: bias b0, no residual, no dropout) and the residual blocks.
 template <int HP, bool DROP>
-__device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCtx& c, int l, float (&o)[5], uint64_t& keep_bits) {
+__device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCtx& c, int l, float (&o)[5], const uint64_t keep_bits) {
     using SM = Smem<HP>;
     constexpr int NBF = SM::NBF, NR = SM::NR;
     const int L = p.L;
@@ -326,11 +343,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             const int col = 16 * blk + 8 * u;
             float x[8];
             if (!STEM) tc::tmem_ld8(c.tX + uint32_t(col), x);
-            uint32_t keep = 0xFFu;
-            if (!STEM && DROP) {
-                keep = dropout_keep8(p, p.sample0 + c.grow, l, col);
-                keep_bits |= uint64_t(keep) << (16 * i + 8 * u);
-            }
+            const uint32_t keep = (!STEM && DROP) ? uint32_t(keep_bits >> (16 * i + 8 * u)) & 0xFFu : 0xFFu;
             if (STEM) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = 0.f;
@@ -353,11 +366,7 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             for (int j = 0; j < 4; ++j) x[j] = tc::tmem_ld_pin(raw[j]);
         }
         if (STEM) x[0] = x[1] = x[2] = x[3] = 0.f;
-        uint32_t keep = 0xFu;
-        if (!STEM && DROP) {
-            keep = (dropout_keep8(p, p.sample0 + c.grow, l, col) >> (col & 7)) & 0xFu;
-            keep_bits |= uint64_t(keep) << (16 * NBF + 4 * r);
-        }
+        const uint32_t keep = (!STEM && DROP) ? uint32_t(keep_bits >> (16 * NBF + 4 * r)) & 0xFu : 0xFu;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float y = fmaf(fmaf(zr[r][j], rstd, shift), gam[col + j], bet[col + j]);
@@ -754,10 +763,11 @@ __global__ void __launch_bounds__(THREADS, 1) update_mlp_x3_kernel(const Params 
             float o[5];
             uint64_t keep1 = 0ull, keep2 = 0ull;                    // dropout masks of this thread's columns in blocks 1 and 2
             for (int l = 0; l <= L; ++l) {                          // z_l is in D once the stage's MMAs are done
+                uint64_t kb = 0ull;
+                if (DROP && l > 0) kb = dropout_keep_row<SM::NBF, SM::NR>(p, p.sample0 + c.grow, l, c.part);   // under the MMAs
                 tc::mbar_wait(&S.mma_done, mma_par);
                 mma_par ^= 1u;
                 tc::fence_after_sync();
-                uint64_t kb = 0ull;
                 fwd_epilogue<HP, DROP>(S, p, c, l, o, kb);
                 if (DROP) {
                     if (l == 1) keep1 = kb;
@@ -1017,7 +1027,7 @@ int g2048_update_mlp_fwd_bwd(const G2048UpdateMlp* u, void* stream) {
     if (u->dropout_p > 0.f) {
         p.drop_thr = uint32_t(u->dropout_p * 65536.0f + 0.5f);
         p.drop_scale = 1.0f / (1.0f - u->dropout_p);
-        p.drop_seed = u->dropout_seed;
+        p.drop_keys = philox_round_keys(u->dropout_seed);
         p.sample0 = u->dropout_sample0;
     }
     const uint8_t* base = static_cast<const uint8_t*>(u->packed);
