@@ -494,6 +494,26 @@ def run_ours(args):
     no_shaping = {"ms_per_launch": ns_ms, "bytes_per_transition": 22, "env_steps_per_sec": world * N_TRANS / (ns_ms * 1e-3),
                   "achieved_gbs": 22 * N_TRANS / (ns_ms * 1e-3) / 1e9, "kernel": "step_kernel_dense<false, false>"}
 
+    # ---- C2 with the spawn draws REPLAYED from a buffer (config 2 as worded: "bit-exact vs game.py on replayed spawns"):
+    # the same kernel reads (u0, u1) per transition -- 8 more input bytes -- instead of running Philox (36 instructions)
+    gen = torch.Generator(device=dev).manual_seed(4096 + rank)
+    rp = [torch.randint(-2 ** 31, 2 ** 31 - 1, (N_BOARDS, 4, 2), generator=gen, device=dev, dtype=torch.int64).to(torch.int32) for _ in range(RING)]
+    rp_graph = capture(lambda k: env.step4(s4_in[k % RING], seed=2048, env0=env0, ctr=1 + k, shaping=True, out=s4_out[k % RING],
+                                           replay=rp[k % RING]), args.steps)
+    barrier()
+    ev0.record()
+    rp_graph.replay()
+    ev1.record()
+    barrier()
+    rp_ms = ev0.elapsed_time(ev1) / args.steps
+    replayed = {"ms_per_launch": rp_ms, "env_steps_per_sec": world * N_TRANS / (rp_ms * 1e-3), "kernel": "step4_kernel_dense<true, true>",
+                "bytes_per_transition": 23, "achieved_gbs": 23 * N_TRANS / (rp_ms * 1e-3) / 1e9,
+                "bytes_per_transition_with_the_draws": 31, "achieved_gbs_with_the_draws": 31 * N_TRANS / (rp_ms * 1e-3) / 1e9,
+                "note": "g2048_step4 with replay != NULL: two u32 draws per transition read from HBM (the reference's own draws in the parity "
+                        "tests) instead of the Philox stream; SURVEY 8(d) counts no bytes for the draws (first pair of figures), the kernel "
+                        "does read them (second pair)"}
+    del rp_graph, rp
+
     # ---- C2 in its 4-move expansion form (g2048_expand4: all four pre-spawn successors per board)
     ex_sets = [dict(succ=torch.empty((N_BOARDS, 4), dtype=torch.int64, device=dev),
                     points=torch.empty((N_BOARDS, 4), dtype=torch.int32, device=dev),
@@ -525,7 +545,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     ex2_ms = ev0.elapsed_time(ev1) / ex_steps
-    expand = {"no_shaping_step": no_shaping, "ms_per_launch": ex_ms, "boards_per_launch": N_BOARDS, "ms_per_launch_on_post_step_boards": ex2_ms,
+    expand = {"no_shaping_step": no_shaping, "replayed_step": replayed, "ms_per_launch": ex_ms, "boards_per_launch": N_BOARDS, "ms_per_launch_on_post_step_boards": ex2_ms,
               "transitions_per_sec": world * N_BOARDS * 4 / (ex_ms * 1e-3),
               "bytes_per_board": 57, "achieved_gbs": 57 * N_BOARDS / (ex_ms * 1e-3) / 1e9,
               "l2": "12 distinct input / output sets (57 MiB each) used round-robin"}
@@ -668,6 +688,9 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
         peak, which = peaks()
         expand["frac_of_hbm_peak"] = expand["achieved_gbs"] / peak
         no_shaping = expand.pop("no_shaping_step")
+        replayed = expand.pop("replayed_step")
+        replayed["frac_of_hbm_peak"] = replayed["achieved_gbs"] / peak
+        replayed["frac_of_hbm_peak_with_the_draws"] = replayed["achieved_gbs_with_the_draws"] / peak
         no_shaping["frac_of_hbm_peak"] = no_shaping["achieved_gbs"] / peak
         expand["large_batch"]["frac_of_hbm_peak"] = expand["large_batch"]["achieved_gbs"] / peak
         achieved = BYTES_PER_BOARD4 * N_BOARDS / (ms_per_step * 1e-3) / 1e9
@@ -691,6 +714,7 @@ def finish(args, world, value, ms_per_step, clocks, e2e_value, e2e_ms, e2e_steps
             PAIRS_FORM["frac_of_hbm_peak"] = PAIRS_FORM["achieved_gbs"] / peak
             line["step_pairs_form"] = PAIRS_FORM
         line["step_without_shaping"] = no_shaping
+        line["step_replayed_draws"] = replayed
         line["expand4"] = expand
         if ro is not None:
             line["rollout"] = ro

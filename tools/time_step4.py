@@ -24,19 +24,20 @@ def boards():
 
 
 ins = [boards() for _ in range(ring)]
-for shaping in (True, False):
+reps = [torch.randint(-2 ** 31, 2 ** 31 - 1, (n, 4, 2), generator=g, device=dev, dtype=torch.int64).to(torch.int32) for _ in range(ring)]
+for shaping, replayed in ((True, False), (False, False), (True, True), (False, True)):
     outs = [dict(boards=torch.empty((n, 4), dtype=torch.int64, device=dev), points=torch.empty((n, 4), dtype=torch.int32, device=dev),
                  flags=torch.empty((n, 4), dtype=torch.uint8, device=dev), shaping=torch.empty((n, 4), dtype=torch.int64, device=dev) if shaping else None)
             for _ in range(ring)]
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for k in range(3):
-            env.step4(ins[k % ring], seed=1, ctr=k, shaping=shaping, out=outs[k % ring])
+            env.step4(ins[k % ring], seed=1, ctr=k, shaping=shaping, out=outs[k % ring], replay=reps[k % ring] if replayed else None)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr, stream=s):
             for k in range(60):
-                env.step4(ins[k % ring], seed=1, ctr=k, shaping=shaping, out=outs[k % ring])
+                env.step4(ins[k % ring], seed=1, ctr=k, shaping=shaping, out=outs[k % ring], replay=reps[k % ring] if replayed else None)
         gr.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -45,5 +46,5 @@ for shaping in (True, False):
         e1.record()
         torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / 60 * 1e3
-    bpb = 8 + 4 * (8 + 4 + 1 + (8 if shaping else 0))
-    print(f"step4 shaping={shaping}: {us:.2f} us per 2^20 boards = {4 * n / us * 1e6:.4g} env-steps/s, {bpb} B/board = {n * bpb / us / 1e3:.1f} GB/s")
+    bpb = 8 + 4 * (8 + 4 + 1 + (8 if shaping else 0) + (8 if replayed else 0))
+    print(f"step4 shaping={shaping} replayed_draws={replayed}: {us:.2f} us per 2^20 boards = {4 * n / us * 1e6:.4g} env-steps/s, {bpb} B/board = {n * bpb / us / 1e3:.1f} GB/s")
