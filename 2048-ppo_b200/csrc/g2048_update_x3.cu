@@ -157,7 +157,7 @@ __device__ __forceinline__ void ld256(const float* p, float* v) {
 // (not inlined, like the Philox call of the dropout mask: the epilogues below are unrolled over a thread's 6-7 column units,
 // and a kernel body of 230 KB spent 38 % of its stall samples waiting for instruction fetches -- ncu, profiles/)
 __device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, float a0, float a1, float a2, float a3, float b0, float b1, float b2,
-                                       float b3, float* dst_a, float* dst_b) {
+                                       float b3, float* dst_a, float* dst_b, float scale = 1.0f) {
     scr[0][lane] = a0; scr[1][lane] = a1; scr[2][lane] = a2; scr[3][lane] = a3;
     scr[4][lane] = b0; scr[5][lane] = b1; scr[6][lane] = b2; scr[7][lane] = b3;
     __syncwarp();
@@ -166,7 +166,7 @@ __device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, float a0, 
     float s = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (seg == 0) red_add(v < 4 ? dst_a + v : dst_b + (v - 4), s);
+    if (seg == 0) red_add(v < 4 ? dst_a + v : dst_b + (v - 4), s * scale);
     __syncwarp();
 }
 
@@ -325,8 +325,12 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
         for (int j = 0; j < 8; ++j) {
             const float y = fmaf(fmaf(zz[j], rstd, shift), gam[col + j], bet[col + j]);
             float r = fmaxf(y, 0.f);
-            if (DROP) r = ((keep >> j) & 1u) ? r * dscale : 0.f;
-            x[j] += r;                 // x = h_{l-1} (0 for the stem)
+            if (DROP) {                // (bit test = one LOP3 with a predicate result; the scale rides on the residual add)
+                r = (keep & (1u << j)) ? r : 0.f;
+                x[j] = fmaf(r, dscale, x[j]);
+            } else {
+                x[j] += r;             // x = h_{l-1} (0 for the stem)
+            }
         }
         if (last) {
 #pragma unroll
@@ -371,8 +375,12 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
         for (int j = 0; j < 4; ++j) {
             const float y = fmaf(fmaf(zr[r][j], rstd, shift), gam[col + j], bet[col + j]);
             float rr = fmaxf(y, 0.f);
-            if (DROP) rr = ((keep >> j) & 1u) ? rr * dscale : 0.f;
-            x[j] += rr;
+            if (DROP) {
+                rr = (keep & (1u << j)) ? rr : 0.f;
+                x[j] = fmaf(rr, dscale, x[j]);
+            } else {
+                x[j] += rr;
+            }
         }
         if (last) {
 #pragma unroll
@@ -444,8 +452,9 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             if (j >= n) break;
             const float x = fmaf(z[j], rstd, shift);
             const float y = fmaf(x, gam[col + j], bet[col + j]);
-            const bool on = DROP ? (y > 0.f && ((keep >> j) & 1u)) : (y > 0.f);
-            const float gj = on ? dh[j] * dscale : 0.f;
+            const bool on = DROP ? (y > 0.f && (keep & (1u << j))) : (y > 0.f);
+            const float gj = on ? dh[j] : 0.f;          // without the dropout scale 1 / (1 - p): everything below is linear in it, so
+                                                        // it is applied once per column sum and once per row (rstd_d in pass B)
             const float t = gj * gam[col + j];
             s1 += t;
             s2 = fmaf(t, x, s2);
@@ -453,8 +462,8 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             gg[j] = gj;
             gx[j] = gj * x;
         }
-        colsum4x2(scr, c.lane, gx[0], gx[1], gx[2], gx[3], gg[0], gg[1], gg[2], gg[3], lnp + col, lnp + HP + col);
-        if (n == 8) colsum4x2(scr, c.lane, gx[4], gx[5], gx[6], gx[7], gg[4], gg[5], gg[6], gg[7], lnp + col + 4, lnp + HP + col + 4);
+        colsum4x2(scr, c.lane, gx[0], gx[1], gx[2], gx[3], gg[0], gg[1], gg[2], gg[3], lnp + col, lnp + HP + col, dscale);
+        if (n == 8) colsum4x2(scr, c.lane, gx[4], gx[5], gx[6], gx[7], gg[4], gg[5], gg[6], gg[7], lnp + col + 4, lnp + HP + col + 4, dscale);
     };
 #pragma unroll
     for (int i = 0; i < NBF; ++i) {
@@ -522,6 +531,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
     wait_a_free(S, p, c);
 
     // ---- pass B: dz_l = rstd * (t - mean(t) - xhat * mean(t * xhat))
+    const float rstd_d = rstd * dscale;
     const bool feeds_gemm = l > 0;
 #pragma unroll
     for (int i = 0; i < NBF; ++i) {
@@ -536,9 +546,9 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             for (int j = 0; j < 8; ++j) {
                 const float x = xh[i][8 * u + j];
                 const float y = fmaf(x, gam[col + j], bet[col + j]);
-                const bool on = DROP ? (y > 0.f && ((keep >> j) & 1u)) : (y > 0.f);
-                const float t = (on ? dh[j] * dscale : 0.f) * gam[col + j];
-                dz[j] = (col + j < h) ? rstd * (t - m1 - x * m2) : 0.f;
+                const bool on = DROP ? (y > 0.f && (keep & (1u << j))) : (y > 0.f);
+                const float t = (on ? dh[j] : 0.f) * gam[col + j];
+                dz[j] = (col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f;
             }
             store_unit<HP>(c, blk, u, dz, !c.valid);
         }
@@ -556,9 +566,9 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
         for (int j = 0; j < 4; ++j) {
             const float x = xhr[r][j], dhj = tc::tmem_ld_pin(raw[j]);
             const float y = fmaf(x, gam[col + j], bet[col + j]);
-            const bool on = DROP ? (y > 0.f && ((keep >> j) & 1u)) : (y > 0.f);
-            const float t = (on ? dhj * dscale : 0.f) * gam[col + j];
-            dz[j] = (col + j < h) ? rstd * (t - m1 - x * m2) : 0.f;
+            const bool on = DROP ? (y > 0.f && (keep & (1u << j))) : (y > 0.f);
+            const float t = (on ? dhj : 0.f) * gam[col + j];
+            dz[j] = (col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f;
         }
         store_quad<HP>(c, blk, dz, !c.valid);
         if (feeds_gemm) warp_arrive(&S.rnd_ready[NBF + r], c.lane);

@@ -505,3 +505,27 @@ def test_step4_replay_and_host_stepper():
     ref = env.step4(boards, seed=9, env0=64, ctr=2)
     for k in ("boards", "points", "flags", "shaping"):
         assert torch.equal(h_out[k], ref[k].cpu()), k
+
+
+def test_c2_full_size_step4_on_replayed_draws_matches_oracle(env):
+    """BASELINE config 2 as it is worded -- 2^20 random boards x 4 moves, bit-exact on REPLAYED spawn draws -- through
+    g2048_step4 (the kernel `bench.py` times, replay form): every output of the 4 194 304 transitions against the oracle."""
+    nb = 1 << 20
+    b = random_boards(nb, 4096)
+    rng = np.random.default_rng(31)
+    draws = rng.integers(0, 2**32, (nb, 4, 2), dtype=np.uint64).astype(np.uint32)
+    draws[::97, :, 1] = 3865470566                       # the threshold pair of the 2 / 4 decision (game.py:937)
+    draws[1::97, :, 1] = 3865470567
+    got = env.step4(dev_boards(b), replay=torch.from_numpy(draws.view(np.int32)).cuda())
+    torch.cuda.synchronize()
+    want_b, want = O.step_batch(np.repeat(b, 4), np.tile(np.arange(4, dtype=np.uint8), nb), replay=draws.reshape(-1, 2))
+    assert want["overflow"].sum() == 0
+    np.testing.assert_array_equal(host_u64(got["boards"].reshape(-1)), want_b)
+    np.testing.assert_array_equal(got["points"].reshape(-1).cpu().numpy(), want["points"])
+    fl = got["flags"].reshape(-1).cpu().numpy()
+    np.testing.assert_array_equal(fl & 0x0F, want["legal_after"])
+    np.testing.assert_array_equal((fl >> 4) & 1, want["done"])
+    np.testing.assert_array_equal((fl >> 5) & 1, want["invalid"])
+    sh = env.decode_shaping(got["shaping"].reshape(-1).cpu().numpy())
+    for k in SH_KEYS:
+        np.testing.assert_array_equal(sh[k], want[k], err_msg=k)

@@ -7,6 +7,7 @@ from test_update_fused_gpu import _model, _boards, _samples
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 128 * 8
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+drop = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0      # Dropout(p) of the update forward (the reference's model: 0.1)
 m = _model(196, 2, 1)
 boards = _boards(n, 2)
 old, actions, legal, adv, g_norm = _samples(n, 3)
@@ -15,7 +16,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 for i in range(reps):
     m.zero_grad()
     e0.record()
-    update.loss_and_grads(m, boards, actions, legal, old, adv, g_norm, packed=packed)
+    update.loss_and_grads(m, boards, actions, legal, old, adv, g_norm, packed=packed, dropout_p=drop, dropout_seed=7)
     e1.record()
     torch.cuda.synchronize()
-    print(f"n={n}: {e0.elapsed_time(e1):.3f} ms")
+    print(f"n={n} dropout={drop}: {e0.elapsed_time(e1):.3f} ms")
