@@ -93,6 +93,14 @@ def test_bad_arguments_are_reported_not_crashes():
     with pytest.raises(_lib.G2048Error):
         _lib.call("g2048_step4", env._ptr(env.lut(torch.device("cuda:0"))), env._ptr(b), env._ptr(torch.zeros((8, 4), dtype=torch.int64, device="cuda")),
                   env._ptr(torch.zeros((8, 4), dtype=torch.int32, device="cuda")), env._ptr(odd), None, 8, None, 0, 0, 0, None)
+    from g2048 import ppo  # noqa: F401  (registers g2048_masked_kl)
+    st = torch.zeros(3, dtype=torch.float64, device="cuda")
+    rc = lib.g2048_masked_kl(None, None, None, None, 5, None, env._ptr(st), None, None)
+    assert rc == -1 and b"NULL" in lib.g2048_last_error()
+    rc = lib.g2048_masked_kl(None, None, None, None, -2, None, env._ptr(st), None, None)
+    assert rc == -1 and b"n < 0" in lib.g2048_last_error()
+    rc = lib.g2048_masked_kl(None, None, None, None, 0, None, None, None, None)
+    assert rc == -1 and b"stats_out" in lib.g2048_last_error()
     with pytest.raises(ValueError):
         rollout.pack_policy(GameMLP(MLPConfig(hidden_dim=512, num_layers=1)).cuda())
     with pytest.raises(_lib.G2048Error):
