@@ -244,7 +244,11 @@ class HostStepper4:
                                shaping=torch.empty((c, 4), dtype=torch.int64, device=self.dev) if shaping else None)
                           for _ in range(streams)]
 
-    def step(self, h_boards, h_out: dict, *, seed: int = 0, env0: int = 0, ctr: int = 0) -> dict:
+    def step(self, h_boards, h_out: dict, *, seed: int = 0, env0: int = 0, ctr: int = 0, join: bool = True) -> dict:
+        """join=False: the call only enqueues (uploads, kernels, downloads on the stepper's own streams) and the caller's stream
+        does not wait for it -- consecutive steps then overlap (the upload and kernel of step k+1 run under the download of step
+        k; a device slot is reused in stream order, so there is no race on the device) and `join()` makes the current stream
+        wait for everything enqueued so far.  The caller keeps one set of host buffers per step in flight."""
         for t in (h_boards, *[v for v in h_out.values() if v is not None]):
             if t.is_cuda or not t.is_pinned():
                 raise ValueError("HostStepper4 works on pinned host tensors")
@@ -266,9 +270,15 @@ class HostStepper4:
                 h_out["flags"][lo:hi].copy_(sl["flags"][:m], non_blocking=True)
                 if self.shaping:
                     h_out["shaping"][lo:hi].copy_(sl["shaping"][:m], non_blocking=True)
+        if join:
+            self.join()
+        return h_out
+
+    def join(self) -> None:
+        """The current stream waits for every step enqueued so far."""
+        cur = torch.cuda.current_stream(self.dev)
         for st in self.streams:
             cur.wait_stream(st)
-        return h_out
 
 
 def expand4(boards: torch.Tensor, *, want_max_tile: bool = False, out: dict | None = None) -> dict:

@@ -629,13 +629,17 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
 
     e2e_steps = max(3, min(args.steps, 20))
 
-    def run(fn):
+    def run(fn, after=None):
         for w in range(3):
             fn(w)
+        if after:
+            after()
         barrier()
         ev0.record()
         for k in range(e2e_steps):
             fn(k)
+        if after:
+            after()                    # the current stream waits for every enqueued step: the downloads end inside the timed region
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -647,6 +651,12 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
 
     pairs_ms = run(e2e_step_pairs)
     e2e_ms = run(e2e_step)
+    # the same steps enqueued without a join between them (HostStepper4.step(join=False) ... join()): the upload and kernel of step
+    # k + 1 run under the download of step k; two sets of host output buffers, as a consumer of a streaming API would hold
+    h_out4b = {k: torch.empty_like(v).pin_memory() for k, v in h_out4.items()}
+    pipe_ms = run(lambda k: stepper4.step(h_boards4, (h_out4, h_out4b)[k % 2], seed=2048, env0=env0, ctr=3000 + k, join=False), after=stepper4.join)
+    del h_out4b
+    joined_ms, e2e_ms = e2e_ms, pipe_ms          # headline: the streaming use of the API; the per-step-joined call beside it
     e2e_value = world * N_TRANS * e2e_steps / (e2e_ms * 1e-3)
     # information only: the same call without the shaping record (13 B instead of 21 B per transition device->host) -- the
     # device->host direction is what bounds this leg
@@ -666,9 +676,14 @@ def e2e_section(args, dev, world, rank, barrier, sets, env0):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ns_ms = float(t.item())
     global E2E_EXTRA
-    E2E_EXTRA = {"api": "g2048.env.HostStepper4.step (g2048_step4 on pinned host buffers, 2^18-board chunks on 2 streams)",
+    E2E_EXTRA = {"api": "g2048.env.HostStepper4.step(join=False) x K, then join() (g2048_step4 on pinned host buffers, 2^18-board chunks on 2 streams; "
+                        "every step uploads its boards and downloads all its outputs; consecutive steps overlap on the stepper's streams, two sets "
+                        "of host output buffers)",
                  "pcie_d2h_gbs_per_gpu": N_TRANS * 21 * e2e_steps / (e2e_ms * 1e-3) / 1e9,
                  "pcie_h2d_gbs_per_gpu": N_BOARDS * 8 * e2e_steps / (e2e_ms * 1e-3) / 1e9,
+                 "joined_per_step": {"value": world * N_TRANS * e2e_steps / (joined_ms * 1e-3), "ms_per_step": joined_ms / e2e_steps,
+                                     "pcie_d2h_gbs_per_gpu": N_TRANS * 21 * e2e_steps / (joined_ms * 1e-3) / 1e9,
+                                     "api": "HostStepper4.step(join=True): the caller's stream waits for every step before the next one is enqueued"},
                  "pairs_form": {"value": world * N_TRANS * e2e_steps / (pairs_ms * 1e-3), "h2d_bytes_per_step": N_TRANS * 9, "d2h_bytes_per_step": N_TRANS * 21,
                                 "api": "g2048.env.HostStepper.step (g2048_step on (board, action) pairs)"},
                  "without_shaping_record": {"value": world * N_TRANS * e2e_steps / (ns_ms * 1e-3), "d2h_bytes_per_step": N_TRANS * 13,

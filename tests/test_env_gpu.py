@@ -529,3 +529,26 @@ def test_c2_full_size_step4_on_replayed_draws_matches_oracle(env):
     sh = env.decode_shaping(got["shaping"].reshape(-1).cpu().numpy())
     for k in SH_KEYS:
         np.testing.assert_array_equal(sh[k], want[k], err_msg=k)
+
+
+def test_host_stepper4_pipelined_steps_equal_joined_steps():
+    """HostStepper4.step(join=False): consecutive steps overlap on the stepper's streams; after join() every step's outputs are
+    what the joined call returns."""
+    from g2048 import env
+    n = 70001
+    b = random_boards(n, 77)
+    h_in = torch.from_numpy(b.view(np.int64)).pin_memory()
+    mk = lambda: dict(boards=torch.empty((n, 4), dtype=torch.int64).pin_memory(), points=torch.empty((n, 4), dtype=torch.int32).pin_memory(),
+                      flags=torch.empty((n, 4), dtype=torch.uint8).pin_memory(), shaping=torch.empty((n, 4), dtype=torch.int64).pin_memory())
+    hs = env.HostStepper4(n, device=0, chunk=1 << 13)
+    outs = [mk() for _ in range(3)]
+    for k in range(3):
+        hs.step(h_in, outs[k], seed=3, env0=10, ctr=k, join=False)
+    hs.join()
+    torch.cuda.synchronize()
+    want = mk()
+    for k in range(3):
+        hs.step(h_in, want, seed=3, env0=10, ctr=k)
+        torch.cuda.synchronize()
+        for key in want:
+            assert torch.equal(outs[k][key], want[key]), (k, key)
