@@ -170,6 +170,21 @@ __device__ __forceinline__ void colsum4x2(float (*scr)[32], int lane, float a0, 
     __syncwarp();
 }
 
+// v if (bit `mask` of keep is set and y > 0) else 0 -- the ReLU gate and the dropout mask in three instructions (a LOP3 that
+// sets a predicate, an FSETP that ANDs with it, an FSEL).  Written in PTX: the C form `(keep & (1u << j)) && y > 0.f` is
+// canonicalised into shift / and / compare / select / compare / select, six instructions per element (SASS, profiles/).
+__device__ __forceinline__ float gate_keep_pos(float y, float v, uint32_t keep, uint32_t mask) {
+    float r;
+    asm("{\n\t.reg .pred pk, pg;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %3, %4;\n\t"
+        "setp.ne.u32 pk, t, 0;\n\t"
+        "setp.gt.and.f32 pg, %1, 0f00000000, pk;\n\t"
+        "selp.f32 %0, %2, 0f00000000, pg;\n\t}"
+        : "=f"(r)
+        : "f"(y), "f"(v), "r"(keep), "r"(mask));
+    return r;
+}
+
 // Dropout mask of 8 consecutive columns of one sample in block l (game.py:1038-1046: x + Dropout(ReLU(LN(Linear x)))):
 // one Philox4x32-10 call, counter = (sample index, l, column group), key = the call's dropout seed; column j of the
 // group is KEPT iff the j-th 16-bit lane of the 128 random bits is >= drop_thr = round(p * 65536).  Bit j of the result.
@@ -178,8 +193,8 @@ __device__ __forceinline__ uint32_t dropout_keep8(const Params& p, int64_t sampl
                                p.drop_keys);
     const uint32_t t2 = p.drop_thr * 0x00010001u;
     const uint32_t a = __vsetgeu2(r.x, t2), b = __vsetgeu2(r.y, t2), c = __vsetgeu2(r.z, t2), d = __vsetgeu2(r.w, t2);   // bits 0, 16
-    return (a & 1u) | ((a >> 15) & 2u) | ((b & 1u) << 2) | ((b >> 13) & 8u) | ((c & 1u) << 4) | ((c >> 11) & 32u) | ((d & 1u) << 6) |
-           ((d >> 9) & 128u);
+    const uint32_t t = a + 4u * b + 16u * c + 64u * d;       // lanes 0 / 1 of a, b, c, d at bits 0, 2, 4, 6 / 16, 18, 20, 22 (three IMADs)
+    return (t & 0x55u) | ((t >> 15) & 0xAAu);
 }
 
 // The masks of one thread's columns of block l (its NBF 16-column k-blocks and its quarter of the 4-column units), packed
@@ -324,12 +339,10 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float y = fmaf(fmaf(zz[j], rstd, shift), gam[col + j], bet[col + j]);
-            float r = fmaxf(y, 0.f);
-            if (DROP) {                // (bit test = one LOP3 with a predicate result; the scale rides on the residual add)
-                r = (keep & (1u << j)) ? r : 0.f;
-                x[j] = fmaf(r, dscale, x[j]);
+            if (DROP) {                // ReLU and mask in one gate; the 1 / (1 - p) scale rides on the residual add
+                x[j] = fmaf(gate_keep_pos(y, y, keep, 1u << j), dscale, x[j]);
             } else {
-                x[j] += r;             // x = h_{l-1} (0 for the stem)
+                x[j] += fmaxf(y, 0.f); // x = h_{l-1} (0 for the stem)
             }
         }
         if (last) {
@@ -374,12 +387,10 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float y = fmaf(fmaf(zr[r][j], rstd, shift), gam[col + j], bet[col + j]);
-            float rr = fmaxf(y, 0.f);
             if (DROP) {
-                rr = (keep & (1u << j)) ? rr : 0.f;
-                x[j] = fmaf(rr, dscale, x[j]);
+                x[j] = fmaf(gate_keep_pos(y, y, keep, 1u << j), dscale, x[j]);
             } else {
-                x[j] += rr;
+                x[j] += fmaxf(y, 0.f);
             }
         }
         if (last) {
@@ -452,9 +463,9 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             if (j >= n) break;
             const float x = fmaf(z[j], rstd, shift);
             const float y = fmaf(x, gam[col + j], bet[col + j]);
-            const bool on = DROP ? (y > 0.f && (keep & (1u << j))) : (y > 0.f);
-            const float gj = on ? dh[j] : 0.f;          // without the dropout scale 1 / (1 - p): everything below is linear in it, so
-                                                        // it is applied once per column sum and once per row (rstd_d in pass B)
+            // (without the dropout scale 1 / (1 - p): everything below is linear in it, so it is applied once per column sum and
+            // once per row -- rstd_d in pass B)
+            const float gj = DROP ? gate_keep_pos(y, dh[j], keep, 1u << j) : (y > 0.f ? dh[j] : 0.f);
             const float t = gj * gam[col + j];
             s1 += t;
             s2 = fmaf(t, x, s2);
@@ -546,8 +557,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             for (int j = 0; j < 8; ++j) {
                 const float x = xh[i][8 * u + j];
                 const float y = fmaf(x, gam[col + j], bet[col + j]);
-                const bool on = DROP ? (y > 0.f && (keep & (1u << j))) : (y > 0.f);
-                const float t = (on ? dh[j] : 0.f) * gam[col + j];
+                const float t = (DROP ? gate_keep_pos(y, dh[j], keep, 1u << j) : (y > 0.f ? dh[j] : 0.f)) * gam[col + j];
                 dz[j] = (col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f;
             }
             store_unit<HP>(c, blk, u, dz, !c.valid);
@@ -566,8 +576,7 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
         for (int j = 0; j < 4; ++j) {
             const float x = xhr[r][j], dhj = tc::tmem_ld_pin(raw[j]);
             const float y = fmaf(x, gam[col + j], bet[col + j]);
-            const bool on = DROP ? (y > 0.f && (keep & (1u << j))) : (y > 0.f);
-            const float t = (on ? dhj : 0.f) * gam[col + j];
+            const float t = (DROP ? gate_keep_pos(y, dhj, keep, 1u << j) : (y > 0.f ? dhj : 0.f)) * gam[col + j];
             dz[j] = (col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f;
         }
         store_quad<HP>(c, blk, dz, !c.valid);
