@@ -553,12 +553,15 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
             float dh[8], dz[8];
             tc::tmem_ld8(c.tX + uint32_t(col), dh);
             const uint32_t keep = uint32_t(keep_bits >> (16 * i + 8 * u)) & 0xFFu;
+            // padded columns (>= h, a multiple of 4) get dz = 0: the factor is chosen per half unit instead of a select per element
+            const float rs[2] = {col + 4 <= h ? rstd_d : 0.f, col + 8 <= h ? rstd_d : 0.f};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float x = xh[i][8 * u + j];
                 const float y = fmaf(x, gam[col + j], bet[col + j]);
                 const float t = (DROP ? gate_keep_pos(y, dh[j], keep, 1u << j) : (y > 0.f ? dh[j] : 0.f)) * gam[col + j];
-                dz[j] = (col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f;
+                // (measured: the factor form is 0.25 ms per chunk faster in the DROP kernel and 0.3 ms slower in the other one)
+                dz[j] = DROP ? rs[j >> 2] * (t - m1 - x * m2) : ((col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f);
             }
             store_unit<HP>(c, blk, u, dz, !c.valid);
         }
@@ -572,12 +575,13 @@ __device__ __forceinline__ void bwd_epilogue(Smem<HP>& S, const Params& p, RowCt
         tc::tmem_ld4_issue(c.tX + uint32_t(col), raw);
         tc::tmem_ld_wait_all();
         const uint32_t keep = uint32_t(keep_bits >> (16 * NBF + 4 * r)) & 0xFu;
+        const float rs = col + 4 <= h ? rstd_d : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float x = xhr[r][j], dhj = tc::tmem_ld_pin(raw[j]);
             const float y = fmaf(x, gam[col + j], bet[col + j]);
             const float t = (DROP ? gate_keep_pos(y, dhj, keep, 1u << j) : (y > 0.f ? dhj : 0.f)) * gam[col + j];
-            dz[j] = (col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f;
+            dz[j] = DROP ? rs * (t - m1 - x * m2) : ((col + j < h) ? rstd_d * (t - m1 - x * m2) : 0.f);
         }
         store_quad<HP>(c, blk, dz, !c.valid);
         if (feeds_gemm) warp_arrive(&S.rnd_ready[NBF + r], c.lane);
