@@ -209,7 +209,9 @@ __device__ __forceinline__ void epilogue(Smem<HP>& S, const RowCtx& c, int h, co
     const float tsq = (S.red[1][0][c.row] + S.red[1][1][c.row]) + (S.red[1][2][c.row] + S.red[1][3][c.row]);
     const float mean = tsum * inv_h;
     const float var = fmaxf(tsq * inv_h - mean * mean, 0.f);
-    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    // rsqrt + one Newton step (within an ulp of 1 / sqrt; the IEEE divide and square root are ~25 instructions per row thread)
+    const float ve = var + 1e-5f, r0 = rsqrtf(ve);
+    const float rstd = r0 * fmaf(-0.5f * ve, r0 * r0, 1.5f);
     const float2 rstd2 = make_float2(rstd, rstd), shift2 = make_float2(-mean * rstd, -mean * rstd);
     float2 o2[5];
 #pragma unroll

@@ -320,7 +320,9 @@ __device__ __forceinline__ void fwd_epilogue(Smem<HP>& S, const Params& p, RowCt
     const float mean = ((S.red[0][0][c.row] + S.red[0][1][c.row]) + (S.red[0][2][c.row] + S.red[0][3][c.row])) * inv_h;
     const float msq = ((S.red[1][0][c.row] + S.red[1][1][c.row]) + (S.red[1][2][c.row] + S.red[1][3][c.row])) * inv_h;
     const float var = fmaxf(msq - mean * mean, 0.f);
-    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    // rsqrt + one Newton step (within an ulp of 1 / sqrt; the IEEE divide and square root are ~25 instructions per row thread)
+    const float ve = var + 1e-5f, r0 = rsqrtf(ve);
+    const float rstd = r0 * fmaf(-0.5f * ve, r0 * r0, 1.5f);
     const float shift = -mean * rstd;       // xhat = z * rstd + shift, the same expression in the backward pass
     if (c.part == 0) {
         S.stats[l][0][c.row] = mean;
