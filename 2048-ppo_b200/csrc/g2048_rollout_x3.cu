@@ -21,6 +21,13 @@
 #include "g2048_rollout_tail.cuh"
 #include "g2048_tc.cuh"
 
+// Softmax / log / divide of the sampling tail through the hardware ex2 / lg2 / rcp units (one thread per env walks this chain while
+// the other three wait: 8 % of the C3 rollout time with the IEEE library functions).  Measured (tools/x3_tail_precision.py, three
+// models): the largest log-prob / value / entropy distances from the torch fp32 and float64 policies are the SAME to three digits
+// with either form -- what separates the kernel from torch is the fp32 rounding of the trunk, not these functions.
+#ifndef G2048_X3_FAST_TAIL
+#define G2048_X3_FAST_TAIL true
+#endif
 namespace g2048 {
 namespace x3 {
 
@@ -567,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                 const int64_t ri = int64_t(t) * p.B + env;
                 if (owner && alive) {
                     TailState ts;
-                    tail_softmax_sample<false>(p, ri, lm, o, S.xch[row].draw[2], ts);
+                    tail_softmax_sample<G2048_X3_FAST_TAIL>(p, ri, lm, o, S.xch[row].draw[2], ts);
                     const MovePre m = S.pre[row][ts.a];
                     ts.u0 = S.xch[row].draw[0];
                     ts.u1 = S.xch[row].draw[1];
@@ -576,7 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) rollout_mlp_x3_kernel(RolloutParam
                     ts.valid = (m.meta & 1u) != 0u;
                     ts.ovf = (m.meta & 2u) != 0u;
                     ts.max_tile = int(m.meta >> 8);
-                    const Board next = tail_spawn<false>(board, ts);
+                    const Board next = tail_spawn<G2048_X3_FAST_TAIL>(board, ts);
                     tail_record(p, ri, board, ts, make_uint2(S.xch[row].pb[0], S.xch[row].pb[1]), make_uint2(m.pa[0], m.pa[1]));
                     board = next;
                     if (ts.flags & FLAG_DONE) {
