@@ -37,8 +37,9 @@ struct TailState {
 template <bool FAST = true>
 __device__ __forceinline__ void tail_sample_and_move(const RolloutParams& p, const LutGlobal& lut, int64_t ri, int64_t env, uint64_t ctr,
                                                      uint32_t lm, const float (&o)[5], Board board, TailState& ts) {
-    // FAST: exp / log / divide as the hardware approximations (ex2 / lg2 / rcp, ~1e-6 relative) for the bf16 kernel,
-    // whose logits already carry bf16 GEMM error (~1e-2); the fp32-grade kernels keep expf / logf.  Only what the
+    // FAST: exp / log / divide as the hardware approximations (ex2 / lg2 / rcp, ~1e-6 relative): the bf16 kernel, whose logits
+    // already carry bf16 GEMM error (~1e-2), and since its measurement (tools/x3_tail_precision.py: no difference in the
+    // distance from torch) the x3 kernel; the fp32 FFMA kernel keeps expf / logf.  Only what the
     // sample needs comes before the move; log-probs and entropy are finished in tail_spawn, off the critical path.
     float mx = -INFINITY;
 #pragma unroll
