@@ -285,9 +285,10 @@ def test_trainer_kl_statistic():
     ln, _ = update.forward(t.model.eval(), boards)
     keep = (flags.cpu() & 0x80) != 0
     ref = _ref_masked_kl(lo.cpu(), ln.cpu(), legal.cpu())[keep]
-    np.testing.assert_allclose(s["kl_total"], float(ref.sum()), rtol=1e-4)
-    np.testing.assert_allclose(s["kl_average"], float(ref.mean()), rtol=1e-4)
-    np.testing.assert_allclose(s["kl_max"], float(ref.max()), rtol=1e-4)
+    # (a per-sample KL of ~1e-4 is a difference of nearly equal fp32 log-probs: ~1e-7 absolute)
+    np.testing.assert_allclose(s["kl_total"], float(ref.sum()), rtol=1e-3)
+    np.testing.assert_allclose(s["kl_average"], float(ref.mean()), rtol=1e-3)
+    np.testing.assert_allclose(s["kl_max"], float(ref.max()), rtol=1e-3, atol=2e-6)
     # the same step without the statistic: identical weights afterwards
     t0 = tr.Trainer(tr.TrainConfig(**kw), dev)
     b0 = t0.collect()
