@@ -21,7 +21,7 @@ def _free_port():
 
 def _cfg():
     from g2048 import trainer as tr
-    return tr.TrainConfig(hidden_dim=64, num_layers=2, envs=1024, horizon=24, chunk=8192, zero_heads=False, seed=5)
+    return tr.TrainConfig(hidden_dim=64, num_layers=2, envs=1024, horizon=24, chunk=8192, zero_heads=False, seed=5, kl_stats=True)
 
 
 def _worker(rank, world, port, out_dir):
@@ -37,6 +37,7 @@ def _worker(rank, world, port, out_dir):
     stats = [t.train_step() for _ in range(2)]
     sd = {k: v.cpu().numpy() for k, v in t.model.state_dict().items()}
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=np.array([s["loss"] for s in stats]),
+             kl=np.array([[s["kl_total"], s["kl_average"], s["kl_max"]] for s in stats]),
              mom=np.array([t.moments.mu, t.moments.m2]), boards=t.boards.cpu().numpy(), **sd)
     dist.destroy_process_group()
 
@@ -52,6 +53,9 @@ def test_two_rank_step_matches_single_gpu(tmp_path):
     # rollouts are bit-identical (shard invariance), so are the sharded final boards
     np.testing.assert_array_equal(np.concatenate([r[0]["boards"], r[1]["boards"]]), t.boards.cpu().numpy())
     np.testing.assert_allclose(r[0]["loss"], [s["loss"] for s in stats], rtol=1e-4)
+    # the KL statistic is global (sum and count all-reduced, the maximum max-reduced) and the same on both ranks
+    np.testing.assert_array_equal(r[0]["kl"], r[1]["kl"])
+    np.testing.assert_allclose(r[0]["kl"], [[s["kl_total"], s["kl_average"], s["kl_max"]] for s in stats], rtol=2e-2, atol=1e-6)
     np.testing.assert_allclose(r[0]["mom"], [t.moments.mu, t.moments.m2], rtol=1e-9)
     np.testing.assert_array_equal(r[0]["mom"], r[1]["mom"])
     for k, v in t.model.state_dict().items():
