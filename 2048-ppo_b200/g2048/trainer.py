@@ -59,9 +59,10 @@ class TrainConfig:
                                    # low).  False = the reference's truncation, as for an episode cut by max_steps.
     upsample_ratio: float = 0.0    # symmetry augmentation (train.py:774-881; the README recipe uses 0.25): that share of the
                                    # recorded steps is drawn and mirrored / rotated copies join the update batch
-    rollout_precision: str = "auto"   # "fp32" FFMA, "bf16" tcgen05, "auto" = bf16 at large env batch
+    rollout_precision: str = "auto"   # "fp32" FFMA, "x3" split-fp16 tcgen05 (fp32 grade), "bf16" tcgen05 (a labelled variant, ~1e-2);
+                                      # "auto" = x3 from rollout.TC_MIN_ENVS envs per GPU up, else fp32
     update_matmul: str = "fused"      # the update's forward/backward: "fused" = one tcgen05 kernel for forward + loss + backward-data
-                                      # and x3 tensor-core weight gradients (g2048.update; split-bf16, ~1e-5), "x3" = torch autograd graph
+                                      # and x3 tensor-core weight gradients (g2048.update; split-fp16, ~1e-5), "x3" = torch autograd graph
                                       # with the x3 GEMM kernels (g2048.linear), "fp32" = autograd + cuBLAS SGEMM (reference
                                       # precision), "tf32" = autograd + cuBLAS TF32
 
